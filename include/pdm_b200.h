@@ -1,0 +1,195 @@
+/*
+ * pdm_b200 -- C ABI of the B200-native empirical-denoiser / thermodynamic-statistics engine.
+ *
+ * This is the drop-in boundary for ONE hot path of antoniibelyshev/physics-of-diffusion-models:
+ * squared distances to all N training points -> min-shifted log-sum-exp partition function ->
+ * posterior energy moments -> softmax-weighted posterior mean.  The reference has no FFI layer for
+ * this path (its boundary is the Python call signature); each entry point below
+ * cites the reference code (file:line, relative to the reference checkout) whose arithmetic it
+ * replaces.  The Python mirror of the reference interface
+ * (physics-of-diffusion-models_b200/utils/{distance,stats,metric_utils}.py,
+ * diffusion/scheduler/scheduler.py) binds these symbols with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain device pointers + int64 sizes, no torch types.  Every pointer is a DEVICE
+ *     pointer unless its name ends in `_host`.  Matrices are row-major; `ld*` are leading dimensions
+ *     in ELEMENTS.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; the caller passes torch's
+ *     current stream) and is asynchronous.  No entry point allocates device memory: scratch and
+ *     outputs are caller-provided (sizes from the *_plan call).
+ *   - Return value: PDM_OK or a negative PDM_ERR_*; pdm_last_error() returns a thread-local message.
+ *     Nothing throws.  There is NO CPU fallback: on a machine without an sm_100 device every compute
+ *     entry point returns PDM_ERR_CUDA / PDM_ERR_UNSUPPORTED.
+ *
+ * Unified math.  For query row b (temperature T_b) and dataset row j:
+ *     E_bj = 1/2 * ((||x_b||^2 - 2 x_b.y_j) + ||y_j||^2)          (reference op order, never clamped)
+ *     m_b  = min_j E_bj,  e_bj = (E_bj - m_b)/T_b,  w_bj = exp(-e_bj)
+ *     l = sum w,  A1 = sum w e,  A2 = sum w e^2,  AUX = sum w s_j,  O = sum w y_j
+ * A partial record holds (m, l, A1, A2, AUX, argmin) for a subset of dataset rows; records combine with
+ * the non-negative shift rule of SURVEY.md section 5 (pdm_merge_partials), which is also how dataset
+ * shards on different GPUs are merged.
+ */
+#ifndef PDM_B200_H
+#define PDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDM_ABI_VERSION 1
+
+#define PDM_OK               0
+#define PDM_ERR_INVALID_ARG (-1)
+#define PDM_ERR_UNSUPPORTED (-2)
+#define PDM_ERR_CUDA        (-3)
+
+/* precision modes of the distance contraction */
+#define PDM_PREC_EXACT_F32  0   /* CUDA-core fp32 FMA (validation variant, small-d path)            */
+#define PDM_PREC_F16X3      1   /* tcgen05 kind::f16, split operands hi*hi + lo*hi + hi*lo, fp32 acc */
+#define PDM_PREC_F16X1      2   /* tcgen05 kind::f16, hi*hi only (11-bit operands; opt-in fast mode) */
+
+/* floats per partial record: m, l, A1, A2, AUX, argmin_lo(bits), argmin_hi(bits), reserved */
+#define PDM_PART_STRIDE 8
+
+/* rows of the output of pdm_merge_partials (struct-of-arrays, each row has M floats) */
+#define PDM_OUT_E_MIN    0   /* m_b                                   utils/stats.py:80,282        */
+#define PDM_OUT_LOG_L    1   /* log sum_j exp(-e_bj)  (= logZ')       utils/stats.py:83,284        */
+#define PDM_OUT_MEAN_E   2   /* <e> = A1/l                            utils/stats.py:87,288        */
+#define PDM_OUT_MEAN_E2  3   /* <e^2> = A2/l                          utils/stats.py:88            */
+#define PDM_OUT_VAR_E    4   /* max(<e^2> - <e>^2, 0)                 utils/stats.py:90            */
+#define PDM_OUT_AUX_MEAN 5   /* sum_j p_j s_j                         utils/stats.py:101           */
+#define PDM_OUT_ENTROPY  6   /* logZ' + <e> - log N                   utils/stats.py:289           */
+#define PDM_OUT_L        7   /* l (the normaliser used by the posterior-mean pass)                 */
+#define PDM_OUT_ROWS     8
+
+typedef void* pdm_stream_t;
+
+const char* pdm_last_error(void);
+int  pdm_abi_version(void);
+/* sm count and compute capability of `device`; PDM_ERR_CUDA when there is no usable device. */
+int  pdm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  row norms.  out[r] = sum_k x[r,k]^2 (accumulated in fp64, rounded once to fp32).
+ * Replaces norm_sqr (utils/distance.py:9-10); dataset norms are computed ONCE and cached by the
+ * caller instead of on every compute_pw_dist_sqr call (utils/distance.py:17-18).
+ * ------------------------------------------------------------------------------------------- */
+int pdm_row_norms_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row preparation: noising, optional rescale, row norm, and the fp16 hi/lo operand split.
+ *   v[r,k] = (noise ? noise[r,k]*sigma[r] + src[r % src_rows, k] : src[r,k]) * (post ? post[r] : 1)
+ * `noise*sigma + src` is evaluated as a rounded multiply followed by a rounded add, the op order of
+ * `torch.randn(...) * t.sqrt() + x0` (utils/stats.py:74, :273).  `post` carries 1/sqrt(alpha_bar) for
+ * the VP form of the ideal denoiser (diffusion/scheduler/scheduler.py:63-64: ||x - a y||^2 =
+ * a^2 ||x/a - y||^2, so the dataset is never rescaled or copied).
+ * Outputs (each optional, NULL = skip):
+ *   x_out[r,k]      fp32 v                                      (ldx)
+ *   norms[r]        ||v_r||^2  (fp64 accumulate)
+ *   hi/lo[r,k]      fp16 split of v*2^kr : hi = rn16(v*2^kr), lo = rn16(v*2^kr - hi); columns
+ *                   d..ldh-1 are zero-filled.  ldh % 8 == 0.
+ *   inv_scale[r]    2^-kr.  kr is chosen per row so that max|v_r|*2^kr is in [2^11, 2^12), unless
+ *                   fixed_scale > 0, in which case 2^kr = fixed_scale for every row.
+ * ------------------------------------------------------------------------------------------- */
+int pdm_prepare_rows(const float* src, int64_t src_rows, int64_t ld_src,
+                     const float* noise, int64_t ld_noise, const float* sigma, const float* post,
+                     int64_t rows, int64_t d, float fixed_scale,
+                     float* x_out, int64_t ldx, float* norms,
+                     uint16_t* hi, uint16_t* lo, int64_t ldh, float* inv_scale,
+                     pdm_stream_t stream);
+
+/* max_k |x[r,k]| over the whole matrix -> out[0] (used once per dataset to pick its global 2^k). */
+int pdm_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream);
+
+/* Transposed fp16 split of the dataset for the posterior-mean contraction:
+ *   yt_hi/yt_lo[k, j] = split(y[j,k]*scale), shape (d, ldt), columns N..ldt-1 zero.  ldt % 8 == 0. */
+int pdm_transpose_split_f16(const float* y, int64_t n, int64_t d, int64_t ld, float scale,
+                            uint16_t* yt_hi, uint16_t* yt_lo, int64_t ldt, pdm_stream_t stream);
+
+/* K11  column moments of the dataset: sum[k] = sum_j y[j,k], sumsq[k] = sum_j y[j,k]^2 (fp64),
+ * minmax[0..1] = global min / max.  Replaces the per-batch torch.var / min / max of
+ * utils/stats.py:39,66,176 (Tr Sigma_0 = sum_k (sumsq_k - sum_k^2/N)/(N-1)). */
+int pdm_column_moments_f32(const float* y, int64_t n, int64_t d, int64_t ld,
+                           double* sum, double* sumsq, float* minmax, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2-K7 fused pass: distances + online min / log-sum-exp / energy moments.  The M x N distance
+ * matrix is never written unless `energy_out` is given.
+ * Replaces, for ALL temperatures of a schedule flattened into the M rows of one launch:
+ *   compute_pw_dist_sqr              utils/distance.py:13-21
+ *   compute_stats_batch inner loop   utils/stats.py:271-289
+ *   compute_metric_stats_batch loop  utils/stats.py:71-101
+ *   true_posterior_mean_x0 weights   diffusion/scheduler/scheduler.py:64-68
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pdm_stats_args {
+    int32_t precision;          /* PDM_PREC_*                                                      */
+    int32_t n_splits;           /* S >= 1: the N range is cut into S interleaved tile sets, each
+                                   emitting its own partial record (0 = auto, see pdm_stats_plan)  */
+    int32_t m_group;            /* tensor path: M tiles scheduled side by side (0 = auto)          */
+    int32_t cta_group;          /* tensor path: 1 or 2 CTAs per MMA (0 = auto = 2)                 */
+    int64_t M, N, d;
+    int64_t index_offset;       /* global dataset index of local row 0 (dataset shards)            */
+    /* fp32 operands (PDM_PREC_EXACT_F32) */
+    const float* q;  int64_t ldq;        /* (M, d) */
+    const float* y;  int64_t ldy;        /* (N, d) */
+    /* fp16 split operands (tensor path), from pdm_prepare_rows */
+    const uint16_t* q_hi; const uint16_t* q_lo; int64_t ldqh;  const float* q_inv_scale;  /* (M) */
+    const uint16_t* y_hi; const uint16_t* y_lo; int64_t ldyh;  float y_inv_scale;
+    /* per-row / per-column scalars */
+    const float* q_norm;        /* (M) ||x||^2                                                     */
+    const float* y_norm;        /* (N) ||y||^2                                                     */
+    const float* inv_temp;      /* (M) 1/T                                                         */
+    const float* y_aux;         /* (N) per-point scalar s_j (utils/stats.py:101) or NULL           */
+    /* outputs */
+    float*   partials;          /* (M, S, PDM_PART_STRIDE)                                         */
+    float*   energy_out;        /* optional (M, lde): energy_mult * E  (2.0 gives the squared
+                                   distance of utils/distance.py:21, 1.0 the energy)               */
+    int64_t  lde;
+    float    energy_mult;
+} pdm_stats_args;
+
+/* Fills args->n_splits / m_group / cta_group when they are 0 and reports the size of `partials`. */
+int pdm_posterior_stats_plan(pdm_stats_args* args, int device, int64_t* partial_floats);
+int pdm_posterior_stats(const pdm_stats_args* args, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Merge of partial records (the only exchange step of the sharded path).
+ * parts is indexed [outer][row][inner][PDM_PART_STRIDE] with strides outer_stride / row_stride /
+ * PDM_PART_STRIDE floats: `inner` = the N splits of one launch, `outer` = dataset shards (GPUs)
+ * after an all-gather.  Writes out[PDM_OUT_ROWS][M] and argmin[M] (int64 global dataset index,
+ * first index on ties like torch.min).  n_total = total dataset size N for the entropy's log N.
+ * ------------------------------------------------------------------------------------------- */
+int pdm_merge_partials(const float* parts, int64_t M, int64_t n_outer, int64_t outer_stride,
+                       int64_t n_inner, int64_t row_stride, const float* inv_temp, int64_t n_total,
+                       float* out, int64_t* argmin, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8 posterior mean  x0_hat_b = sum_j p_bj y_j,  p_bj = exp(-(E_bj - m_b)/T_b)/l_b.
+ * Replaces p = exp(-h/(1-ab)); p /= p.sum; p @ data  (diffusion/scheduler/scheduler.py:66-69).
+ * Step 1 turns a stored energy tile into normalised weights (fp16 hi/lo split, scaled by 2^14, or
+ * fp32); step 2 contracts them with the dataset on tensor cores (f16x3) or CUDA cores (exact).
+ * ------------------------------------------------------------------------------------------- */
+int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t M, int64_t N,
+                            const float* e_min, const float* l, const float* inv_temp,
+                            float* p_f32, int64_t ldp32,
+                            uint16_t* p_hi, uint16_t* p_lo, int64_t ldph, pdm_stream_t stream);
+
+/* out (M, d) [+]= scale * (A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T), A (M, K) and B (d, K) fp16
+ * K-major (lda, ldb multiples of 8).  For the posterior mean A = weights, B = transposed dataset,
+ * K = N, scale = 2^-14 * y_inv_scale.  accumulate != 0 adds into `out`. */
+int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
+                         const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
+                         float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
+                         pdm_stream_t stream);
+
+/* Exact fp32 CUDA-core version: out (M, d) [+]= P (M, N) @ Y (N, d). */
+int pdm_weighted_mean_exact_f32(const float* p, int64_t ldp, int64_t M, int64_t N,
+                                const float* y, int64_t ldy, int64_t d,
+                                float* out, int64_t ldo, int32_t accumulate, pdm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDM_B200_H */

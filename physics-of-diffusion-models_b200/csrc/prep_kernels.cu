@@ -1,0 +1,399 @@
+// HBM-bound preparation kernels: row norms, noising + fp16 hi/lo operand split, dataset transpose,
+// column moments, and the energy -> normalised-weight pass.  All are single-pass, coalesced,
+// 128-bit vectorised where alignment allows.  See include/pdm_b200.h for the reference lines each replaces.
+#include "pdm_common.cuh"
+#include "online_stats.cuh"
+
+namespace pdm {
+
+// ------------------------------------------------------------------------------------------------
+// small reductions
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_reduce(T v, Op op) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* smem /* >= 32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_reduce(v, op);
+    __syncthreads();
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    T r = (threadIdx.x < nwarp) ? smem[threadIdx.x] : identity;
+    if (warp == 0) r = warp_reduce(r, op);
+    if (threadIdx.x == 0) smem[0] = r;
+    __syncthreads();
+    return smem[0];
+}
+
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpMaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpMinF { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// K1 row norms: one warp per row, fp64 accumulation.
+// ------------------------------------------------------------------------------------------------
+template <bool kVec>
+__global__ void __launch_bounds__(256) row_norms_kernel(const float* __restrict__ x, int64_t rows, int64_t d,
+                                                        int64_t ld, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* p = x + row * ld;
+    double acc = 0.0;
+    if (kVec) {
+        const int64_t nv = d >> 2;
+        for (int64_t i = lane; i < nv; i += 32) {
+            const float4 v = ldg_f4(p + 4 * i);
+            acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        }
+    } else {
+        for (int64_t i = lane; i < d; i += 32) { const float v = __ldg(p + i); acc += (double)v * v; }
+    }
+    acc = warp_reduce(acc, OpAddD());
+    if (lane == 0) out[row] = (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row preparation (noising, rescale, norm, fp16 split).  One 256-thread block per row.
+// ------------------------------------------------------------------------------------------------
+struct PrepParams {
+    const float* src; int64_t src_rows; int64_t ld_src;
+    const float* noise; int64_t ld_noise; const float* sigma; const float* post;
+    int64_t rows; int64_t d; float fixed_scale;
+    float* x_out; int64_t ldx; float* norms;
+    __half* hi; __half* lo; int64_t ldh; float* inv_scale;
+};
+
+__device__ __forceinline__ float prep_value(float s, float n, float sig, float post, bool has_noise, bool has_post) {
+    float v = s;
+    if (has_noise) v = __fadd_rn(__fmul_rn(n, sig), s);   // randn * sqrt(t) + x0, two roundings
+    if (has_post) v = __fmul_rn(v, post);
+    return v;
+}
+
+__device__ __forceinline__ void split_f16(float v, __half& h, __half& l) {
+    h = __float2half_rn(v);
+    l = __float2half_rn(v - __half2float(h));
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256) prepare_rows_kernel(PrepParams p) {
+    __shared__ double red_d[32];
+    __shared__ float red_f[32];
+    const int64_t row = blockIdx.x;
+    const bool has_noise = p.noise != nullptr, has_post = p.post != nullptr;
+    const float* s = p.src + (has_noise ? (row % p.src_rows) : row) * p.ld_src;
+    const float* n = has_noise ? p.noise + row * p.ld_noise : nullptr;
+    const float sig = has_noise ? p.sigma[row] : 0.f;
+    const float post = has_post ? p.post[row] : 1.f;
+    float* xo = p.x_out ? p.x_out + row * p.ldx : nullptr;
+
+    double acc = 0.0;
+    float amax = 0.f;
+    if (kVec) {
+        const int64_t nv = p.d >> 2;
+        for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) {
+            const float4 a = ldg_f4(s + 4 * i);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_noise) b = ldg_f4(n + 4 * i);
+            float4 v;
+            v.x = prep_value(a.x, b.x, sig, post, has_noise, has_post);
+            v.y = prep_value(a.y, b.y, sig, post, has_noise, has_post);
+            v.z = prep_value(a.z, b.z, sig, post, has_noise, has_post);
+            v.w = prep_value(a.w, b.w, sig, post, has_noise, has_post);
+            acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            if (xo) *reinterpret_cast<float4*>(xo + 4 * i) = v;
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < p.d; i += blockDim.x) {
+            const float v = prep_value(__ldg(s + i), has_noise ? __ldg(n + i) : 0.f, sig, post, has_noise, has_post);
+            acc += (double)v * v;
+            amax = fmaxf(amax, fabsf(v));
+            if (xo) xo[i] = v;
+        }
+    }
+    if (p.norms) {
+        const double tot = block_reduce(acc, OpAddD(), 0.0, red_d);
+        if (threadIdx.x == 0) p.norms[row] = (float)tot;
+    }
+    if (!p.hi) return;
+
+    float scale = p.fixed_scale;
+    if (!(scale > 0.f)) {
+        amax = block_reduce(amax, OpMaxF(), 0.f, red_f);
+        int e = 0;
+        scale = 1.f;
+        if (amax > 0.f && amax < INFINITY) {
+            frexpf(amax, &e);                       // amax = f * 2^e, f in [0.5, 1)
+            e = max(-100, min(100, 12 - e));
+            scale = ldexpf(1.f, e);                 // amax * scale in [2^11, 2^12)
+        }
+    }
+    if (threadIdx.x == 0 && p.inv_scale) p.inv_scale[row] = 1.f / scale;
+
+    __half* hi = p.hi + row * p.ldh;
+    __half* lo = p.lo + row * p.ldh;
+    if (kVec) {
+        const int64_t nv = p.ldh >> 2, dv = p.d >> 2;   // d % 4 == 0 on this path
+        for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) {
+            __half h[4], l[4];
+            if (i < dv) {
+                const float4 a = ldg_f4(s + 4 * i);
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_noise) b = ldg_f4(n + 4 * i);
+                split_f16(prep_value(a.x, b.x, sig, post, has_noise, has_post) * scale, h[0], l[0]);
+                split_f16(prep_value(a.y, b.y, sig, post, has_noise, has_post) * scale, h[1], l[1]);
+                split_f16(prep_value(a.z, b.z, sig, post, has_noise, has_post) * scale, h[2], l[2]);
+                split_f16(prep_value(a.w, b.w, sig, post, has_noise, has_post) * scale, h[3], l[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { h[k] = __float2half_rn(0.f); l[k] = h[k]; }
+            }
+            *reinterpret_cast<uint2*>(hi + 4 * i) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(lo + 4 * i) = *reinterpret_cast<uint2*>(l);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < p.ldh; i += blockDim.x) {
+            __half h = __float2half_rn(0.f), l = h;
+            if (i < p.d) {
+                const float v = prep_value(__ldg(s + i), has_noise ? __ldg(n + i) : 0.f, sig, post, has_noise, has_post);
+                split_f16(v * scale, h, l);
+            }
+            hi[i] = h; lo[i] = l;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// global abs-max (non-negative floats order like their bit patterns)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t rows, int64_t d, int64_t ld,
+                                                     unsigned* __restrict__ out_bits) {
+    __shared__ float red_f[32];
+    float amax = 0.f;
+    const int64_t total = rows * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d, c = i - r * d;
+        amax = fmaxf(amax, fabsf(__ldg(x + r * ld + c)));
+    }
+    amax = block_reduce(amax, OpMaxF(), 0.f, red_f);
+    if (threadIdx.x == 0) atomicMax(out_bits, __float_as_uint(amax));
+}
+
+// ------------------------------------------------------------------------------------------------
+// transposed fp16 split of the dataset: y (n, d) -> yt_hi/lo (d, ldt)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ y, int64_t n, int64_t d, int64_t ld,
+                                                              float scale, __half* __restrict__ th, __half* __restrict__ tl,
+                                                              int64_t ldt) {
+    __shared__ float tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t j = j0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (j < n && k < d) ? __ldg(y + j * ld + k) * scale : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t k = k0 + r, j = j0 + threadIdx.x;
+        if (k < d && j < ldt) {
+            __half h, l;
+            split_f16(tile[threadIdx.x][r], h, l);
+            th[k * ldt + j] = h;
+            tl[k * ldt + j] = l;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11 column moments (fp64 sums per column, global min/max)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+    int* a = reinterpret_cast<int*>(addr);
+    int old = *a;
+    while (__int_as_float(old) > v) { const int assumed = old; old = atomicCAS(a, assumed, __float_as_int(v)); if (old == assumed) break; }
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+    int* a = reinterpret_cast<int*>(addr);
+    int old = *a;
+    while (__int_as_float(old) < v) { const int assumed = old; old = atomicCAS(a, assumed, __float_as_int(v)); if (old == assumed) break; }
+}
+
+__global__ void moments_init_kernel(double* sum, double* sumsq, int64_t d, float* minmax) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d) { sum[i] = 0.0; sumsq[i] = 0.0; }
+    if (i == 0) { minmax[0] = INFINITY; minmax[1] = -INFINITY; }
+}
+
+// block = (32 columns, 8 row lanes); grid = (ceil(d/32), row slabs)
+__global__ void __launch_bounds__(256) column_moments_kernel(const float* __restrict__ y, int64_t n, int64_t d, int64_t ld,
+                                                             double* __restrict__ sum, double* __restrict__ sumsq,
+                                                             float* __restrict__ minmax) {
+    __shared__ double s1[8][33], s2[8][33];
+    __shared__ float red_f[32];
+    const int64_t k = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t rows_per = ceil_div(n, (int64_t)gridDim.y);
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    double a1 = 0.0, a2 = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    if (k < d) {
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            const float v = __ldg(y + r * ld + k);
+            a1 += v; a2 += (double)v * v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+        }
+    }
+    s1[threadIdx.y][threadIdx.x] = a1; s2[threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < d) {
+        for (int i = 1; i < 8; ++i) { a1 += s1[i][threadIdx.x]; a2 += s2[i][threadIdx.x]; }
+        atomicAdd(sum + k, a1);
+        atomicAdd(sumsq + k, a2);
+    }
+    // flatten thread index for the block-wide min/max
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    mn = warp_reduce(mn, OpMinF()); mx = warp_reduce(mx, OpMaxF());
+    __syncthreads();
+    if (lane == 0) { red_f[warp] = mn; red_f[8 + warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; ++i) { mn = fminf(mn, red_f[i]); mx = fmaxf(mx, red_f[8 + i]); }
+        if (mn < INFINITY) atomic_min_f(minmax, mn);
+        if (mx > -INFINITY) atomic_max_f(minmax + 1, mx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// energy -> normalised weights p = exp(-(E - m)/T) / l   (scheduler.py:66-68)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ energy, int64_t lde, int64_t M, int64_t N,
+                                                      const float* __restrict__ e_min, const float* __restrict__ l,
+                                                      const float* __restrict__ inv_temp,
+                                                      float* __restrict__ p32, int64_t ldp32,
+                                                      __half* __restrict__ ph, __half* __restrict__ pl, int64_t ldph) {
+    const int64_t row = blockIdx.y;
+    const float m = e_min[row], it = inv_temp[row], inv_l = 1.f / l[row];
+    const int64_t width = ph ? ldph : N;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < width; j += (int64_t)gridDim.x * blockDim.x) {
+        float p = 0.f;
+        if (j < N) {
+            const float e = fminf((__ldg(energy + row * lde + j) - m) * it, kMaxE);
+            p = fast_exp2(-e * kLog2e) * inv_l;
+        }
+        if (p32 && j < N) p32[row * ldp32 + j] = p;
+        if (ph) {
+            __half h, lo;
+            split_f16(p * 16384.f, h, lo);
+            ph[row * ldph + j] = h;
+            pl[row * ldph + j] = lo;
+        }
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace pdm
+
+using namespace pdm;
+
+extern "C" int pdm_row_norms_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream) {
+    PDM_REQUIRE(x && out && rows >= 0 && d > 0 && ld >= d, "pdm_row_norms_f32: bad arguments");
+    if (rows == 0) return PDM_OK;
+    const unsigned grid = (unsigned)ceil_div(rows, 8);
+    if (aligned16(x) && d % 4 == 0 && ld % 4 == 0)
+        row_norms_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, rows, d, ld, out);
+    else
+        row_norms_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, rows, d, ld, out);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_prepare_rows(const float* src, int64_t src_rows, int64_t ld_src,
+                                const float* noise, int64_t ld_noise, const float* sigma, const float* post,
+                                int64_t rows, int64_t d, float fixed_scale,
+                                float* x_out, int64_t ldx, float* norms,
+                                uint16_t* hi, uint16_t* lo, int64_t ldh, float* inv_scale,
+                                pdm_stream_t stream) {
+    PDM_REQUIRE(src && rows >= 0 && d > 0 && src_rows > 0 && ld_src >= d, "pdm_prepare_rows: bad source");
+    PDM_REQUIRE(!noise || (sigma && ld_noise >= d), "pdm_prepare_rows: noise needs sigma and ld_noise >= d");
+    PDM_REQUIRE(noise || src_rows >= rows, "pdm_prepare_rows: src_rows < rows without noise");
+    PDM_REQUIRE((hi == nullptr) == (lo == nullptr), "pdm_prepare_rows: hi and lo go together");
+    PDM_REQUIRE(!hi || (ldh >= d && ldh % 8 == 0 && inv_scale), "pdm_prepare_rows: ldh must be >= d, a multiple of 8, and inv_scale given");
+    PDM_REQUIRE(!x_out || ldx >= d, "pdm_prepare_rows: ldx < d");
+    if (rows == 0) return PDM_OK;
+    PrepParams p{src, src_rows, ld_src, noise, ld_noise, sigma, post, rows, d, fixed_scale,
+                 x_out, ldx, norms, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ldh, inv_scale};
+    const bool vec = d % 4 == 0 && ld_src % 4 == 0 && aligned16(src) &&
+                     (!noise || (ld_noise % 4 == 0 && aligned16(noise))) &&
+                     (!x_out || (ldx % 4 == 0 && aligned16(x_out))) &&
+                     (!hi || (aligned16(hi) && aligned16(lo)));
+    if (vec) prepare_rows_kernel<true><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(p);
+    else     prepare_rows_kernel<false><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(p);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream) {
+    PDM_REQUIRE(x && out && rows > 0 && d > 0 && ld >= d, "pdm_absmax_f32: bad arguments");
+    PDM_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float), as_stream(stream)));
+    const int64_t total = rows * d;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256 * 8), 148 * 16);
+    absmax_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, rows, d, ld, reinterpret_cast<unsigned*>(out));
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_transpose_split_f16(const float* y, int64_t n, int64_t d, int64_t ld, float scale,
+                                       uint16_t* yt_hi, uint16_t* yt_lo, int64_t ldt, pdm_stream_t stream) {
+    PDM_REQUIRE(y && yt_hi && yt_lo && n > 0 && d > 0 && ld >= d && ldt >= n && ldt % 8 == 0 && scale > 0.f,
+                "pdm_transpose_split_f16: bad arguments");
+    dim3 grid((unsigned)ceil_div(ldt, 32), (unsigned)ceil_div(d, 32)), block(32, 8);
+    transpose_split_kernel<<<grid, block, 0, as_stream(stream)>>>(y, n, d, ld, scale, reinterpret_cast<__half*>(yt_hi),
+                                                                 reinterpret_cast<__half*>(yt_lo), ldt);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_column_moments_f32(const float* y, int64_t n, int64_t d, int64_t ld,
+                                      double* sum, double* sumsq, float* minmax, pdm_stream_t stream) {
+    PDM_REQUIRE(y && sum && sumsq && minmax && n > 0 && d > 0 && ld >= d, "pdm_column_moments_f32: bad arguments");
+    moments_init_kernel<<<(unsigned)ceil_div(d, 256), 256, 0, as_stream(stream)>>>(sum, sumsq, d, minmax);
+    const int64_t col_blocks = ceil_div(d, 32);
+    const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 64), ceil_div(148 * 8, col_blocks)));
+    dim3 grid((unsigned)col_blocks, (unsigned)slabs), block(32, 8);
+    column_moments_kernel<<<grid, block, 0, as_stream(stream)>>>(y, n, d, ld, sum, sumsq, minmax);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t M, int64_t N,
+                                       const float* e_min, const float* l, const float* inv_temp,
+                                       float* p_f32, int64_t ldp32,
+                                       uint16_t* p_hi, uint16_t* p_lo, int64_t ldph, pdm_stream_t stream) {
+    PDM_REQUIRE(energy && e_min && l && inv_temp && M >= 0 && N > 0 && lde >= N, "pdm_weights_from_energy: bad arguments");
+    PDM_REQUIRE(p_f32 || p_hi, "pdm_weights_from_energy: no output requested");
+    PDM_REQUIRE((p_hi == nullptr) == (p_lo == nullptr), "pdm_weights_from_energy: p_hi and p_lo go together");
+    PDM_REQUIRE(!p_hi || (ldph >= N && ldph % 8 == 0), "pdm_weights_from_energy: ldph must be >= N and a multiple of 8");
+    PDM_REQUIRE(!p_f32 || ldp32 >= N, "pdm_weights_from_energy: ldp32 < N");
+    if (M == 0) return PDM_OK;
+    PDM_REQUIRE(M <= 65535 * 1024LL, "pdm_weights_from_energy: M too large for one launch");
+    const int64_t width = p_hi ? ldph : N;
+    for (int64_t r0 = 0; r0 < M; r0 += 65535) {
+        const int64_t rows = std::min<int64_t>(65535, M - r0);
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div(width, 256), 64), (unsigned)rows);
+        weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+            energy + r0 * lde, lde, rows, N, e_min + r0, l + r0, inv_temp + r0,
+            p_f32 ? p_f32 + r0 * ldp32 : nullptr, ldp32,
+            p_hi ? reinterpret_cast<__half*>(p_hi) + r0 * ldph : nullptr,
+            p_lo ? reinterpret_cast<__half*>(p_lo) + r0 * ldph : nullptr, ldph);
+        PDM_CUDA_CHECK(cudaGetLastError());
+    }
+    return PDM_OK;
+}

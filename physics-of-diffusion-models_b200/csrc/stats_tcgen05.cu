@@ -1,0 +1,497 @@
+// tcgen05 / TMEM / TMA fused pass for sm_100a.
+//
+// One warp-specialised persistent kernel computes S = A.B^T on the 5th-generation tensor cores with the
+// fp16 hi/lo operand split (three kind::f16 MMAs per k-step: hi.hi + lo.hi + hi.lo, fp32 accumulation in
+// TMEM) and consumes each accumulator tile straight from TMEM in one of two epilogues:
+//   EPI_STATS  energies E = 0.5*((|x|^2 - 2 x.y) + |y|^2) -> online min / log-sum-exp / energy moments
+//              per query row (online_stats.cuh); the M x N distance matrix never reaches HBM.
+//              Replaces utils/distance.py:13-21 + utils/stats.py:71-101, 271-289 + scheduler.py:64-68.
+//   EPI_STORE  out = scale * S, the posterior-mean contraction p @ data (scheduler.py:69).
+//
+// Per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only with cta_group::2), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (thread <-> TMEM lane <-> query row).  Pipelines: smem full/empty
+// (TMA <-> MMA, kStages deep) and TMEM full/empty (MMA <-> epilogue, 2 accumulator stages), all mbarriers.
+// With cta_group::2 a CTA pair owns a 256-row x 256-column tile: each CTA loads its 128 A rows and half of
+// the B rows, the leader issues M=256 MMAs, each CTA's epilogue drains its own TMEM half.
+//
+// Schedule: pair p -> (i = p % m_group, s = p / m_group).  Round r handles row super-tile r*m_group + i;
+// within it the pair walks column tiles s, s + n_splits, ...  Pairs that share i re-use the same A tiles
+// out of L2 while pairs that share s stream the same B tiles; partial records per (row, s) are merged by
+// pdm_merge_partials (the same rule that merges dataset shards across GPUs).
+#include "pdm_common.cuh"
+#include "online_stats.cuh"
+#include "sm100_ptx.cuh"
+
+#include <mutex>
+
+namespace pdm {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int kRowsPerCta = 128;
+constexpr int kBlockK = 64;                       // fp16 elements = one 128-byte swizzled row
+constexpr int kTileBytes = kRowsPerCta * kBlockK * 2;
+constexpr int kThreads = 256;
+constexpr int kAccStages = 2;
+constexpr int kEpiWarp0 = 4;
+
+enum { EPI_STATS = 0, EPI_STORE = 1 };
+
+struct GemmParams {
+    int64_t M;            // rows of A (queries)
+    int64_t ncols;        // rows of B (dataset rows for EPI_STATS, feature columns for EPI_STORE)
+    int32_t num_kb;       // number of 64-element k blocks
+    int32_t m_tiles;      // row super-tiles of 128*CG rows
+    int32_t n_tiles;      // column tiles of kBlockN
+    int32_t m_group, n_splits;
+    // EPI_STATS
+    const float* q_norm; const float* q_inv_scale; const float* inv_temp;
+    const float* y_norm; const float* y_aux; float y_inv_scale; int64_t index_offset;
+    float* partials; float* energy_out; int64_t lde; float energy_mult;
+    // EPI_STORE
+    float* out; int64_t ldo; float out_scale; int32_t accumulate;
+};
+
+template <int CG, int TERMS>
+struct Cfg {
+    static constexpr int kBlockN = (CG == 2) ? 256 : 128;
+    static constexpr int kTilesPerStage = (TERMS == 3) ? 4 : 2;
+    static constexpr int kStageBytes = kTilesPerStage * kTileBytes;
+    static constexpr int kStages = (TERMS == 3) ? 3 : 6;
+    static constexpr uint32_t kTmemCols = kAccStages * kBlockN;
+    static constexpr uint32_t kIdesc = make_idesc_f16(128 * CG, kBlockN);
+    static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
+    static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 8 * kNumBars + 16;
+};
+
+template <int CG, int TERMS, int EPI, bool AUX>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  const GemmParams p) {
+    using C = Cfg<CG, TERMS>;
+    constexpr int kBlockN = C::kBlockN;
+    constexpr int kStages = C::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    const uint32_t smem_base = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * C::kStageBytes);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + C::kNumBars);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / CG;
+
+    if (CG == 2) cluster_sync_all();          // both CTAs of the pair are resident before the paired TMEM alloc
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tm_a_hi);
+        prefetch_tensormap(&tm_b_hi);
+        if (TERMS == 3) { prefetch_tensormap(&tm_a_lo); prefetch_tensormap(&tm_b_lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * 128); }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 2) {
+        tmem_alloc<CG>(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
+        tmem_relinquish<CG>();
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const bool active = pair < p.m_group * p.n_splits;
+    const int mi = pair % p.m_group, sp = pair / p.m_group;
+
+    if (active && warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+            const int32_t a_row = (mt * CG + (int)rank) * kRowsPerCta;
+            for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
+                const int32_t b_row = nt * kBlockN + (int)rank * kRowsPerCta;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t dst = smem_base + (uint32_t)stage * C::kStageBytes;
+                    const uint32_t fb = full_bar(stage);
+                    const int32_t kc = kb * kBlockK;
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(fb, C::kStageBytes);
+                        tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
+                        if (TERMS == 3) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
+                        tma_load_2d(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
+                        if (TERMS == 3) tma_load_2d(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(fb, 2u * C::kStageBytes);
+                        else mbar_arrive_remote(fb, 0);
+                        tma_load_2d_pair(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
+                        if (TERMS == 3) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
+                        tma_load_2d_pair(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
+                        if (TERMS == 3) tma_load_2d_pair(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (active && warp == 1 && lane == 0 && leader) {
+        // ===================== MMA issuer =====================
+        int stage = 0; uint32_t phase = 0; uint32_t tile_iter = 0;
+        for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+            for (int nt = sp; nt < p.n_tiles; nt += p.n_splits, ++tile_iter) {
+                const uint32_t as = tile_iter & 1u, aphase = (tile_iter >> 1) & 1u;
+                mbar_wait(tempty_bar(as), aphase ^ 1u);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kBlockN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_base + (uint32_t)stage * C::kStageBytes;
+                    const uint64_t a_hi = make_smem_desc_sw128(sb);
+                    const uint64_t a_lo = make_smem_desc_sw128(sb + kTileBytes);
+                    const uint64_t b_hi = make_smem_desc_sw128(sb + (TERMS == 3 ? 2 : 1) * kTileBytes);
+                    const uint64_t b_lo = make_smem_desc_sw128(sb + 3 * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes = 2 descriptor units
+                        umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        if (TERMS == 3) {
+                            umma_f16<CG>(d_tmem, a_lo + ko, b_hi + ko, C::kIdesc, 1u);
+                            umma_f16<CG>(d_tmem, a_hi + ko, b_lo + ko, C::kIdesc, 1u);
+                        }
+                    }
+                    umma_commit<CG>(empty_bar(stage));                      // smem slot reusable once these retire
+                    if (kb == p.num_kb - 1) umma_commit<CG>(tfull_bar(as)); // accumulator complete
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (active && warp >= kEpiWarp0) {
+        // ===================== epilogue =====================
+        const int quarter = warp - kEpiWarp0;                 // == warp % 4: the TMEM lane quarter this warp may read
+        const int row_in_cta = quarter * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t tile_iter = 0;
+        for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+            const int64_t grow = (int64_t)(mt * CG + (int)rank) * kRowsPerCta + row_in_cta;
+            const bool row_ok = grow < p.M;
+            float xn = 0.f, neg2inv = 0.f, inv_t = 1.f;
+            RowState st;
+            if (EPI == EPI_STATS) {
+                if (row_ok) {
+                    xn = p.q_norm[grow];
+                    neg2inv = -2.f * p.q_inv_scale[grow] * p.y_inv_scale;
+                    inv_t = p.inv_temp[grow];
+                }
+                state_init(st);
+            }
+            for (int nt = sp; nt < p.n_tiles; nt += p.n_splits, ++tile_iter) {
+                const uint32_t as = tile_iter & 1u, aphase = (tile_iter >> 1) & 1u;
+                const int64_t n0 = (int64_t)nt * kBlockN;
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + lane_base + as * kBlockN + c0, v);
+                    tmem_ld_wait();
+                    const int64_t col0 = n0 + c0;
+                    if (col0 >= p.ncols) continue;            // whole chunk beyond the last column
+                    const bool full_chunk = col0 + 32 <= p.ncols;
+                    if (EPI == EPI_STATS) {
+                        float E[32], ax[32];
+                        if (full_chunk) {
+                            const float4* yn4 = reinterpret_cast<const float4*>(p.y_norm + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 y = __ldg(yn4 + i);
+                                E[4 * i + 0] = y.x; E[4 * i + 1] = y.y; E[4 * i + 2] = y.z; E[4 * i + 3] = y.w;
+                            }
+                            if (AUX) {
+                                const float4* ax4 = reinterpret_cast<const float4*>(p.y_aux + col0);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 y = __ldg(ax4 + i);
+                                    ax[4 * i + 0] = y.x; ax[4 * i + 1] = y.y; ax[4 * i + 2] = y.z; ax[4 * i + 3] = y.w;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                E[i] = 0.5f * __fadd_rn(fmaf(__uint_as_float(v[i]), neg2inv, xn), E[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const bool ok = col0 + i < p.ncols;
+                                const float yn = ok ? __ldg(p.y_norm + col0 + i) : 0.f;
+                                if (AUX) ax[i] = ok ? __ldg(p.y_aux + col0 + i) : 0.f;
+                                E[i] = ok ? 0.5f * __fadd_rn(fmaf(__uint_as_float(v[i]), neg2inv, xn), yn) : kBigE;
+                            }
+                        }
+                        if (p.energy_out && row_ok) {
+                            float* eo = p.energy_out + grow * p.lde + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (full_chunk || col0 + i < p.ncols) eo[i] = p.energy_mult * E[i];
+                        }
+                        if (p.partials) state_add_chunk<32, AUX>(st, E, ax, p.index_offset + col0, 1, inv_t);
+                    } else {
+                        if (row_ok) {
+                            float* o = p.out + grow * p.ldo + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                if (full_chunk || col0 + i < p.ncols) {
+                                    const float r = p.out_scale * __uint_as_float(v[i]);
+                                    o[i] = p.accumulate ? o[i] + r : r;
+                                }
+                            }
+                        }
+                    }
+                }
+                // all of this thread's tcgen05.ld for the tile have completed (wait::ld above)
+                tc_fence_before();
+                if (CG == 1 || leader) mbar_arrive(tempty_bar(as));
+                else mbar_arrive_remote(tempty_bar(as), 0);
+            }
+            if (EPI == EPI_STATS && p.partials && row_ok)
+                state_store(st, p.partials + (grow * p.n_splits + sp) * PDM_PART_STRIDE);
+        }
+    }
+
+    __syncwarp();                             // single-lane roles rejoin their warp before the aligned barrier
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc<CG>(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+    static std::mutex mu;
+    static EncodeTiledFn fn = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PDM_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !ptr) {
+            set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+            return PDM_ERR_UNSUPPORTED;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    *out = fn;
+    return PDM_OK;
+}
+
+// fp16 matrix (rows, k) with leading dimension ld -> box of 64 k-elements x 128 rows, 128B swizzle.
+// Reads beyond (rows, k) are zero-filled by the TMA unit, so padding never has to be materialised.
+static int make_tile_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t k, int64_t ld) {
+    EncodeTiledFn fn;
+    int rc = get_encode_fn(&fn);
+    if (rc != PDM_OK) return rc;
+    PDM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0 && ld >= k,
+                "fp16 operand must be 16-byte aligned with ld %% 8 == 0 and ld >= k");
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kRowsPerCta};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PDM_ERR_CUDA; }
+    return PDM_OK;
+}
+
+template <int CG, int TERMS, int EPI, bool AUX>
+static int launch_variant(const CUtensorMap* maps, const GemmParams& p, int sm_count, cudaStream_t stream) {
+    using C = Cfg<CG, TERMS>;
+    auto kern = fused_gemm_kernel<CG, TERMS, EPI, AUX>;
+    PDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    const int pairs = sm_count / CG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pairs * CG));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PDM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], p));
+    return PDM_OK;
+}
+
+template <int EPI, bool AUX>
+static int dispatch(int cg, int terms, const CUtensorMap* maps, const GemmParams& p, int sm_count, cudaStream_t stream) {
+    if (cg == 2 && terms == 3) return launch_variant<2, 3, EPI, AUX>(maps, p, sm_count, stream);
+    if (cg == 1 && terms == 3) return launch_variant<1, 3, EPI, AUX>(maps, p, sm_count, stream);
+    if (cg == 2 && terms == 1) return launch_variant<2, 1, EPI, AUX>(maps, p, sm_count, stream);
+    if (cg == 1 && terms == 1) return launch_variant<1, 1, EPI, AUX>(maps, p, sm_count, stream);
+    set_error("unsupported cta_group %d / terms %d", cg, terms);
+    return PDM_ERR_INVALID_ARG;
+}
+
+static int require_sm100(DeviceInfo* info) {
+    int rc = current_device_info(info);
+    if (rc != PDM_OK) return rc;
+    if (info->cc_major != 10) {
+        set_error("the tensor path needs an sm_100 device (found sm_%d%d); there is no fallback", info->cc_major, info->cc_minor);
+        return PDM_ERR_UNSUPPORTED;
+    }
+    return PDM_OK;
+}
+
+// Pick (m_group, n_splits): use as many CTA pairs as possible while the A tiles that are live at the same
+// time (m_group of them) stay well inside L2, so that they are re-read from L2 rather than HBM.
+void plan_schedule(int pairs, int64_t m_tiles, int64_t n_tiles, int64_t a_tile_bytes, int* m_group, int* n_splits) {
+    const int64_t budget = 40ll << 20;
+    int best_g = 1, best_s = 1;
+    int64_t best_used = 0;
+    for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
+        int64_t g = std::min<int64_t>(pairs / s, m_tiles);
+        g = std::min<int64_t>(g, std::max<int64_t>(1, budget / std::max<int64_t>(1, a_tile_bytes)));
+        if (g < 1) continue;
+        const int64_t used = g * s;
+        if (used > best_used || (used == best_used && g > best_g)) { best_used = used; best_g = (int)g; best_s = s; }
+    }
+    *m_group = best_g;
+    *n_splits = best_s;
+}
+
+int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
+    DeviceInfo info;
+    int rc = require_sm100(&info);
+    if (rc != PDM_OK) return rc;
+    const int cg = a.cta_group;
+    const int terms = a.precision == PDM_PREC_F16X3 ? 3 : 1;
+    PDM_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
+    PDM_REQUIRE(a.q_hi && a.y_hi && a.q_inv_scale && a.y_inv_scale > 0.f, "tensor path: q_hi / y_hi / scales missing");
+    PDM_REQUIRE(terms == 1 || (a.q_lo && a.y_lo), "f16x3 needs the lo operands");
+    PDM_REQUIRE((reinterpret_cast<uintptr_t>(a.y_norm) & 15) == 0 && (!a.y_aux || (reinterpret_cast<uintptr_t>(a.y_aux) & 15) == 0),
+                "y_norm / y_aux must be 16-byte aligned");
+    PDM_REQUIRE(a.M < (1ll << 31) - 512 && a.N < (1ll << 31) - 512, "M and N must fit in int32 for the TMA coordinates");
+    CUtensorMap maps[4];
+    if ((rc = make_tile_map(&maps[0], a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
+    if ((rc = make_tile_map(&maps[1], terms == 3 ? a.q_lo : a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
+    if ((rc = make_tile_map(&maps[2], a.y_hi, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
+    if ((rc = make_tile_map(&maps[3], terms == 3 ? a.y_lo : a.y_hi, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
+    const int block_n = cg == 2 ? 256 : 128;
+    GemmParams p = {};
+    p.M = a.M; p.ncols = a.N;
+    p.num_kb = (int32_t)ceil_div(a.d, kBlockK);
+    p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
+    p.n_tiles = (int32_t)ceil_div(a.N, block_n);
+    p.m_group = a.m_group; p.n_splits = a.n_splits;
+    PDM_REQUIRE(p.m_group >= 1 && p.n_splits >= 1 && (int64_t)p.m_group * p.n_splits <= info.sm_count / cg,
+                "m_group * n_splits must be between 1 and the number of CTA groups (%d)", info.sm_count / cg);
+    p.q_norm = a.q_norm; p.q_inv_scale = a.q_inv_scale; p.inv_temp = a.inv_temp;
+    p.y_norm = a.y_norm; p.y_aux = a.y_aux; p.y_inv_scale = a.y_inv_scale; p.index_offset = a.index_offset;
+    p.partials = a.partials; p.energy_out = a.energy_out; p.lde = a.lde; p.energy_mult = a.energy_mult;
+    if (a.y_aux) return dispatch<EPI_STATS, true>(cg, terms, maps, p, info.sm_count, stream);
+    return dispatch<EPI_STATS, false>(cg, terms, maps, p, info.sm_count, stream);
+}
+
+}  // namespace tc
+
+int launch_exact_stats(const pdm_stats_args& a, cudaStream_t stream);   // stats_exact.cu
+
+}  // namespace pdm
+
+using namespace pdm;
+
+extern "C" int pdm_posterior_stats_plan(pdm_stats_args* a, int device, int64_t* partial_floats) {
+    PDM_REQUIRE(a && a->M >= 0 && a->N > 0 && a->d > 0, "pdm_posterior_stats_plan: bad sizes");
+    int sm = 0, maj = 0, min_ = 0;
+    int rc = pdm_device_info(device, &sm, &maj, &min_);
+    if (rc != PDM_OK) return rc;
+    if (a->precision == PDM_PREC_EXACT_F32) {
+        const int64_t m_tiles = std::max<int64_t>(1, ceil_div(a->M, 128)), n_tiles = ceil_div(a->N, 128);
+        if (a->n_splits <= 0)
+            a->n_splits = (int32_t)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_tiles, 64), ceil_div(4 * sm, m_tiles)));
+        a->m_group = 1;
+        a->cta_group = 1;
+    } else {
+        if (a->cta_group <= 0) a->cta_group = 2;
+        const int cg = a->cta_group;
+        PDM_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
+        const int pairs = sm / cg;
+        const int64_t m_tiles = std::max<int64_t>(1, ceil_div(a->M, 128 * cg)), n_tiles = ceil_div(a->N, cg == 2 ? 256 : 128);
+        const int64_t k_pad = round_up(a->d, 64);
+        const int64_t a_tile_bytes = 128ll * cg * k_pad * 2 * (a->precision == PDM_PREC_F16X3 ? 2 : 1);
+        int g = a->m_group, s = a->n_splits;
+        if (g <= 0 && s <= 0) tc::plan_schedule(pairs, m_tiles, n_tiles, a_tile_bytes, &g, &s);
+        else if (g <= 0) g = (int)std::max<int64_t>(1, std::min<int64_t>(pairs / s, m_tiles));
+        else if (s <= 0) s = (int)std::max<int64_t>(1, std::min<int64_t>(pairs / g, n_tiles));
+        a->m_group = g; a->n_splits = s;
+    }
+    if (partial_floats) *partial_floats = a->M * a->n_splits * PDM_PART_STRIDE;
+    return PDM_OK;
+}
+
+extern "C" int pdm_posterior_stats(const pdm_stats_args* a, pdm_stream_t stream) {
+    PDM_REQUIRE(a, "pdm_posterior_stats: null args");
+    PDM_REQUIRE(a->M >= 0 && a->N > 0 && a->d > 0, "pdm_posterior_stats: bad sizes");
+    PDM_REQUIRE(a->q_norm && a->y_norm, "pdm_posterior_stats: q_norm / y_norm missing");
+    PDM_REQUIRE(a->partials || a->energy_out, "pdm_posterior_stats: no output requested");
+    PDM_REQUIRE(!a->partials || a->inv_temp, "pdm_posterior_stats: inv_temp missing");
+    PDM_REQUIRE(!a->energy_out || a->lde >= a->N, "pdm_posterior_stats: lde < N");
+    PDM_REQUIRE(a->n_splits >= 1, "pdm_posterior_stats: n_splits must be planned (>= 1)");
+    if (a->M == 0) return PDM_OK;
+    switch (a->precision) {
+        case PDM_PREC_EXACT_F32: return launch_exact_stats(*a, as_stream(stream));
+        case PDM_PREC_F16X3:
+        case PDM_PREC_F16X1: return tc::launch_tensor_stats(*a, as_stream(stream));
+        default: set_error("unknown precision %d", a->precision); return PDM_ERR_INVALID_ARG;
+    }
+}
+
+extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
+                                    const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
+                                    float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
+                                    pdm_stream_t stream) {
+    PDM_REQUIRE(a_hi && a_lo && b_hi && b_lo && out && M >= 0 && d > 0 && K > 0 && ldo >= d, "pdm_split_gemm_f16x3: bad arguments");
+    if (M == 0) return PDM_OK;
+    DeviceInfo info;
+    int rc = tc::require_sm100(&info);
+    if (rc != PDM_OK) return rc;
+    const int cg = cta_group <= 0 ? 2 : cta_group;
+    PDM_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
+    PDM_REQUIRE(M < (1ll << 31) - 512 && d < (1ll << 31) - 512, "M and d must fit in int32");
+    CUtensorMap maps[4];
+    if ((rc = tc::make_tile_map(&maps[0], a_hi, M, K, lda)) != PDM_OK) return rc;
+    if ((rc = tc::make_tile_map(&maps[1], a_lo, M, K, lda)) != PDM_OK) return rc;
+    if ((rc = tc::make_tile_map(&maps[2], b_hi, d, K, ldb)) != PDM_OK) return rc;
+    if ((rc = tc::make_tile_map(&maps[3], b_lo, d, K, ldb)) != PDM_OK) return rc;
+    const int block_n = cg == 2 ? 256 : 128;
+    tc::GemmParams p = {};
+    p.M = M; p.ncols = d;
+    p.num_kb = (int32_t)ceil_div(K, tc::kBlockK);
+    p.m_tiles = (int32_t)ceil_div(M, (int64_t)tc::kRowsPerCta * cg);
+    p.n_tiles = (int32_t)ceil_div(d, block_n);
+    // every (row tile, column tile) is an independent output tile: spread column tiles first
+    const int pairs = info.sm_count / cg;
+    p.n_splits = (int32_t)std::min<int64_t>(p.n_tiles, pairs);
+    p.m_group = (int32_t)std::max<int64_t>(1, std::min<int64_t>(pairs / p.n_splits, p.m_tiles));
+    p.out = out; p.ldo = ldo; p.out_scale = scale; p.accumulate = accumulate;
+    return tc::dispatch<tc::EPI_STORE, false>(cg, 3, maps, p, info.sm_count, as_stream(stream));
+}

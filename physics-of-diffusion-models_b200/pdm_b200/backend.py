@@ -1,0 +1,210 @@
+"""Tensor-level wrapper over the C ABI: torch owns the device memory and the stream, the library does
+the arithmetic.  One method per entry point of include/pdm_b200.h; no computation happens in torch here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import PdmError, StatsArgs, check
+
+PRECISIONS = {"exact": _cabi.PREC_EXACT_F32, "f16x3": _cabi.PREC_F16X3, "f16x1": _cabi.PREC_F16X1}
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class CudaBackend:
+    """Dispatches into libpdm_b200.so.  Raises PdmError if the library or a CUDA device is missing."""
+
+    name = "cuda"
+
+    def __init__(self, device: Optional[torch.device] = None):
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise PdmError("pdm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.pdm_device_info(self.device.index or 0, C.byref(sm), C.byref(major), C.byref(minor)),
+              "pdm_device_info")
+        self.sm_count, self.cc = sm.value, (major.value, minor.value)
+        self.launches = 0          # kernels of ours launched through this backend (bench reports it)
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _f32(self, t: Tensor) -> Tensor:
+        if t.device != self.device or t.dtype != torch.float32 or t.stride(-1) != 1:
+            raise PdmError(f"expected a contiguous-row float32 tensor on {self.device}, got {t.dtype} on {t.device}")
+        return t
+
+    def supports_tensor_path(self) -> bool:
+        return self.cc[0] == 10
+
+    # ---- K1 ------------------------------------------------------------------------------------
+    def row_norms(self, x: Tensor) -> Tensor:
+        x = self._f32(x)
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_row_norms_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
+                                         self._stream()), "pdm_row_norms_f32")
+        self.launches += 1
+        return out
+
+    def absmax(self, x: Tensor) -> Tensor:
+        x = self._f32(x)
+        out = torch.empty(1, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_absmax_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
+                                      self._stream()), "pdm_absmax_f32")
+        self.launches += 1
+        return out
+
+    # ---- row preparation -----------------------------------------------------------------------
+    def prepare_rows(self, src: Tensor, rows: int, *, noise: Optional[Tensor] = None, sigma: Optional[Tensor] = None,
+                     post: Optional[Tensor] = None, fixed_scale: float = 0.0, want_x: bool = False,
+                     want_norms: bool = True, want_split: bool = True) -> dict:
+        src = self._f32(src)
+        d = src.shape[1]
+        if noise is not None:
+            noise, sigma = self._f32(noise), self._f32(sigma)
+        out = {"x": None, "norms": None, "hi": None, "lo": None, "inv_scale": None}
+        if want_x:
+            out["x"] = torch.empty(rows, d, dtype=torch.float32, device=self.device)
+        if want_norms:
+            out["norms"] = torch.empty(rows, dtype=torch.float32, device=self.device)
+        ldh = _round_up(d, 8)
+        if want_split:
+            out["hi"] = torch.empty(rows, ldh, dtype=torch.float16, device=self.device)
+            out["lo"] = torch.empty(rows, ldh, dtype=torch.float16, device=self.device)
+            out["inv_scale"] = torch.empty(rows, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_prepare_rows(
+            src.data_ptr(), src.shape[0], src.stride(0),
+            _ptr(noise), noise.stride(0) if noise is not None else 0, _ptr(sigma), _ptr(post),
+            rows, d, float(fixed_scale),
+            _ptr(out["x"]), d, _ptr(out["norms"]),
+            _ptr(out["hi"]), _ptr(out["lo"]), ldh, _ptr(out["inv_scale"]), self._stream()), "pdm_prepare_rows")
+        self.launches += 1
+        return out
+
+    def transpose_split(self, y: Tensor, scale: float):
+        y = self._f32(y)
+        n, d = y.shape
+        ldt = _round_up(n, 8)
+        hi = torch.empty(d, ldt, dtype=torch.float16, device=self.device)
+        lo = torch.empty(d, ldt, dtype=torch.float16, device=self.device)
+        check(self.lib.pdm_transpose_split_f16(y.data_ptr(), n, d, y.stride(0), float(scale), hi.data_ptr(),
+                                               lo.data_ptr(), ldt, self._stream()), "pdm_transpose_split_f16")
+        self.launches += 1
+        return hi, lo
+
+    def column_moments(self, y: Tensor):
+        y = self._f32(y)
+        n, d = y.shape
+        s = torch.empty(d, dtype=torch.float64, device=self.device)
+        s2 = torch.empty(d, dtype=torch.float64, device=self.device)
+        mm = torch.empty(2, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_column_moments_f32(y.data_ptr(), n, d, y.stride(0), s.data_ptr(), s2.data_ptr(),
+                                              mm.data_ptr(), self._stream()), "pdm_column_moments_f32")
+        self.launches += 2
+        return s, s2, mm
+
+    # ---- fused pass ----------------------------------------------------------------------------
+    def posterior_stats(self, *, precision: str, M: int, N: int, d: int, q_norm: Tensor, y_norm: Tensor,
+                        inv_temp: Optional[Tensor], q: Optional[Tensor] = None, y: Optional[Tensor] = None,
+                        q_split=None, y_split=None, y_inv_scale: float = 1.0, y_aux: Optional[Tensor] = None,
+                        index_offset: int = 0, n_splits: int = 0, m_group: int = 0, cta_group: int = 0,
+                        want_partials: bool = True, energy_out: Optional[Tensor] = None,
+                        energy_mult: float = 1.0) -> Optional[Tensor]:
+        a = StatsArgs()
+        a.precision = PRECISIONS[precision]
+        a.n_splits, a.m_group, a.cta_group = n_splits, m_group, cta_group
+        a.M, a.N, a.d, a.index_offset = M, N, d, index_offset
+        keep = [q_norm, y_norm, inv_temp, y_aux, q, y, q_split, y_split, energy_out]
+        if precision == "exact":
+            q, y = self._f32(q), self._f32(y)
+            a.q, a.ldq, a.y, a.ldy = q.data_ptr(), q.stride(0), y.data_ptr(), y.stride(0)
+        else:
+            q_hi, q_lo, q_inv = q_split
+            y_hi, y_lo = y_split
+            a.q_hi, a.q_lo, a.ldqh, a.q_inv_scale = q_hi.data_ptr(), _ptr(q_lo), q_hi.stride(0), q_inv.data_ptr()
+            a.y_hi, a.y_lo, a.ldyh, a.y_inv_scale = y_hi.data_ptr(), _ptr(y_lo), y_hi.stride(0), float(y_inv_scale)
+        a.q_norm, a.y_norm, a.inv_temp, a.y_aux = q_norm.data_ptr(), y_norm.data_ptr(), _ptr(inv_temp), _ptr(y_aux)
+        nfloats = C.c_int64()
+        check(self.lib.pdm_posterior_stats_plan(C.byref(a), self.device.index or 0, C.byref(nfloats)),
+              "pdm_posterior_stats_plan")
+        partials = None
+        if want_partials:
+            partials = torch.empty(M, a.n_splits, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
+            a.partials = partials.data_ptr()
+        if energy_out is not None:
+            a.energy_out, a.lde, a.energy_mult = energy_out.data_ptr(), energy_out.stride(0), float(energy_mult)
+        check(self.lib.pdm_posterior_stats(C.byref(a), self._stream()), "pdm_posterior_stats")
+        self.launches += 1
+        self.last_plan = (a.n_splits, a.m_group, a.cta_group)
+        del keep
+        return partials
+
+    def merge(self, parts: Tensor, inv_temp: Tensor, n_total: int):
+        """parts: (M, S, 8) or (G, M, S, 8) contiguous."""
+        if parts.dim() == 3:
+            parts = parts.unsqueeze(0)
+        parts = parts.contiguous()
+        g, m, s, _ = parts.shape
+        out = torch.empty(_cabi.OUT_ROWS, m, dtype=torch.float32, device=self.device)
+        argmin = torch.empty(m, dtype=torch.int64, device=self.device)
+        check(self.lib.pdm_merge_partials(parts.data_ptr(), m, g, parts.stride(0), s, parts.stride(1),
+                                          inv_temp.data_ptr(), n_total, out.data_ptr(), argmin.data_ptr(),
+                                          self._stream()), "pdm_merge_partials")
+        self.launches += 1
+        return out, argmin
+
+    # ---- posterior mean ------------------------------------------------------------------------
+    def weights_from_energy(self, energy: Tensor, e_min: Tensor, l: Tensor, inv_temp: Tensor, *, split: bool):
+        m, n = energy.shape
+        if split:
+            ld = _round_up(n, 8)
+            hi = torch.empty(m, ld, dtype=torch.float16, device=self.device)
+            lo = torch.empty(m, ld, dtype=torch.float16, device=self.device)
+            check(self.lib.pdm_weights_from_energy(energy.data_ptr(), energy.stride(0), m, n, e_min.data_ptr(),
+                                                   l.data_ptr(), inv_temp.data_ptr(), None, 0, hi.data_ptr(),
+                                                   lo.data_ptr(), ld, self._stream()), "pdm_weights_from_energy")
+            self.launches += 1
+            return hi, lo
+        p = torch.empty(m, n, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_weights_from_energy(energy.data_ptr(), energy.stride(0), m, n, e_min.data_ptr(),
+                                               l.data_ptr(), inv_temp.data_ptr(), p.data_ptr(), n, None, None, 0,
+                                               self._stream()), "pdm_weights_from_energy")
+        self.launches += 1
+        return p
+
+    def split_gemm(self, a_hi: Tensor, a_lo: Tensor, b_hi: Tensor, b_lo: Tensor, k: int, scale: float,
+                   out: Optional[Tensor] = None, accumulate: bool = False, cta_group: int = 0) -> Tensor:
+        m, d = a_hi.shape[0], b_hi.shape[0]
+        if out is None:
+            out = torch.empty(m, d, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_split_gemm_f16x3(a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), m, b_hi.data_ptr(),
+                                            b_lo.data_ptr(), b_hi.stride(0), d, k, float(scale), out.data_ptr(),
+                                            out.stride(0), int(accumulate), cta_group, self._stream()),
+              "pdm_split_gemm_f16x3")
+        self.launches += 1
+        return out
+
+    def weighted_mean_exact(self, p: Tensor, y: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+        m, n = p.shape
+        d = y.shape[1]
+        if out is None:
+            out = torch.empty(m, d, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_weighted_mean_exact_f32(p.data_ptr(), p.stride(0), m, n, y.data_ptr(), y.stride(0), d,
+                                                   out.data_ptr(), out.stride(0), int(accumulate), self._stream()),
+              "pdm_weighted_mean_exact_f32")
+        self.launches += 1
+        return out

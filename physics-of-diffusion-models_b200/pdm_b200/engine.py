@@ -1,0 +1,287 @@
+"""Host-side orchestration of the empirical-denoiser hot path.
+
+``EmpiricalDataset`` keeps one shard of the training set resident in HBM together with everything that
+is computed once per dataset (row norms, the global power-of-two scale, the fp16 hi/lo operand split, the
+transposed split for the posterior-mean contraction, Tr Sigma_0).  ``PosteriorEngine`` runs the fused
+pass for a block of query rows -- all temperatures of a schedule are flattened into the rows of one
+launch -- merges the per-split / per-shard partial records and finalises the quantities the reference
+reports.  Every numerical step happens in the CUDA library (``backend``); torch provides memory, streams,
+the RNG stream of the reference (``torch.randn`` per temperature) and ``torch.distributed`` plumbing.
+
+Reference call sites this replaces: utils/stats.py:71-111, 271-290 (per-temperature loops),
+diffusion/scheduler/scheduler.py:60-69 (ideal denoiser), utils/distance.py:13-21.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import PdmError
+
+STAT_KEYS = ("e_min", "log_l", "mean_e", "mean_e2", "var_e", "aux_mean", "entropy", "l")
+
+
+def default_backend():
+    from .backend import CudaBackend
+    return CudaBackend()
+
+
+def _env_int(name: str, default: int = 0) -> int:
+    v = os.environ.get(name)
+    return int(v) if v else default
+
+
+def pow2_scale_for(absmax: float) -> float:
+    """2^k with absmax * 2^k in [2^11, 2^12): the fp16 hi part keeps 11 bits, hi+lo 22 bits."""
+    if not (absmax > 0.0) or math.isinf(absmax) or math.isnan(absmax):
+        return 1.0
+    _, e = math.frexp(absmax)           # absmax = f * 2^e, f in [0.5, 1)
+    return math.ldexp(1.0, max(-100, min(100, 12 - e)))
+
+
+class EmpiricalDataset:
+    """A (shard of a) training set resident on one GPU."""
+
+    def __init__(self, data: Tensor, *, backend=None, index_offset: int = 0, n_total: Optional[int] = None,
+                 global_absmax: Optional[float] = None):
+        self.backend = backend if backend is not None else default_backend()
+        dev = self.backend.device
+        flat = data.reshape(data.shape[0], -1)
+        self.y = flat.to(device=dev, dtype=torch.float32).contiguous()
+        self.item_shape = tuple(data.shape[1:])
+        self.n, self.d = self.y.shape
+        self.index_offset = int(index_offset)
+        self.n_total = int(n_total) if n_total is not None else self.n
+        self.y_norm = self.backend.row_norms(self.y)
+        self._global_absmax = global_absmax
+        self._split = None
+        self._tsplit = None
+        self._moments = None
+        self._scale = None
+
+    # -- lazily built device-side views ----------------------------------------------------------
+    @property
+    def scale(self) -> float:
+        if self._scale is None:
+            amax = self._global_absmax
+            if amax is None:
+                amax = float(self.backend.absmax(self.y).item())
+            self._scale = pow2_scale_for(amax)
+        return self._scale
+
+    def split(self):
+        """(y_hi, y_lo) fp16 operands of y * scale, shape (n, round_up(d, 8))."""
+        if self._split is None:
+            r = self.backend.prepare_rows(self.y, self.n, fixed_scale=self.scale, want_norms=False)
+            self._split = (r["hi"], r["lo"])
+        return self._split
+
+    def transposed_split(self):
+        if self._tsplit is None:
+            self._tsplit = self.backend.transpose_split(self.y, self.scale)
+        return self._tsplit
+
+    def moments(self):
+        """(column sums, column sums of squares, [min, max]) -- fp64 / fp32 device tensors."""
+        if self._moments is None:
+            self._moments = self.backend.column_moments(self.y)
+        return self._moments
+
+    def tr_sigma0(self) -> float:
+        """sum_k Var_k (unbiased), torch.var(x, dim=0).sum() of utils/stats.py:39,176 (single-shard form)."""
+        s, s2, _ = self.moments()
+        n = float(self.n)
+        return float(((s2 - s * s / n) / (n - 1.0)).sum().item())
+
+    def value_range(self):
+        mm = self.moments()[2]
+        return float(mm[0].item()), float(mm[1].item())
+
+
+@dataclass
+class EngineConfig:
+    precision: str = "auto"            # auto | exact | f16x3 | f16x1
+    tensor_min_dim: int = 256          # auto: below this the exact CUDA-core kernel is used
+    cta_group: int = 0                 # 0 = library default (2)
+    m_group: int = 0
+    n_splits: int = 0
+    max_query_bytes: int = 2 << 30     # scratch budget for one block of query rows (noise + split)
+    max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
+
+    @staticmethod
+    def from_env() -> "EngineConfig":
+        return EngineConfig(precision=os.environ.get("PDM_PRECISION", "auto"),
+                            cta_group=_env_int("PDM_CTA_GROUP"), m_group=_env_int("PDM_M_GROUP"),
+                            n_splits=_env_int("PDM_N_SPLITS"))
+
+
+class PosteriorEngine:
+    """Fused posterior statistics / posterior mean of query rows against one dataset shard.
+
+    ``group``: optional torch.distributed process group over which the dataset is row-sharded; every rank
+    must present the same query rows, partial records are all-gathered and merged.
+    """
+
+    def __init__(self, dataset: EmpiricalDataset, config: Optional[EngineConfig] = None, group=None):
+        self.ds = dataset
+        self.backend = dataset.backend
+        self.cfg = config if config is not None else EngineConfig.from_env()
+        self.group = group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
+
+    # -- precision -------------------------------------------------------------------------------
+    def precision(self) -> str:
+        p = self.cfg.precision
+        if p == "auto":
+            tensor_ok = getattr(self.backend, "supports_tensor_path", lambda: False)()
+            return "f16x3" if (self.ds.d >= self.cfg.tensor_min_dim and tensor_ok) else "exact"
+        if p not in ("exact", "f16x3", "f16x1"):
+            raise PdmError(f"unknown precision {p!r}")
+        return p
+
+    def rows_per_block(self, row_multiple: int = 1) -> int:
+        per_row = self.ds.d * 4 * 3
+        rows = max(1, self.cfg.max_query_bytes // per_row)
+        return max(row_multiple, rows // row_multiple * row_multiple)
+
+    # -- core: one block of query rows -----------------------------------------------------------
+    def _prepare(self, src: Tensor, rows: int, noise, sigma, post, precision: str, want_x: bool):
+        tensor = precision != "exact"
+        return self.backend.prepare_rows(src, rows, noise=noise, sigma=sigma, post=post,
+                                         want_x=(want_x or not tensor), want_norms=True, want_split=tensor)
+
+    def _local_partials(self, prep: dict, rows: int, inv_temp: Tensor, aux: Optional[Tensor], precision: str,
+                        energy_out: Optional[Tensor] = None, energy_mult: float = 1.0, want_partials: bool = True):
+        ds = self.ds
+        kw = dict(precision=precision, M=rows, N=ds.n, d=ds.d, q_norm=prep["norms"], y_norm=ds.y_norm,
+                  inv_temp=inv_temp, y_aux=aux, index_offset=ds.index_offset, n_splits=self.cfg.n_splits,
+                  m_group=self.cfg.m_group, cta_group=self.cfg.cta_group, want_partials=want_partials,
+                  energy_out=energy_out, energy_mult=energy_mult)
+        if precision == "exact":
+            return self.backend.posterior_stats(q=prep["x"], y=ds.y, **kw)
+        return self.backend.posterior_stats(q_split=(prep["hi"], prep["lo"], prep["inv_scale"]), y_split=ds.split(),
+                                            y_inv_scale=1.0 / ds.scale, **kw)
+
+    def _merge(self, parts: Tensor, inv_temp: Tensor):
+        if self.world > 1:
+            import torch.distributed as dist
+            gathered = torch.empty((self.world,) + tuple(parts.shape), dtype=parts.dtype, device=parts.device)
+            dist.all_gather_into_tensor(gathered, parts.contiguous(), group=self.group)
+            parts = gathered
+        return self.backend.merge(parts, inv_temp, self.ds.n_total)
+
+    def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
+                    sigma: Optional[Tensor] = None, post: Optional[Tensor] = None, aux: Optional[Tensor] = None):
+        """Statistics for ``rows`` query rows; returns (out (8, rows), argmin (rows,)) device tensors.
+        Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional)."""
+        precision = self.precision()
+        inv_temp = (1.0 / temp_rows.to(torch.float32)).contiguous()
+        prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
+        parts = self._local_partials(prep, rows, inv_temp, aux, precision)
+        return self._merge(parts, inv_temp)
+
+    def stats(self, x: Tensor, temp_rows: Tensor, aux: Optional[Tensor] = None) -> dict:
+        """Per-row Boltzmann statistics of explicit queries x (M, ...) at per-row temperatures."""
+        dev = self.backend.device
+        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(xf.shape[0]).contiguous()
+        outs, idxs = [], []
+        step = self.rows_per_block()
+        for r0 in range(0, xf.shape[0], step):
+            r1 = min(xf.shape[0], r0 + step)
+            o, i = self.stats_block(xf[r0:r1], r1 - r0, temp_rows[r0:r1], aux=aux)
+            outs.append(o)
+            idxs.append(i)
+        out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
+        res = {k: out[j] for j, k in enumerate(STAT_KEYS)}
+        res["argmin"] = torch.cat(idxs) if len(idxs) > 1 else idxs[0]
+        return res
+
+    def noised_stats(self, x0: Tensor, temp: Tensor, aux: Optional[Tensor] = None, noise_fn=None) -> dict:
+        """Statistics of xt = randn * sqrt(T_i) + x0 for every temperature of ``temp``.
+
+        The noise is drawn with one ``torch.randn(*x0.shape, device=...)`` per temperature in schedule
+        order -- the reference's RNG stream (utils/stats.py:74, :273).  Returns tensors of shape (n_T, B)."""
+        dev = self.backend.device
+        b = x0.shape[0]
+        x0f = x0.reshape(b, -1).to(device=dev, dtype=torch.float32).contiguous()
+        temp = temp.to(device=dev, dtype=torch.float32).reshape(-1)
+        n_t = temp.shape[0]
+        t_per_block = max(1, self.rows_per_block() // b)
+        outs, idxs = [], []
+        draw = noise_fn if noise_fn is not None else (lambda i: torch.randn(*x0.shape, device=dev))
+        for t0 in range(0, n_t, t_per_block):
+            t1 = min(n_t, t0 + t_per_block)
+            nb = t1 - t0
+            noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
+            for i in range(nb):
+                noise[i].copy_(draw(t0 + i).reshape(b, -1))
+            if self.world > 1 and noise_fn is None:
+                import torch.distributed as dist
+                dist.broadcast(noise, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                               group=self.group)
+            t_rows = temp[t0:t1].repeat_interleave(b)
+            o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux)
+            outs.append(o)
+            idxs.append(i)
+        out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
+        res = {k: out[j].view(n_t, b) for j, k in enumerate(STAT_KEYS)}
+        res["argmin"] = (torch.cat(idxs) if len(idxs) > 1 else idxs[0]).view(n_t, b)
+        return res
+
+    # -- posterior mean ---------------------------------------------------------------------------
+    def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None) -> Tensor:
+        """x0_hat[r] = sum_j p_rj y_j with p ~ exp(-||x_r*post_r - y_j||^2 / (2 T_r)).  Returns (M, d)."""
+        dev = self.backend.device
+        ds = self.ds
+        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        m = xf.shape[0]
+        temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
+        if post is not None:
+            post = post.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
+        precision = self.precision()
+        tensor = precision != "exact"
+        out = torch.empty(m, ds.d, dtype=torch.float32, device=dev)
+        step = max(128, min(m, self.cfg.max_energy_bytes // (ds.n * 8)))
+        for r0 in range(0, m, step):
+            r1 = min(m, r0 + step)
+            rows = r1 - r0
+            inv_temp = (1.0 / temp_rows[r0:r1]).contiguous()
+            prep = self._prepare(xf[r0:r1], rows, None, None, None if post is None else post[r0:r1], precision, False)
+            energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
+            parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)
+            st, _ = self._merge(parts, inv_temp)
+            e_min, l = st[_cabi.OUT_E_MIN], st[_cabi.OUT_L]
+            if tensor:
+                p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
+                yt_hi, yt_lo = ds.transposed_split()
+                self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / ds.scale, out=out[r0:r1],
+                                        cta_group=self.cfg.cta_group)
+            else:
+                p = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=False)
+                self.backend.weighted_mean_exact(p, ds.y, out=out[r0:r1])
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out, group=self.group)
+        return out
+
+    # -- dense distances (callers of compute_pw_dist_sqr index / min / scatter the matrix) -----------
+    def pairwise_sqdist(self, x: Tensor) -> Tensor:
+        """Dense (M, N) squared distances ||x_b - y_j||^2 in the reference's op order (utils/distance.py:21)."""
+        dev = self.backend.device
+        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        m = xf.shape[0]
+        precision = self.precision()
+        out = torch.empty(m, self.ds.n, dtype=torch.float32, device=dev)
+        prep = self._prepare(xf, m, None, None, None, precision, False)
+        self._local_partials(prep, m, None, None, precision, energy_out=out, energy_mult=2.0, want_partials=False)
+        return out

@@ -1,0 +1,242 @@
+"""GPU parity tests of the CUDA kernels behind the C ABI, against the CPU oracle (fp32 restatement of the
+reference, with its fp64 re-evaluation as arbiter).  Run on the B200 box:  pytest -m gpu
+
+Tolerance contract (BASELINE.json north_star): min-shifted log l, <e>, <e^2>, Var,
+entropy, posterior mean and E_min within 1e-4 relative of the reference on identical inputs, where the
+fp64 oracle arbitrates when the reference's own fp32 cancellation noise is larger:
+    |ours - ref64| <= max(rtol*|ref64| + atol, 2*|ref32 - ref64|);  arg-min indices bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import posterior as orc
+from oracle import synthetic as syn
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def backend(cuda_device):
+    from pdm_b200.backend import CudaBackend
+    return CudaBackend(cuda_device)
+
+
+def arbitrated_close(ours, ref32, ref64, rtol=RTOL, atol=1e-6, what=""):
+    ours = ours.detach().double().cpu()
+    ref32 = ref32.detach().double().cpu()
+    ref64 = ref64.detach().double().cpu()
+    tol = torch.maximum(rtol * ref64.abs() + atol, 2 * (ref32 - ref64).abs())
+    err = (ours - ref64).abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.numel()} outside tolerance; worst err "
+                           f"{err[bad].max().item():.3e} vs tol {tol[bad][err[bad].argmax()].item():.3e}")
+
+
+def oracle_rows(xq, data, temp_rows, aux=None):
+    """fp32 and fp64 oracle statistics for explicit query rows with per-row temperatures."""
+    res = {}
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        e = 0.5 * orc.pairwise_sqdist(xq.to(dt), data.to(dt))
+        st = orc.boltzmann_rows(e, temp_rows.to(dt)[:, None], aux=None if aux is None else aux.to(dt))
+        st["entropy"] = st["log_l"] + st["mean_e"] - math.log(len(data))
+        res[name] = st
+    return res
+
+
+def run_stats(backend, xq, data, temp_rows, precision, aux=None, cta_group=0, n_splits=0, m_group=0):
+    dev = backend.device
+    y = data.reshape(len(data), -1).float().to(dev).contiguous()
+    x = xq.reshape(len(xq), -1).float().to(dev).contiguous()
+    inv_t = (1.0 / temp_rows.float()).to(dev).contiguous()
+    y_norm = backend.row_norms(y)
+    auxd = None if aux is None else aux.float().to(dev).contiguous()
+    if precision == "exact":
+        prep = backend.prepare_rows(x, len(x), want_x=True, want_split=False)
+        parts = backend.posterior_stats(precision="exact", M=len(x), N=len(y), d=y.shape[1], q_norm=prep["norms"],
+                                        y_norm=y_norm, inv_temp=inv_t, q=prep["x"], y=y, y_aux=auxd, n_splits=n_splits)
+    else:
+        from pdm_b200.engine import pow2_scale_for
+        scale = pow2_scale_for(float(backend.absmax(y).item()))
+        ys = backend.prepare_rows(y, len(y), fixed_scale=scale, want_norms=False)
+        prep = backend.prepare_rows(x, len(x))
+        parts = backend.posterior_stats(precision=precision, M=len(x), N=len(y), d=y.shape[1], q_norm=prep["norms"],
+                                        y_norm=y_norm, inv_temp=inv_t, q_split=(prep["hi"], prep["lo"], prep["inv_scale"]),
+                                        y_split=(ys["hi"], ys["lo"]), y_inv_scale=1.0 / scale, y_aux=auxd,
+                                        cta_group=cta_group, n_splits=n_splits, m_group=m_group)
+    out, argmin = backend.merge(parts, inv_t, len(y))
+    torch.cuda.synchronize()
+    return out.cpu(), argmin.cpu()
+
+
+def check_stats(out, argmin, ref, aux=False, what=""):
+    from pdm_b200 import _cabi as cabi
+    r32, r64 = ref["f32"], ref["f64"]
+    # bit-exact arg-min wherever the reference's own fp32 and fp64 evaluations agree on it
+    agree = r32["argmin"] == r64["argmin"]
+    assert torch.equal(argmin[agree], r64["argmin"][agree]), what + ": argmin mismatch"
+    arbitrated_close(out[cabi.OUT_E_MIN], r32["e_min"], r64["e_min"], atol=1e-5, what=what + " e_min")
+    arbitrated_close(out[cabi.OUT_LOG_L], r32["log_l"], r64["log_l"], atol=1e-5, what=what + " log_l")
+    arbitrated_close(out[cabi.OUT_MEAN_E], r32["mean_e"], r64["mean_e"], atol=1e-5, what=what + " mean_e")
+    arbitrated_close(out[cabi.OUT_MEAN_E2], r32["mean_e2"], r64["mean_e2"], atol=1e-5, what=what + " mean_e2")
+    arbitrated_close(out[cabi.OUT_VAR_E], r32["var_e"], r64["var_e"], atol=2e-5, what=what + " var_e")
+    arbitrated_close(out[cabi.OUT_ENTROPY], r32["entropy"], r64["entropy"], atol=2e-5, what=what + " entropy")
+    if aux:
+        arbitrated_close(out[cabi.OUT_AUX_MEAN], r32["aux_mean"], r64["aux_mean"], atol=1e-7, what=what + " aux")
+
+
+# ------------------------------------------------------------------------------------------------
+def test_prep_kernels(backend):
+    dev = backend.device
+    g = syn.gen(1)
+    for rows, d in ((37, 50), (64, 192), (5, 3072)):
+        x = torch.randn(rows, d, generator=g)
+        xd = x.to(dev)
+        ref = (x.double() ** 2).sum(1)
+        got = backend.row_norms(xd).cpu().double()
+        assert ((got - ref).abs() <= 1.2e-7 * ref).all()
+        noise = torch.randn(3 * rows, d, generator=g)
+        sigma = torch.rand(3 * rows, generator=g) + 0.1
+        post = torch.rand(3 * rows, generator=g) + 0.5
+        r = backend.prepare_rows(xd, 3 * rows, noise=noise.to(dev), sigma=sigma.to(dev), post=post.to(dev), want_x=True)
+        want = (noise * sigma[:, None] + x.repeat(3, 1)) * post[:, None]
+        assert torch.equal(r["x"].cpu(), want), "noising must match torch's mul-then-add bit for bit"
+        nref = (want.double() ** 2).sum(1)
+        assert ((r["norms"].cpu().double() - nref).abs() <= 1.2e-7 * nref).all()
+        # hi + lo reconstructs v * 2^k to ~22 bits of the row maximum
+        inv = r["inv_scale"].cpu().double()[:, None]
+        rec = (r["hi"].cpu().double()[:, :d] + r["lo"].cpu().double()[:, :d]) * inv
+        amax = want.abs().max(1).values.double()[:, None]
+        assert ((rec - want.double()).abs() <= amax * 2.0 ** -21).all()
+        scaled_max = (want.abs().max(1).values.double() / inv[:, 0])
+        assert ((scaled_max >= 2048) & (scaled_max < 4096)).all()
+        assert (r["hi"].cpu()[:, d:] == 0).all() and (r["lo"].cpu()[:, d:] == 0).all()
+    y = torch.randn(70, 45, generator=g)
+    hi, lo = backend.transpose_split(y.to(dev), 64.0)
+    rec = (hi.cpu().double() + lo.cpu().double())[:, :70] / 64.0
+    assert (rec - y.t().double()).abs().max() < 2.0 ** -20 * y.abs().max()
+    assert (hi.cpu()[:, 70:] == 0).all()
+    s, s2, mm = backend.column_moments(y.to(dev))
+    torch.testing.assert_close(s.cpu(), y.double().sum(0), rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(s2.cpu(), (y.double() ** 2).sum(0), rtol=1e-12, atol=1e-12)
+    assert mm[0].item() == y.min().item() and mm[1].item() == y.max().item()
+    assert backend.absmax(y.to(dev)).item() == y.abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["stats_gmm.npz", "stats_images.npz", "stats_clustered.npz"])
+def test_exact_stats_golden(backend, name):
+    g = load_golden(name)
+    data = g["data"].reshape(len(g["data"]), -1)
+    n_t, b = g["xt"].shape[:2]
+    xq = g["xt"].reshape(n_t * b, -1)
+    t_rows = g["temp"].repeat_interleave(b)
+    sig = orc.knn_sigma_reg_sq(g["data"], int(g["knn_k"]), float(g["sigma_reg_scale"]))
+    ref = oracle_rows(xq, data, t_rows, aux=sig)
+    for splits in (1, 3):
+        out, argmin = run_stats(backend, xq, data, t_rows, "exact", aux=sig, n_splits=splits)
+        check_stats(out, argmin, ref, aux=True, what=f"{name} exact S={splits}")
+    # the reference's own batch outputs (entropy per query, utils/stats.py:289)
+    from pdm_b200 import _cabi as cabi
+    ent = out[cabi.OUT_ENTROPY].view(n_t, b)
+    ref64 = ref["f64"]["entropy"].view(n_t, b)
+    arbitrated_close(ent, g["entropy"], ref64, atol=2e-5, what=name + " entropy vs reference golden")
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("precision", ["f16x3"])
+def test_tensor_stats_small(backend, cta_group, precision):
+    """Tensor path at shapes that exercise ragged tiles: M, N, d not multiples of the tile sizes."""
+    g = syn.gen(5)
+    for (m, n, d) in ((200, 700, 192), (300, 1000, 328), (130, 260, 64)):
+        data = torch.rand(n, d, generator=g) * 2 - 1
+        x0 = data[torch.randint(0, n, (m,), generator=g)]
+        t_rows = torch.logspace(-3, 3, m)
+        xq = x0 + t_rows.sqrt()[:, None] * torch.randn(m, d, generator=g)
+        aux = torch.rand(n, generator=g) * 0.1
+        ref = oracle_rows(xq, data, t_rows, aux=aux)
+        for splits, grp in ((0, 0), (1, 1), (3, 2)):
+            out, argmin = run_stats(backend, xq, data, t_rows, precision, aux=aux, cta_group=cta_group,
+                                    n_splits=splits, m_group=grp)
+            check_stats(out, argmin, ref, aux=True, what=f"tensor cg={cta_group} ({m},{n},{d}) S={splits}")
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tensor_stats_cifar_slice(backend, cta_group):
+    g = load_golden("cifar_slice.npz")
+    n, b = int(g["n"]), int(g["b"])
+    data = syn.uniform_images(n, (3, 32, 32), int(g["data_seed"]))
+    x0 = data[:b].clone()
+    torch.manual_seed(int(g["noise_seed"]))
+    xt = orc.draw_noised_queries(x0, g["temp"], loader_iters="per_temp")
+    n_t = len(g["temp"])
+    xq = xt.reshape(n_t * b, -1)
+    t_rows = g["temp"].repeat_interleave(b)
+    ref = oracle_rows(xq, data.reshape(n, -1), t_rows)
+    out, argmin = run_stats(backend, xq, data, t_rows, "f16x3", cta_group=cta_group)
+    check_stats(out, argmin, ref, what=f"cifar slice cg={cta_group}")
+    from pdm_b200 import _cabi as cabi
+    arbitrated_close(out[cabi.OUT_ENTROPY].view(n_t, b), g["entropy"], ref["f64"]["entropy"].view(n_t, b), atol=2e-5,
+                     what="cifar slice entropy vs reference golden")
+
+
+def test_tensor_accumulation_error(backend):
+    """How far the tensor-core Gram entries are from fp64 (documents the accumulation behaviour)."""
+    g = syn.gen(9)
+    n, d, m = 512, 3072, 128
+    data = torch.rand(n, d, generator=g) * 2 - 1
+    xq = data[:m] + 0.05 * torch.randn(m, d, generator=g)
+    dev = backend.device
+    from pdm_b200.engine import pow2_scale_for
+    y = data.to(dev)
+    scale = pow2_scale_for(float(backend.absmax(y).item()))
+    ys = backend.prepare_rows(y, n, fixed_scale=scale, want_norms=False)
+    prep = backend.prepare_rows(xq.to(dev), m)
+    y_norm = backend.row_norms(y)
+    for prec in ("f16x3", "f16x1"):
+        dist = torch.empty(m, n, device=dev)
+        backend.posterior_stats(precision=prec, M=m, N=n, d=d, q_norm=prep["norms"], y_norm=y_norm, inv_temp=None,
+                                q_split=(prep["hi"], prep["lo"], prep["inv_scale"]), y_split=(ys["hi"], ys["lo"]),
+                                y_inv_scale=1.0 / scale, want_partials=False, energy_out=dist, energy_mult=2.0)
+        ref64 = orc.pairwise_sqdist(xq.double(), data.double())
+        ref32 = orc.pairwise_sqdist(xq, data)
+        err = (dist.cpu().double() - ref64)
+        e32 = (ref32.double() - ref64)
+        print(f"\n[{prec}] dist err vs fp64: max {err.abs().max():.3e} mean {err.mean():.3e} rms {err.pow(2).mean().sqrt():.3e}"
+              f" | reference fp32: max {e32.abs().max():.3e} mean {e32.mean():.3e} rms {e32.pow(2).mean().sqrt():.3e}")
+        if prec == "f16x3":
+            assert err.abs().max() < 20 * max(e32.abs().max().item(), 1e-4)
+
+
+def test_posterior_mean(backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = load_golden("denoiser.npz")
+    ds = EmpiricalDataset(g["data"], backend=backend)
+    for prec in ("exact", "f16x3"):
+        eng = PosteriorEngine(ds, EngineConfig(precision=prec))
+        for i in range(len(g["taus"])):
+            ab = g[f"alpha_bar_{i}"].double()
+            xt = g[f"xt_{i}"]
+            t_rows = ((1 - ab) / ab).float().expand(len(xt))
+            post = (1 / ab.sqrt()).float().expand(len(xt))
+            got = eng.posterior_mean(xt, t_rows, post=post).cpu()
+            ref64 = orc.posterior_mean_x0(xt, g[f"alpha_bar_{i}"], g["data"], dtype=torch.float64).reshape(len(xt), -1)
+            arbitrated_close(got, g[f"x0hat_{i}"].reshape(len(xt), -1), ref64, atol=2e-5, what=f"x0hat {prec} tau#{i}")
+
+
+def test_pairwise_dense(backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = load_golden("distance.npz")
+    ds = EmpiricalDataset(g["pts"], backend=backend)
+    eng = PosteriorEngine(ds, EngineConfig(precision="exact"))
+    d = eng.pairwise_sqdist(g["pts"]).cpu()
+    ref64 = orc.pairwise_sqdist(g["pts"].double())
+    arbitrated_close(d, g["pw_pts"], ref64, atol=2e-5, what="dense self distance")
+    d.fill_diagonal_(1e10)
+    nn1, i1 = d.min(1)
+    assert torch.equal(i1, g["nn1_idx"])
+    d.scatter_(1, i1[:, None], 1e10)
+    assert torch.equal(d.min(1).indices, g["nn2_idx"])
