@@ -129,6 +129,10 @@ typedef struct pdm_stats_args {
                                    emitting its own partial record (0 = auto, see pdm_stats_plan)  */
     int32_t m_group;            /* tensor path: M tiles scheduled side by side (0 = auto)          */
     int32_t cta_group;          /* tensor path: 1 or 2 CTAs per MMA (0 = auto = 2)                 */
+    int32_t records_per_row;    /* OUT of pdm_posterior_stats_plan: partial records emitted per query
+                                   row (S on the exact path, 2*S on the tensor path: one per column
+                                   half of a tile)                                                 */
+    int32_t reserved0;
     int64_t M, N, d;
     int64_t index_offset;       /* global dataset index of local row 0 (dataset shards)            */
     /* fp32 operands (PDM_PREC_EXACT_F32) */
@@ -143,14 +147,15 @@ typedef struct pdm_stats_args {
     const float* inv_temp;      /* (M) 1/T                                                         */
     const float* y_aux;         /* (N) per-point scalar s_j (utils/stats.py:101) or NULL           */
     /* outputs */
-    float*   partials;          /* (M, S, PDM_PART_STRIDE)                                         */
+    float*   partials;          /* (M, records_per_row, PDM_PART_STRIDE)                           */
     float*   energy_out;        /* optional (M, lde): energy_mult * E  (2.0 gives the squared
                                    distance of utils/distance.py:21, 1.0 the energy)               */
     int64_t  lde;
     float    energy_mult;
 } pdm_stats_args;
 
-/* Fills args->n_splits / m_group / cta_group when they are 0 and reports the size of `partials`. */
+/* Fills args->n_splits / m_group / cta_group when they are 0, sets args->records_per_row and reports the
+ * size of `partials` in floats. */
 int pdm_posterior_stats_plan(pdm_stats_args* args, int device, int64_t* partial_floats);
 int pdm_posterior_stats(const pdm_stats_args* args, pdm_stream_t stream);
 

@@ -23,6 +23,7 @@
 #include "sm100_ptx.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace pdm {
 namespace tc {
@@ -32,9 +33,12 @@ using namespace ptx;
 constexpr int kRowsPerCta = 128;
 constexpr int kBlockK = 64;                       // fp16 elements = one 128-byte swizzled row
 constexpr int kTileBytes = kRowsPerCta * kBlockK * 2;
-constexpr int kThreads = 256;
 constexpr int kAccStages = 2;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 4;                      // warps 0-3: producer / MMA / TMEM alloc / spare
+constexpr int kEpiWarps = 8;                      // warps 4-11: two warps per TMEM lane quarter
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
+constexpr int kRegsControl = 40;                  // setmaxnreg budgets: 128*40 + 256*232 == 384*168
+constexpr int kRegsEpilogue = 232;
 
 enum { EPI_STATS = 0, EPI_STORE = 1 };
 
@@ -42,6 +46,7 @@ struct GemmParams {
     int64_t M;            // rows of A (queries)
     int64_t ncols;        // rows of B (dataset rows for EPI_STATS, feature columns for EPI_STORE)
     int32_t num_kb;       // number of 64-element k blocks
+    int32_t flush_kb;     // k blocks accumulated inside the tensor core before a flush to registers
     int32_t m_tiles;      // row super-tiles of 128*CG rows
     int32_t n_tiles;      // column tiles of kBlockN
     int32_t m_group, n_splits;
@@ -56,6 +61,7 @@ struct GemmParams {
 template <int CG, int TERMS>
 struct Cfg {
     static constexpr int kBlockN = (CG == 2) ? 256 : 128;
+    static constexpr int kColsPerThread = kBlockN / 2;          // two epilogue warps share a lane quarter
     static constexpr int kTilesPerStage = (TERMS == 3) ? 4 : 2;
     static constexpr int kStageBytes = kTilesPerStage * kTileBytes;
     static constexpr int kStages = (TERMS == 3) ? 3 : 6;
@@ -65,6 +71,17 @@ struct Cfg {
     static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 8 * kNumBars + 16;
 };
 
+// Register re-balancing between warpgroups (all four warps of a warpgroup execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// The tensor core adds each MMA's K=16 partial product into the fp32 TMEM accumulator with truncation
+// (measured on B200: ~0.35 ulp of bias per MMA, 0.025 absolute on a d=3072 near-neighbour dot product --
+// 50x the fp32 SGEMM noise of the reference).  So the accumulator only ever holds `flush_kb` k-blocks
+// (12 MMAs at flush_kb = 1); the epilogue warps drain it into fp32 registers with round-to-nearest adds
+// while the MMA warp fills the other accumulator stage, and the statistics are computed from the registers.
 template <int CG, int TERMS, int EPI, bool AUX>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -73,6 +90,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     using C = Cfg<CG, TERMS>;
     constexpr int kBlockN = C::kBlockN;
     constexpr int kStages = C::kStages;
+    constexpr int CPT = C::kColsPerThread;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -100,7 +118,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * 128); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * kEpiWarps); }
         fence_mbar_init();
     }
     __syncwarp();
@@ -115,157 +133,182 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
     const bool active = pair < p.m_group * p.n_splits;
     const int mi = pair % p.m_group, sp = pair / p.m_group;
+    const int n_chunks = (p.num_kb + p.flush_kb - 1) / p.flush_kb;
 
-    if (active && warp == 0 && lane == 0) {
-        // ===================== TMA producer =====================
-        int stage = 0; uint32_t phase = 0;
-        for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
-            const int32_t a_row = (mt * CG + (int)rank) * kRowsPerCta;
-            for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
-                const int32_t b_row = nt * kBlockN + (int)rank * kRowsPerCta;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t dst = smem_base + (uint32_t)stage * C::kStageBytes;
-                    const uint32_t fb = full_bar(stage);
-                    const int32_t kc = kb * kBlockK;
-                    if (CG == 1) {
-                        mbar_arrive_expect_tx(fb, C::kStageBytes);
-                        tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
-                        if (TERMS == 3) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
-                        tma_load_2d(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
-                        if (TERMS == 3) tma_load_2d(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
-                    } else {
-                        if (leader) mbar_arrive_expect_tx(fb, 2u * C::kStageBytes);
-                        else mbar_arrive_remote(fb, 0);
-                        tma_load_2d_pair(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
-                        if (TERMS == 3) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
-                        tma_load_2d_pair(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
-                        if (TERMS == 3) tma_load_2d_pair(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
-                    }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (active && warp == 1 && lane == 0 && leader) {
-        // ===================== MMA issuer =====================
-        int stage = 0; uint32_t phase = 0; uint32_t tile_iter = 0;
-        for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
-            for (int nt = sp; nt < p.n_tiles; nt += p.n_splits, ++tile_iter) {
-                const uint32_t as = tile_iter & 1u, aphase = (tile_iter >> 1) & 1u;
-                mbar_wait(tempty_bar(as), aphase ^ 1u);      // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * kBlockN;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t sb = smem_base + (uint32_t)stage * C::kStageBytes;
-                    const uint64_t a_hi = make_smem_desc_sw128(sb);
-                    const uint64_t a_lo = make_smem_desc_sw128(sb + kTileBytes);
-                    const uint64_t b_hi = make_smem_desc_sw128(sb + (TERMS == 3 ? 2 : 1) * kTileBytes);
-                    const uint64_t b_lo = make_smem_desc_sw128(sb + 3 * kTileBytes);
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes = 2 descriptor units
-                        umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc, (kb | k) != 0 ? 1u : 0u);
-                        if (TERMS == 3) {
-                            umma_f16<CG>(d_tmem, a_lo + ko, b_hi + ko, C::kIdesc, 1u);
-                            umma_f16<CG>(d_tmem, a_hi + ko, b_lo + ko, C::kIdesc, 1u);
-                        }
-                    }
-                    umma_commit<CG>(empty_bar(stage));                      // smem slot reusable once these retire
-                    if (kb == p.num_kb - 1) umma_commit<CG>(tfull_bar(as)); // accumulator complete
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (active && warp >= kEpiWarp0) {
-        // ===================== epilogue =====================
-        const int quarter = warp - kEpiWarp0;                 // == warp % 4: the TMEM lane quarter this warp may read
-        const int row_in_cta = quarter * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        uint32_t tile_iter = 0;
-        for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
-            const int64_t grow = (int64_t)(mt * CG + (int)rank) * kRowsPerCta + row_in_cta;
-            const bool row_ok = grow < p.M;
-            float xn = 0.f, neg2inv = 0.f, inv_t = 1.f;
-            RowState st;
-            if (EPI == EPI_STATS) {
-                if (row_ok) {
-                    xn = p.q_norm[grow];
-                    neg2inv = -2.f * p.q_inv_scale[grow] * p.y_inv_scale;
-                    inv_t = p.inv_temp[grow];
-                }
-                state_init(st);
-            }
-            for (int nt = sp; nt < p.n_tiles; nt += p.n_splits, ++tile_iter) {
-                const uint32_t as = tile_iter & 1u, aphase = (tile_iter >> 1) & 1u;
-                const int64_t n0 = (int64_t)nt * kBlockN;
-                mbar_wait(tfull_bar(as), aphase);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + lane_base + as * kBlockN + c0, v);
-                    tmem_ld_wait();
-                    const int64_t col0 = n0 + c0;
-                    if (col0 >= p.ncols) continue;            // whole chunk beyond the last column
-                    const bool full_chunk = col0 + 32 <= p.ncols;
-                    if (EPI == EPI_STATS) {
-                        float E[32], ax[32];
-                        if (full_chunk) {
-                            const float4* yn4 = reinterpret_cast<const float4*>(p.y_norm + col0);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 y = __ldg(yn4 + i);
-                                E[4 * i + 0] = y.x; E[4 * i + 1] = y.y; E[4 * i + 2] = y.z; E[4 * i + 3] = y.w;
-                            }
-                            if (AUX) {
-                                const float4* ax4 = reinterpret_cast<const float4*>(p.y_aux + col0);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 y = __ldg(ax4 + i);
-                                    ax[4 * i + 0] = y.x; ax[4 * i + 1] = y.y; ax[4 * i + 2] = y.z; ax[4 * i + 3] = y.w;
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                E[i] = 0.5f * __fadd_rn(fmaf(__uint_as_float(v[i]), neg2inv, xn), E[i]);
+    if (warp < kEpiWarp0) {
+        setmaxnreg_dec<kRegsControl>();
+        if (active && warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+                const int32_t a_row = (mt * CG + (int)rank) * kRowsPerCta;
+                for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
+                    const int32_t b_row = nt * kBlockN + (int)rank * kRowsPerCta;
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t dst = smem_base + (uint32_t)stage * C::kStageBytes;
+                        const uint32_t fb = full_bar(stage);
+                        const int32_t kc = kb * kBlockK;
+                        if (CG == 1) {
+                            mbar_arrive_expect_tx(fb, C::kStageBytes);
+                            tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
+                            if (TERMS == 3) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
+                            tma_load_2d(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
+                            if (TERMS == 3) tma_load_2d(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
                         } else {
+                            if (leader) mbar_arrive_expect_tx(fb, 2u * C::kStageBytes);
+                            else mbar_arrive_remote(fb, 0);
+                            tma_load_2d_pair(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
+                            if (TERMS == 3) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
+                            tma_load_2d_pair(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
+                            if (TERMS == 3) tma_load_2d_pair(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
+                        }
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        } else if (active && warp == 1 && lane == 0 && leader) {
+            // ===================== MMA issuer =====================
+            int stage = 0; uint32_t phase = 0; uint32_t chunk_iter = 0;
+            for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+                for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
+                    for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.flush_kb, ++chunk_iter) {
+                        const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
+                        mbar_wait(tempty_bar(as), aphase ^ 1u);      // epilogue has drained this accumulator
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + as * kBlockN;
+                        const int kb1 = min(p.num_kb, kb0 + p.flush_kb);
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            mbar_wait(full_bar(stage), phase);
+                            tc_fence_after();
+                            const uint32_t sb = smem_base + (uint32_t)stage * C::kStageBytes;
+                            const uint64_t a_hi = make_smem_desc_sw128(sb);
+                            const uint64_t a_lo = make_smem_desc_sw128(sb + kTileBytes);
+                            const uint64_t b_hi = make_smem_desc_sw128(sb + (TERMS == 3 ? 2 : 1) * kTileBytes);
+                            const uint64_t b_lo = make_smem_desc_sw128(sb + 3 * kTileBytes);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const bool ok = col0 + i < p.ncols;
-                                const float yn = ok ? __ldg(p.y_norm + col0 + i) : 0.f;
-                                if (AUX) ax[i] = ok ? __ldg(p.y_aux + col0 + i) : 0.f;
-                                E[i] = ok ? 0.5f * __fadd_rn(fmaf(__uint_as_float(v[i]), neg2inv, xn), yn) : kBigE;
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);   // 16 fp16 = 32 bytes = 2 descriptor units
+                                umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                                if (TERMS == 3) {
+                                    umma_f16<CG>(d_tmem, a_lo + ko, b_hi + ko, C::kIdesc, 1u);
+                                    umma_f16<CG>(d_tmem, a_hi + ko, b_lo + ko, C::kIdesc, 1u);
+                                }
                             }
+                            umma_commit<CG>(empty_bar(stage));                 // smem slot reusable once these retire
+                            if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(as)); // chunk accumulator complete
+                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
                         }
-                        if (p.energy_out && row_ok) {
-                            float* eo = p.energy_out + grow * p.lde + col0;
+                    }
+                }
+            }
+        }
+    } else {
+        setmaxnreg_inc<kRegsEpilogue>();
+        if (active) {
+            // ===================== epilogue (8 warps) =====================
+            const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
+            const int half = (warp - kEpiWarp0) >> 2;             // which half of the tile's columns
+            const int row_in_cta = quarter * 32 + lane;
+            const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+            uint32_t chunk_iter = 0;
+            for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+                const int64_t grow = (int64_t)(mt * CG + (int)rank) * kRowsPerCta + row_in_cta;
+                const bool row_ok = grow < p.M;
+                float xn = 0.f, neg2inv = 0.f, inv_t = 1.f;
+                RowState st;
+                if (EPI == EPI_STATS) {
+                    if (row_ok) {
+                        xn = p.q_norm[grow];
+                        neg2inv = -2.f * p.q_inv_scale[grow] * p.y_inv_scale;
+                        if (p.inv_temp) inv_t = p.inv_temp[grow];
+                    }
+                    state_init(st);
+                }
+                for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
+                    float sums[CPT];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (full_chunk || col0 + i < p.ncols) eo[i] = p.energy_mult * E[i];
+                    for (int i = 0; i < CPT; ++i) sums[i] = 0.f;
+                    for (int ch = 0; ch < n_chunks; ++ch, ++chunk_iter) {
+                        const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
+                        mbar_wait(tfull_bar(as), aphase);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + t_lane + as * kBlockN + half * CPT;
+#pragma unroll
+                        for (int c0 = 0; c0 < CPT; c0 += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(taddr + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sums[c0 + i] = __fadd_rn(sums[c0 + i], __uint_as_float(v[i]));
                         }
-                        if (p.partials) state_add_chunk<32, AUX>(st, E, ax, p.index_offset + col0, 1, inv_t);
-                    } else {
-                        if (row_ok) {
-                            float* o = p.out + grow * p.ldo + col0;
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 1 || leader) mbar_arrive(tempty_bar(as));
+                            else mbar_arrive_remote(tempty_bar(as), 0);
+                        }
+                    }
+                    // ---- the tile's Gram entries are complete in registers ----
+                    const int64_t nbase = (int64_t)nt * kBlockN + half * CPT;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                if (full_chunk || col0 + i < p.ncols) {
-                                    const float r = p.out_scale * __uint_as_float(v[i]);
-                                    o[i] = p.accumulate ? o[i] + r : r;
+                    for (int c0 = 0; c0 < CPT; c0 += 32) {
+                        const int64_t col0 = nbase + c0;
+                        if (col0 < p.ncols) {
+                            const bool full_chunk = col0 + 32 <= p.ncols;
+                            if (EPI == EPI_STATS) {
+                                float E[32], ax[32];
+                                if (full_chunk) {
+                                    const float4* yn4 = reinterpret_cast<const float4*>(p.y_norm + col0);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 y = __ldg(yn4 + i);
+                                        E[4 * i + 0] = y.x; E[4 * i + 1] = y.y; E[4 * i + 2] = y.z; E[4 * i + 3] = y.w;
+                                    }
+                                    if (AUX) {
+                                        const float4* ax4 = reinterpret_cast<const float4*>(p.y_aux + col0);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) {
+                                            const float4 y = __ldg(ax4 + i);
+                                            ax[4 * i + 0] = y.x; ax[4 * i + 1] = y.y; ax[4 * i + 2] = y.z; ax[4 * i + 3] = y.w;
+                                        }
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        E[i] = 0.5f * __fadd_rn(fmaf(sums[c0 + i], neg2inv, xn), E[i]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) {
+                                        const bool ok = col0 + i < p.ncols;
+                                        const float yn = ok ? __ldg(p.y_norm + col0 + i) : 0.f;
+                                        if (AUX) ax[i] = ok ? __ldg(p.y_aux + col0 + i) : 0.f;
+                                        E[i] = ok ? 0.5f * __fadd_rn(fmaf(sums[c0 + i], neg2inv, xn), yn) : kBigE;
+                                    }
+                                }
+                                if (p.energy_out && row_ok) {
+                                    float* eo = p.energy_out + grow * p.lde + col0;
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        if (full_chunk || col0 + i < p.ncols) eo[i] = p.energy_mult * E[i];
+                                }
+                                if (p.partials) state_add_chunk<32, AUX>(st, E, ax, p.index_offset + col0, 1, inv_t);
+                            } else if (row_ok) {
+                                float* o = p.out + grow * p.ldo + col0;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    if (full_chunk || col0 + i < p.ncols) {
+                                        const float r = p.out_scale * sums[c0 + i];
+                                        o[i] = p.accumulate ? o[i] + r : r;
+                                    }
                                 }
                             }
                         }
                     }
                 }
-                // all of this thread's tcgen05.ld for the tile have completed (wait::ld above)
-                tc_fence_before();
-                if (CG == 1 || leader) mbar_arrive(tempty_bar(as));
-                else mbar_arrive_remote(tempty_bar(as), 0);
+                // one partial record per (row, split, column half)
+                if (EPI == EPI_STATS && p.partials && row_ok)
+                    state_store(st, p.partials + (grow * (2 * p.n_splits) + 2 * sp + half) * PDM_PART_STRIDE);
             }
-            if (EPI == EPI_STATS && p.partials && row_ok)
-                state_store(st, p.partials + (grow * p.n_splits + sp) * PDM_PART_STRIDE);
         }
     }
 
@@ -351,6 +394,17 @@ static int dispatch(int cg, int terms, const CUtensorMap* maps, const GemmParams
     return PDM_ERR_INVALID_ARG;
 }
 
+// k-blocks accumulated inside the tensor core between flushes (PDM_FLUSH_KB, default 1 = every 64 elements)
+static int flush_kb_setting() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("PDM_FLUSH_KB");
+        v = e ? atoi(e) : 1;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
 static int require_sm100(DeviceInfo* info) {
     int rc = current_device_info(info);
     if (rc != PDM_OK) return rc;
@@ -399,6 +453,7 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     GemmParams p = {};
     p.M = a.M; p.ncols = a.N;
     p.num_kb = (int32_t)ceil_div(a.d, kBlockK);
+    p.flush_kb = flush_kb_setting();
     p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
     p.m_group = a.m_group; p.n_splits = a.n_splits;
@@ -444,7 +499,9 @@ extern "C" int pdm_posterior_stats_plan(pdm_stats_args* a, int device, int64_t* 
         else if (s <= 0) s = (int)std::max<int64_t>(1, std::min<int64_t>(pairs / g, n_tiles));
         a->m_group = g; a->n_splits = s;
     }
-    if (partial_floats) *partial_floats = a->M * a->n_splits * PDM_PART_STRIDE;
+    // the tensor path emits two records per split (one per column half of a tile)
+    a->records_per_row = a->n_splits * (a->precision == PDM_PREC_EXACT_F32 ? 1 : 2);
+    if (partial_floats) *partial_floats = a->M * a->records_per_row * PDM_PART_STRIDE;
     return PDM_OK;
 }
 
@@ -486,6 +543,7 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     tc::GemmParams p = {};
     p.M = M; p.ncols = d;
     p.num_kb = (int32_t)ceil_div(K, tc::kBlockK);
+    p.flush_kb = tc::flush_kb_setting();
     p.m_tiles = (int32_t)ceil_div(M, (int64_t)tc::kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(d, block_n);
     // every (row tile, column tile) is an independent output tile: spread column tiles first

@@ -28,6 +28,7 @@ class StatsArgs(C.Structure):
     """Mirror of ``struct pdm_stats_args`` (include/pdm_b200.h) -- field order and types must match."""
     _fields_ = [
         ("precision", C.c_int32), ("n_splits", C.c_int32), ("m_group", C.c_int32), ("cta_group", C.c_int32),
+        ("records_per_row", C.c_int32), ("reserved0", C.c_int32),
         ("M", C.c_int64), ("N", C.c_int64), ("d", C.c_int64), ("index_offset", C.c_int64),
         ("q", C.c_void_p), ("ldq", C.c_int64), ("y", C.c_void_p), ("ldy", C.c_int64),
         ("q_hi", C.c_void_p), ("q_lo", C.c_void_p), ("ldqh", C.c_int64), ("q_inv_scale", C.c_void_p),

@@ -143,7 +143,7 @@ class CudaBackend:
               "pdm_posterior_stats_plan")
         partials = None
         if want_partials:
-            partials = torch.empty(M, a.n_splits, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
+            partials = torch.empty(M, a.records_per_row, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
             a.partials = partials.data_ptr()
         if energy_out is not None:
             a.energy_out, a.lde, a.energy_mult = energy_out.data_ptr(), energy_out.stride(0), float(energy_mult)
