@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the empirical-denoiser statistics hot path (BASELINE.json metric: query x dataset pairs/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): CIFAR-10-shaped synthetic data,
+N = 50 000 training points of d = 3072, B = 1024 queries drawn from the data, noised at each of the 1000
+temperatures of the linear-beta DDPM schedule; one STEP is one full pass of the reference's
+``compute_stats_batch`` over that batch (1 024 000 noised queries x 50 000 points = 5.12e10 pairs):
+noise draw (torch.randn per temperature), noising + operand split, fused distance / log-sum-exp / moment
+pass, merge, entropy per (temperature, query).
+
+  value    : pairs/s with x0, the temperatures and the prepared dataset resident in HBM (device-timed,
+             max over ranks).  With N GPUs the dataset is row-sharded (N/G rows per GPU), every GPU sees
+             all queries, per-row partial records are reduced locally, all-gathered over NCCL and merged:
+             total work is fixed -> "scaling": "strong".
+  e2e      : the same step through the reference-facing call utils.stats.compute_stats_batch(dataloader,
+             x0_traj, temp) with HOST inputs (pinned x0_traj + temperatures copied in, the (n_T, B) entropy
+             copied out, every step).  The training set behind the DataLoader is uploaded once, on the
+             first call, and cached per DataLoader object (that is the engine's residency feature).
+  roofline : the fused tcgen05 kernel, algorithmic 2*d flop per pair over its CUDA-event time, against
+             the measured bf16 tensor peak in MEASURED_PEAKS.json (the kernel executes 3x that in fp16
+             split MMAs; "executed_tflops" reports it).
+  cpu_baseline / --impl reference : oracle/posterior.py (torch CPU restatement of the reference, pinned to
+             it bit for bit) on a bounded sample of the same workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "physics-of-diffusion-models_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "query x dataset pairs/s (empirical posterior statistics, CIFAR-10 shape)"
+UNIT = "pairs/s"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def workload():
+    return {
+        "N": env_int("PDM_BENCH_N", 50_000), "d": 3072, "shape": (3, 32, 32),
+        "B": env_int("PDM_BENCH_B", 1024), "n_T": env_int("PDM_BENCH_NT", 1000),
+        "min_temp": 1e-4, "max_temp": 2.478e4,
+    }
+
+
+def ddpm_temperatures(n_steps, min_temp, max_temp):
+    """T_k of the linear-beta schedule at tau = linspace(0,1,n+1)[1:] (diffusion/scheduler/linear.py:5-13)."""
+    tau = torch.linspace(0, 1, n_steps + 1, dtype=torch.float64)[1:]
+    scale = 1 + min_temp
+    gamma = math.log((1 + max_temp) / scale)
+    return ((tau.pow(2) * gamma).exp() * scale - 1).float()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))),
+                "hbm_gbs": float(p.get("hbm_gbs", 6650.0)), "source": "MEASURED_PEAKS.json (bf16 sustained)"}
+    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi samples of SM clock / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        mhz, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                c, m, pw = float(f[0]), float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = max(mx, m)
+            if pw > 400:            # a sample taken under load
+                mhz.append(c)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples_under_load": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm (oracle port, torch CPU) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(w, b_cpu, nt_cpu, seed):
+    from oracle import posterior as orc
+    g = torch.Generator().manual_seed(seed)
+    data = torch.rand(w["N"], w["d"], generator=g) * 2 - 1
+    x0 = data[:b_cpu].clone()
+    temps = ddpm_temperatures(w["n_T"], w["min_temp"], w["max_temp"])
+    idx = torch.linspace(0, w["n_T"] - 1, nt_cpu).long()
+    return orc, data, x0, temps[idx]
+
+
+def cpu_step(orc, data, x0, temps):
+    """One bounded sample of the step: the reference's per-temperature loop with its DataLoader chunking
+    (dataloader batch 5000) on the CPU."""
+    xt = orc.draw_noised_queries(x0, temps)
+    ent = orc.entropy_batch(xt, data, temps, chunk=5000)
+    return ent, x0.shape[0] * len(temps) * data.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = workload()
+    b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 2)
+    orc, data, x0, temps = cpu_sample(w, b_cpu, nt_cpu, 0)
+    cores = torch.get_num_threads()
+    for _ in range(args.warmup):
+        cpu_step(orc, data, x0, temps)
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(args.steps):
+        pairs += cpu_step(orc, data, x0, temps)[1]
+    dt = time.perf_counter() - t0
+    value = pairs / dt
+    sample = f"B={b_cpu} queries x {nt_cpu} temperatures x full N={w['N']}, d={w['d']} per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: N=50000 d=3072 B=1024 x 1000-step linear-beta DDPM temperatures",
+                   "reference_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    from pdm_b200.backend import CudaBackend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    w = workload()
+    n, d, b, n_t = w["N"], w["d"], w["B"], w["n_T"]
+    torch.manual_seed(0)
+    data_full = torch.rand(n, d, device=dev) * 2 - 1                      # synthetic CIFAR-10-shaped set
+    x0 = data_full[:b].clone()
+    temps = ddpm_temperatures(n_t, w["min_temp"], w["max_temp"]).to(dev)
+    per = (n + world - 1) // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+    backend = CudaBackend(dev)
+    ds = EmpiricalDataset(data_full[lo:hi], backend=backend, index_offset=lo, n_total=n,
+                          global_absmax=float(data_full.abs().max().item()))
+    cfg = EngineConfig.from_env()
+    cfg.sync_noise = False                      # every rank seeds its generator identically below
+    eng = PosteriorEngine(ds, cfg, group=group)
+    precision = eng.precision()
+    if precision != "exact":
+        ds.split()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        torch.manual_seed(1000 + i)             # same stream on every rank
+        st = eng.noised_stats(x0, temps)
+        return st["entropy"].mean(dim=1)        # (n_T,) stays on the device
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    backend.kernel_events = []
+    launches0 = backend.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(args.warmup + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = backend.launches - launches0
+    # fused-kernel time from the CUDA events recorded around its launches on the launching stream
+    kev = backend.kernel_events
+    backend.kernel_events = None
+    k_ms = sum(a.elapsed_time(bb) for a, bb, _ in kev)
+    k_pairs = sum(p for _, _, p in kev)
+    pairs_per_step = b * n_t * n
+    value = pairs_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e through the reference-facing API with host inputs --------------------------------
+    from torch.utils.data import DataLoader, TensorDataset
+    import utils.stats as ustats
+    if world > 1:
+        os.environ["PDM_SHARD_DATASET"] = "1"
+    host_data = data_full.cpu().view(n, *w["shape"])
+    loader = DataLoader(TensorDataset(host_data), batch_size=5000, shuffle=False)
+    x0_host = x0.cpu().view(b, *w["shape"]).pin_memory()
+    temps_host = temps.cpu().pin_memory()
+    del data_full
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(1)
+        ustats.compute_stats_batch(loader, x0_host, temps_host)         # uploads + caches the dataset
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        torch.manual_seed(2000 + i)
+        ent = ustats.compute_stats_batch(loader, x0_host, temps_host)["entropy"]
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step * args.steps / float(e2e_s.item())
+    h2d = x0_host.numel() * 4 + temps_host.numel() * 4
+    d2h = ent.numel() * 4
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ach = (2.0 * d * k_pairs / (k_ms * 1e-3)) / 1e12 if k_ms > 0 else 0.0
+        terms = 3 if precision == "f16x3" else 1
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate)" if precision != "exact" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "C2: N=50000 d=3072 B=1024 x 1000-step linear-beta DDPM temperatures "
+                                   "(compute_stats_batch)", "N": n, "d": d, "B": b, "n_T": n_t,
+                       "precision": precision, "sharding": f"dataset rows / {world}",
+                       "l2": "inputs (dataset 614 MB + queries) exceed the 126 MB L2; no flush needed",
+                       "plan_splits_group_cta": list(getattr(backend, "last_plan", ()))},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "utils.stats.compute_stats_batch(dataloader, x0_traj, temp), dataset cached on device "
+                           "after the first call"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["tflops"], "traffic": None, "kernel": "pdm::tc::fused_gemm_kernel",
+                         "executed_tflops": terms * ach, "kernel_ms_per_step": k_ms / max(1, args.steps),
+                         "peak_source": peaks["source"], "flops_per_pair": 2 * d},
+            "clocks": clocks,
+        }
+        if world == 1:
+            b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 4)
+            orc, cdata, cx0, ctemps = cpu_sample(w, b_cpu, nt_cpu, 0)
+            cpu_step(orc, cdata[:2000], cx0, ctemps[:1])           # warm the BLAS threads
+            t0 = time.perf_counter()
+            _, cpairs = cpu_step(orc, cdata, cx0, ctemps)
+            cdt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cpairs / cdt, "unit": UNIT, "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": f"B={b_cpu} queries x {nt_cpu} temperatures x full N={n}, d={d}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -170,6 +170,13 @@ int pdm_merge_partials(const float* parts, int64_t M, int64_t n_outer, int64_t o
                        int64_t n_inner, int64_t row_stride, const float* inv_temp, int64_t n_total,
                        float* out, int64_t* argmin, pdm_stream_t stream);
 
+/* Same combination without the finalisation: out_records (M, PDM_PART_STRIDE) holds ONE merged record
+ * per row.  A rank reduces its own splits with this before the all-gather, so that 32 bytes per query
+ * row cross NVLink instead of 32 bytes per (row, split). */
+int pdm_reduce_partials(const float* parts, int64_t M, int64_t n_outer, int64_t outer_stride,
+                        int64_t n_inner, int64_t row_stride, const float* inv_temp, float* out_records,
+                        pdm_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K8 posterior mean  x0_hat_b = sum_j p_bj y_j,  p_bj = exp(-(E_bj - m_b)/T_b)/l_b.
  * Replaces p = exp(-h/(1-ab)); p /= p.sum; p @ data  (diffusion/scheduler/scheduler.py:66-69).

@@ -52,7 +52,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 
 constexpr uint64_t kWatchdogNs = 4000000000ull;   // 4 s: far beyond any legitimate wait in these kernels
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
     uint32_t done = 0;
     uint64_t t0 = 0;
     while (true) {
@@ -60,7 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
         if (done) break;
         const uint64_t now = global_timer_ns();
         if (t0 == 0) t0 = now;

@@ -47,6 +47,7 @@ struct GemmParams {
     int64_t ncols;        // rows of B (dataset rows for EPI_STATS, feature columns for EPI_STORE)
     int32_t num_kb;       // number of 64-element k blocks
     int32_t flush_kb;     // k blocks accumulated inside the tensor core before a flush to registers
+    uint32_t wait_hint_ns; // suspend-time hint of mbarrier.try_wait
     int32_t m_tiles;      // row super-tiles of 128*CG rows
     int32_t n_tiles;      // column tiles of kBlockN
     int32_t m_group, n_splits;
@@ -145,7 +146,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
                     const int32_t b_row = nt * kBlockN + (int)rank * kRowsPerCta;
                     for (int kb = 0; kb < p.num_kb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
                         const uint32_t dst = smem_base + (uint32_t)stage * C::kStageBytes;
                         const uint32_t fb = full_bar(stage);
                         const int32_t kc = kb * kBlockK;
@@ -174,12 +175,12 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
                     for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.flush_kb, ++chunk_iter) {
                         const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
-                        mbar_wait(tempty_bar(as), aphase ^ 1u);      // epilogue has drained this accumulator
+                        mbar_wait(tempty_bar(as), aphase ^ 1u, p.wait_hint_ns);      // epilogue has drained this accumulator
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + as * kBlockN;
                         const int kb1 = min(p.num_kb, kb0 + p.flush_kb);
                         for (int kb = kb0; kb < kb1; ++kb) {
-                            mbar_wait(full_bar(stage), phase);
+                            mbar_wait(full_bar(stage), phase, p.wait_hint_ns);
                             tc_fence_after();
                             const uint32_t sb = smem_base + (uint32_t)stage * C::kStageBytes;
                             const uint64_t a_hi = make_smem_desc_sw128(sb);
@@ -231,7 +232,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     for (int i = 0; i < CPT; ++i) sums[i] = 0.f;
                     for (int ch = 0; ch < n_chunks; ++ch, ++chunk_iter) {
                         const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
-                        mbar_wait(tfull_bar(as), aphase);
+                        mbar_wait(tfull_bar(as), aphase, p.wait_hint_ns);
                         tc_fence_after();
                         const uint32_t taddr = tmem_base + t_lane + as * kBlockN + half * CPT;
 #pragma unroll
@@ -405,6 +406,16 @@ static int flush_kb_setting() {
     return v;
 }
 
+static uint32_t wait_hint_setting() {
+    static long v = -1;
+    if (v < 0) {
+        const char* e = getenv("PDM_WAIT_HINT_NS");
+        v = e ? atol(e) : 20000;
+        if (v < 0) v = 0;
+    }
+    return (uint32_t)v;
+}
+
 static int require_sm100(DeviceInfo* info) {
     int rc = current_device_info(info);
     if (rc != PDM_OK) return rc;
@@ -415,18 +426,28 @@ static int require_sm100(DeviceInfo* info) {
     return PDM_OK;
 }
 
-// Pick (m_group, n_splits): use as many CTA pairs as possible while the A tiles that are live at the same
-// time (m_group of them) stay well inside L2, so that they are re-read from L2 rather than HBM.
+// Pick (m_group, n_splits).  Every CTA group walks ceil(m_tiles/G) * ceil(n_tiles/S) tiles, so the
+// schedule's length is that product (tile quantisation); among the shortest schedules prefer the one whose
+// G live A tiles stay inside an L2 budget (they are re-read from L2 for every column tile) and, after
+// that, the larger G (fewer partial records per row).
 void plan_schedule(int pairs, int64_t m_tiles, int64_t n_tiles, int64_t a_tile_bytes, int* m_group, int* n_splits) {
-    const int64_t budget = 40ll << 20;
+    const int64_t budget = 48ll << 20;
+    const int64_t g_cap = std::max<int64_t>(1, budget / std::max<int64_t>(1, a_tile_bytes));
     int best_g = 1, best_s = 1;
-    int64_t best_used = 0;
+    int64_t best_steps = -1;
+    bool best_fits = false;
     for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
-        int64_t g = std::min<int64_t>(pairs / s, m_tiles);
-        g = std::min<int64_t>(g, std::max<int64_t>(1, budget / std::max<int64_t>(1, a_tile_bytes)));
-        if (g < 1) continue;
-        const int64_t used = g * s;
-        if (used > best_used || (used == best_used && g > best_g)) { best_used = used; best_g = (int)g; best_s = s; }
+        for (int64_t g = std::min<int64_t>(pairs / s, m_tiles); g >= 1; --g) {
+            const int64_t steps = ceil_div(m_tiles, g) * ceil_div(n_tiles, (int64_t)s);
+            const bool fits = g <= g_cap;
+            bool better = best_steps < 0;
+            if (!better) {
+                // allow 2% longer schedules if they keep the A tiles inside the L2 budget
+                const double cost = steps * (fits ? 1.0 : 1.02), bcost = best_steps * (best_fits ? 1.0 : 1.02);
+                better = cost < bcost || (cost == bcost && g > best_g);
+            }
+            if (better) { best_steps = steps; best_g = (int)g; best_s = s; best_fits = fits; }
+        }
     }
     *m_group = best_g;
     *n_splits = best_s;
@@ -454,6 +475,7 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.M = a.M; p.ncols = a.N;
     p.num_kb = (int32_t)ceil_div(a.d, kBlockK);
     p.flush_kb = flush_kb_setting();
+    p.wait_hint_ns = wait_hint_setting();
     p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
     p.m_group = a.m_group; p.n_splits = a.n_splits;
@@ -544,6 +566,7 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     p.M = M; p.ncols = d;
     p.num_kb = (int32_t)ceil_div(K, tc::kBlockK);
     p.flush_kb = tc::flush_kb_setting();
+    p.wait_hint_ns = tc::wait_hint_setting();
     p.m_tiles = (int32_t)ceil_div(M, (int64_t)tc::kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(d, block_n);
     // every (row tile, column tile) is an independent output tile: spread column tiles first

@@ -1,0 +1,94 @@
+"""``Scheduler`` base class with the closed-form ideal denoiser on the B200 engine.
+
+Mirror of the reference's diffusion/scheduler/scheduler.py:13-69: same free functions, same abstract
+interface (``log_temp_from_tau`` / ``tau_from_log_temp``), same ``add_noise`` and the same
+``true_posterior_mean_x0(xt, tau, data)`` signature and result (float32, shaped like ``xt``, on ``xt``'s
+device).  The reference evaluates  h = 1/2 ||xt - sqrt(ab) y||^2, p = softmax(-h / (1 - ab)), p @ data  with
+a fresh sqrt(ab)-scaled copy of the whole dataset per call (:64); here the identity
+||x - a y||^2 = a^2 ||x/a - y||^2 turns it into the VE form with queries x/sqrt(ab) at temperature
+T = (1 - ab)/ab, so the resident dataset (norms, fp16 split, transposed split) is reused untouched.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from pdm_b200 import EmpiricalDataset, PosteriorEngine
+from pdm_b200.engine import default_backend
+
+
+def log_temp_from_alpha_bar(alpha_bar: Tensor) -> Tensor:
+    return (1 - alpha_bar).log() - alpha_bar.log()
+
+
+def alpha_bar_from_log_temp(log_temp: Tensor) -> Tensor:
+    return torch.sigmoid(-log_temp)
+
+
+def cast_log_temp(log_temp: Tensor, target: Tensor) -> Tensor:
+    return log_temp.view(-1, *[1] * (target.ndim - 1))
+
+
+_DENOISER_ENGINES: dict[tuple, PosteriorEngine] = {}
+
+
+def _engine_for_data(data: Tensor) -> PosteriorEngine:
+    """One resident dataset per training-data tensor (keyed by storage, shape and version)."""
+    key = (data.data_ptr(), tuple(data.shape), data.dtype, str(data.device), data._version)
+    eng = _DENOISER_ENGINES.get(key)
+    if eng is None:
+        if len(_DENOISER_ENGINES) >= 4:
+            _DENOISER_ENGINES.clear()
+        eng = PosteriorEngine(EmpiricalDataset(data, backend=default_backend()))
+        _DENOISER_ENGINES[key] = eng
+    return eng
+
+
+class Scheduler(ABC):
+    def __init__(self):
+        pass
+
+    @abstractmethod
+    def log_temp_from_tau(self, tau: Tensor) -> Tensor:
+        pass
+
+    @abstractmethod
+    def tau_from_log_temp(self, log_temp: Tensor) -> Tensor:
+        pass
+
+    def alpha_bar_from_tau(self, tau: Tensor) -> Tensor:
+        return alpha_bar_from_log_temp(self.log_temp_from_tau(tau))
+
+    def add_noise(self, x0: Tensor, tau: Optional[Tensor] = None) -> tuple[Tensor, Tensor, Tensor]:
+        """xt = sqrt(ab) x0 + sqrt(1 - ab) eps with tau ~ U[0,1) per sample unless given (scheduler.py:40-45)."""
+        tau = torch.rand((len(x0),), device=x0.device) if tau is None else tau
+        alpha_bar = cast_log_temp(self.alpha_bar_from_tau(tau), x0)
+        eps = torch.randn_like(x0)
+        return tau, eps, alpha_bar.sqrt() * x0 + eps * (1 - alpha_bar).sqrt()
+
+    def true_score(self, xt: Tensor, tau: Tensor, train_data: Tensor) -> Tensor:
+        """Ideal score (x0_hat sqrt(ab) - xt)/(1 - ab).  The reference's version (scheduler.py:47-56, never
+        called by its own code) materialises an (N, B, ...) tensor; this one goes through the fused path."""
+        alpha_bar = cast_log_temp(self.alpha_bar_from_tau(tau), xt)
+        x0_hat = self.true_posterior_mean_x0(xt, tau, train_data)
+        return (x0_hat * alpha_bar.sqrt() - xt.float()) / (1 - alpha_bar)
+
+    @torch.autocast(device_type="cuda", enabled=False)
+    def true_posterior_mean_x0(self, xt: Tensor, tau: Tensor, data: Tensor) -> Tensor:
+        if torch.is_grad_enabled() and (xt.requires_grad or (isinstance(tau, Tensor) and tau.requires_grad)):
+            raise NotImplementedError(
+                "true_posterior_mean_x0 on the B200 engine has no backward pass yet (needed only by "
+                "scripts/optimize_schedule.py); call it under torch.no_grad()")
+        x = xt.float()
+        b = x.shape[0]
+        alpha_bar = self.alpha_bar_from_tau(tau).float().reshape(-1)
+        if alpha_bar.numel() not in (1, b):
+            raise ValueError(f"tau must be scalar-like or hold one value per sample, got {alpha_bar.numel()} for batch {b}")
+        alpha_bar = alpha_bar.expand(b)
+        temp_rows = ((1 - alpha_bar) / alpha_bar).clamp_min(1e-30)
+        eng = _engine_for_data(data)
+        x0_hat = eng.posterior_mean(x, temp_rows, post=alpha_bar.rsqrt())
+        return x0_hat.to(x.device).view_as(x)

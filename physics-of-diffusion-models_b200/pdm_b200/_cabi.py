@@ -53,6 +53,7 @@ SIGNATURES = {
     "pdm_posterior_stats_plan": (C.c_int, [C.POINTER(StatsArgs), C.c_int, C.POINTER(C.c_int64)]),
     "pdm_posterior_stats": (C.c_int, [C.POINTER(StatsArgs), _P]),
     "pdm_merge_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
+    "pdm_reduce_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "pdm_weights_from_energy": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "pdm_split_gemm_f16x3": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P]),
     "pdm_weighted_mean_exact_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I32, _P]),

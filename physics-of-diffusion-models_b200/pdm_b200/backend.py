@@ -38,6 +38,7 @@ class CudaBackend:
               "pdm_device_info")
         self.sm_count, self.cc = sm.value, (major.value, minor.value)
         self.launches = 0          # kernels of ours launched through this backend (bench reports it)
+        self.kernel_events = None  # bench hook: list of (start, end, pairs) CUDA events around the fused kernel
 
     # ---- helpers -------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -147,7 +148,13 @@ class CudaBackend:
             a.partials = partials.data_ptr()
         if energy_out is not None:
             a.energy_out, a.lde, a.energy_mult = energy_out.data_ptr(), energy_out.stride(0), float(energy_mult)
+        if self.kernel_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(self.lib.pdm_posterior_stats(C.byref(a), self._stream()), "pdm_posterior_stats")
+        if self.kernel_events is not None:
+            ev1.record()
+            self.kernel_events.append((ev0, ev1, M * N))
         self.launches += 1
         self.last_plan = (a.n_splits, a.m_group, a.cta_group)
         del keep
@@ -166,6 +173,16 @@ class CudaBackend:
                                           self._stream()), "pdm_merge_partials")
         self.launches += 1
         return out, argmin
+
+    def reduce(self, parts: Tensor, inv_temp: Tensor) -> Tensor:
+        """(M, S, 8) -> (M, 1, 8): one merged, not yet finalised, record per row."""
+        parts = parts.contiguous()
+        m, s, _ = parts.shape
+        out = torch.empty(m, 1, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_reduce_partials(parts.data_ptr(), m, 1, 0, s, parts.stride(0), inv_temp.data_ptr(),
+                                           out.data_ptr(), self._stream()), "pdm_reduce_partials")
+        self.launches += 1
+        return out
 
     # ---- posterior mean ------------------------------------------------------------------------
     def weights_from_energy(self, energy: Tensor, e_min: Tensor, l: Tensor, inv_temp: Tensor, *, split: bool):

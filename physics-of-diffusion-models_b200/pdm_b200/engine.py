@@ -113,6 +113,8 @@ class EngineConfig:
     n_splits: int = 0
     max_query_bytes: int = 2 << 30     # scratch budget for one block of query rows (noise + split)
     max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
+    sync_noise: bool = True            # sharded runs: broadcast rank 0's noise (set False when every rank
+                                       # seeds its generator identically and draws the same stream)
 
     @staticmethod
     def from_env() -> "EngineConfig":
@@ -174,8 +176,9 @@ class PosteriorEngine:
     def _merge(self, parts: Tensor, inv_temp: Tensor):
         if self.world > 1:
             import torch.distributed as dist
-            gathered = torch.empty((self.world,) + tuple(parts.shape), dtype=parts.dtype, device=parts.device)
-            dist.all_gather_into_tensor(gathered, parts.contiguous(), group=self.group)
+            local = self.backend.reduce(parts, inv_temp)          # 32 B per row cross the link, not 32 B per split
+            gathered = torch.empty((self.world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
             parts = gathered
         return self.backend.merge(parts, inv_temp, self.ds.n_total)
 
@@ -225,7 +228,7 @@ class PosteriorEngine:
             noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
             for i in range(nb):
                 noise[i].copy_(draw(t0 + i).reshape(b, -1))
-            if self.world > 1 and noise_fn is None:
+            if self.world > 1 and self.cfg.sync_noise:
                 import torch.distributed as dist
                 dist.broadcast(noise, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                                group=self.group)
@@ -239,8 +242,10 @@ class PosteriorEngine:
         return res
 
     # -- posterior mean ---------------------------------------------------------------------------
-    def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None) -> Tensor:
-        """x0_hat[r] = sum_j p_rj y_j with p ~ exp(-||x_r*post_r - y_j||^2 / (2 T_r)).  Returns (M, d)."""
+    def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None,
+                       values: Optional[Tensor] = None) -> Tensor:
+        """x0_hat[r] = sum_j p_rj y_j with p ~ exp(-||x_r*post_r - y_j||^2 / (2 T_r)).  Returns (M, d).
+        ``values`` (N, dv) replaces y_j in the weighted sum (posterior mean of arbitrary per-point vectors)."""
         dev = self.backend.device
         ds = self.ds
         xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
@@ -250,7 +255,15 @@ class PosteriorEngine:
             post = post.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
         precision = self.precision()
         tensor = precision != "exact"
-        out = torch.empty(m, ds.d, dtype=torch.float32, device=dev)
+        vt = None
+        if values is not None:
+            values = values.reshape(values.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+            if values.shape[0] != ds.n:
+                raise PdmError("values must have one row per dataset row")
+            if tensor:
+                vscale = pow2_scale_for(float(self.backend.absmax(values).item()))
+                vt = self.backend.transpose_split(values, vscale) + (vscale,)
+        out = torch.empty(m, ds.d if values is None else values.shape[1], dtype=torch.float32, device=dev)
         step = max(128, min(m, self.cfg.max_energy_bytes // (ds.n * 8)))
         for r0 in range(0, m, step):
             r1 = min(m, r0 + step)
@@ -263,12 +276,12 @@ class PosteriorEngine:
             e_min, l = st[_cabi.OUT_E_MIN], st[_cabi.OUT_L]
             if tensor:
                 p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
-                yt_hi, yt_lo = ds.transposed_split()
-                self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / ds.scale, out=out[r0:r1],
+                yt_hi, yt_lo, yscale = vt if vt is not None else (ds.transposed_split() + (ds.scale,))
+                self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=out[r0:r1],
                                         cta_group=self.cfg.cta_group)
             else:
                 p = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=False)
-                self.backend.weighted_mean_exact(p, ds.y, out=out[r0:r1])
+                self.backend.weighted_mean_exact(p, ds.y if values is None else values, out=out[r0:r1])
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out, group=self.group)

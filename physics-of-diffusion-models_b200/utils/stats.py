@@ -1,0 +1,249 @@
+"""Drop-in for the reference's ``utils/stats.py`` on the B200 engine.
+
+Public names, argument order, defaults, returned keys and the CPU residency of results follow the
+reference (utils/stats.py:14-23, 116-125, 261, 295-300, 314): callers pass a ``DataLoader`` over the
+training set plus a generator of query batches and get CPU tensors they ``np.savez``.
+
+What changed underneath:
+  * the dataset is read from the loader ONCE per loader object and kept resident in HBM with its row
+    norms and fp16 operand split (the reference re-reads it for every temperature, utils/stats.py:276,
+    or every batch, :31-35) -- with ``data_augmentation`` switched on this freezes one augmentation
+    draw per loader instead of one per temperature;
+  * all temperatures of the schedule are flattened into the rows of a few fused launches: distances,
+    the min-shifted log-sum-exp and the energy moments never materialise a (B, N) matrix;
+  * the noise is still drawn with one ``torch.randn(*x0_traj.shape, device=...)`` per temperature, in
+    schedule order, so a seeded run sees the reference's CUDA RNG stream (utils/stats.py:74, :273).
+There is no CPU path: without the CUDA library or a GPU these functions raise ``PdmError``.
+"""
+from __future__ import annotations
+
+import math
+import os
+import weakref
+from collections import defaultdict
+from typing import Generator, Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.utils.data import DataLoader
+from tqdm import tqdm
+
+from pdm_b200 import EmpiricalDataset, PosteriorEngine
+from pdm_b200.engine import default_backend
+
+_ENGINES: dict[int, tuple] = {}
+
+
+def _sharding_group():
+    """Row-shard the dataset over torch.distributed's default group when PDM_SHARD_DATASET=1."""
+    if os.environ.get("PDM_SHARD_DATASET", "0") != "1":
+        return None, 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    return dist.group.WORLD, dist.get_rank(), dist.get_world_size()
+
+
+def _engine_for(dataloader: DataLoader) -> PosteriorEngine:
+    """One resident dataset (and engine) per DataLoader object."""
+    key = id(dataloader)
+    hit = _ENGINES.get(key)
+    if hit is not None and hit[0]() is dataloader:
+        return hit[1]
+    backend = default_backend()
+    chunks = [batch[0].to(backend.device, non_blocking=True) for batch in dataloader]
+    data = torch.cat(chunks, dim=0)
+    group, rank, world = _sharding_group()
+    n_total = data.shape[0]
+    if world > 1:
+        per = (n_total + world - 1) // world
+        lo, hi = rank * per, min(n_total, (rank + 1) * per)
+        amax = float(data.abs().max().item())
+        ds = EmpiricalDataset(data[lo:hi], backend=backend, index_offset=lo, n_total=n_total, global_absmax=amax)
+        ds.full_moments_source = data          # Tr Sigma_0 is a whole-dataset quantity
+    else:
+        ds = EmpiricalDataset(data, backend=backend)
+    eng = PosteriorEngine(ds, group=group)
+    _ENGINES[key] = (weakref.ref(dataloader, lambda _r, k=key: _ENGINES.pop(k, None)), eng)
+    return eng
+
+
+def _dataset_summary(eng: PosteriorEngine) -> tuple[float, float, float]:
+    """(Tr Sigma_0, min, max) of the whole dataset, computed once (utils/stats.py:39, 66, 176)."""
+    cached = getattr(eng, "_summary", None)
+    if cached is None:
+        src = getattr(eng.ds, "full_moments_source", None)
+        ds = eng.ds if src is None else EmpiricalDataset(src, backend=eng.backend)
+        lo, hi = ds.value_range()
+        cached = (ds.tr_sigma0(), lo, hi)
+        eng._summary = cached
+    return cached
+
+
+def _knn_sigma_reg_sq(eng: PosteriorEngine, knn_k: int, sigma_reg_scale: float) -> Tensor:
+    """d_k^2 * scale / D with d_k the distance to the k-th neighbour, self excluded
+    (utils/stats.py:137-146, where sklearn's kneighbors(k+1) runs on the CPU)."""
+    ds = eng.ds
+    if eng.world > 1:
+        raise NotImplementedError("adaptive k-NN regularisation is not available with a sharded dataset yet")
+    out = torch.empty(ds.n, dtype=torch.float32, device=ds.y.device)
+    step = max(1, min(ds.n, (1 << 30) // (4 * ds.n)))
+    for r0 in range(0, ds.n, step):
+        d2 = eng.pairwise_sqdist(ds.y[r0:r0 + step])
+        kth = torch.topk(d2, knn_k + 1, dim=1, largest=False).values[:, -1]
+        out[r0:r0 + step] = kth.clamp_(min=0)
+    return out * sigma_reg_scale / float(ds.d)
+
+
+def _gaussian_cluster_metric(sigma_sq: Tensor, t: Tensor) -> Tensor:
+    """Metric of an isotropic Gaussian cluster of variance sigma^2 at temperature T (utils/stats.py:102,107)."""
+    return 0.5 * sigma_sq * (sigma_sq + 2 * t) / (sigma_sq + t).pow(2)
+
+
+def compute_metric_stats_batch(
+    dataloader: DataLoader,
+    x0_traj: Tensor,
+    temp: Tensor,
+    regularize: bool = False,
+    adaptive_knn: bool = False,
+    knn_k: int = 5,
+    sigma_reg_scale: float = 1.0,
+    precomputed_sigma_reg_sq: Optional[Tensor] = None,
+) -> dict[str, Tensor]:
+    """Var_w(E/T) per temperature, averaged over the batch (utils/stats.py:14-113)."""
+    eng = _engine_for(dataloader)
+    dev = eng.backend.device
+    tr_sigma0, lo, hi = _dataset_summary(eng)
+
+    aux: Optional[Tensor] = None
+    if regularize and adaptive_knn:
+        if precomputed_sigma_reg_sq is not None:
+            aux = precomputed_sigma_reg_sq.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            aux = _knn_sigma_reg_sq(eng, knn_k, sigma_reg_scale)
+    if lo < -2 or hi > 2:
+        print(f"Warning: Data range [{lo:.2f}, {hi:.2f}] is unexpected (expected [-1, 1]).")
+    print(f"Dataset D={eng.ds.d}, Tr(Sigma0)={tr_sigma0:.4f}")
+
+    st = eng.noised_stats(x0_traj, temp, aux=aux)
+    var = st["var_e"]                                        # (n_T, B)
+    if regularize:
+        t = temp.to(device=dev, dtype=torch.float32).reshape(-1, 1)
+        sigma_sq = st["aux_mean"] if aux is not None else torch.tensor(1e-3, device=dev)
+        var = torch.maximum(var, _gaussian_cluster_metric(sigma_sq, t))
+    return {"metric_values": var.mean(dim=1).to(torch.float32).cpu()}
+
+
+def compute_metric_stats(
+    dataloader: DataLoader,
+    data_generator: Generator[tuple[Tensor, ...], None, None],
+    temp: Tensor,
+    n_samples: int,
+    regularize: bool = False,
+    adaptive_knn: bool = False,
+    knn_k: int = 5,
+    sigma_reg_scale: float = 1.0,
+) -> dict[str, Tensor]:
+    """Batch loop + mean of compute_metric_stats_batch, plus Tr Sigma_0 (utils/stats.py:116-183)."""
+    eng = _engine_for(dataloader)
+    pre_sigma = _knn_sigma_reg_sq(eng, knn_k, sigma_reg_scale) if (regularize and adaptive_knn) else None
+
+    per_batch: list[Tensor] = []
+    with tqdm(total=n_samples, desc="Computing metric stats...") as pbar:
+        remaining = n_samples
+        while remaining > 0:
+            x0_traj = next(data_generator)[0]
+            per_batch.append(compute_metric_stats_batch(
+                dataloader, x0_traj, temp, regularize=regularize, adaptive_knn=adaptive_knn, knn_k=knn_k,
+                sigma_reg_scale=sigma_reg_scale, precomputed_sigma_reg_sq=pre_sigma)["metric_values"])
+            remaining -= len(x0_traj)
+            pbar.update(len(x0_traj))
+    metric = torch.stack(per_batch, dim=1).mean(dim=1)
+    return {
+        "temp": temp,
+        "metric": metric,
+        "log_temp": temp.log(),
+        "dataset_tr_sigma0": torch.tensor(_dataset_summary(eng)[0]),
+    }
+
+
+@torch.no_grad()
+def compute_model_metric_stats_batch(ddpm: torch.nn.Module, x0_traj: Tensor, temp: Tensor) -> dict[str, Tensor]:
+    """Model-based metric 0.5 * E||x0 - x0_hat||^2 / T (utils/stats.py:186-216).  Not part of the
+    closed-form hot path: it only calls ``ddpm.get_predictions``; kept so the module's API is complete
+    (with ``DDPMTrue`` the prediction itself runs on the engine)."""
+    dev = "cuda" if torch.cuda.is_available() else "cpu"       # get_default_device(), utils/utils.py:158-163
+    temp = temp.to(dev)
+    x0 = x0_traj.to(dev)
+    vals = []
+    for t in temp:
+        xt = torch.randn_like(x0) * t.sqrt() + x0
+        x0_hat = ddpm.get_predictions(xt, t.log().view(1)).x0
+        mse = ((x0 - x0_hat).reshape(len(x0), -1) ** 2).sum(dim=1).mean()
+        vals.append((0.5 * mse / t).detach().cpu())
+    return {"metric_values": torch.stack(vals)}
+
+
+def compute_model_metric_stats(dataloader: DataLoader, data_generator, ddpm: torch.nn.Module, temp: Tensor,
+                               n_samples: int) -> dict[str, Tensor]:
+    """utils/stats.py:219-254."""
+    ddpm.eval()
+    per_batch = []
+    with tqdm(total=n_samples, desc="Computing model-based metric stats...") as pbar:
+        remaining = n_samples
+        while remaining > 0:
+            x0_traj = next(data_generator)[0]
+            per_batch.append(compute_model_metric_stats_batch(ddpm, x0_traj, temp)["metric_values"])
+            remaining -= len(x0_traj)
+            pbar.update(len(x0_traj))
+    eng = _engine_for(dataloader)
+    return {
+        "temp": temp,
+        "metric": torch.stack(per_batch, dim=1).mean(dim=1),
+        "log_temp": temp.log(),
+        "dataset_tr_sigma0": torch.tensor(_dataset_summary(eng)[0]),
+    }
+
+
+def compute_average(p: Tensor, vals: Tensor) -> Tensor:
+    """sum_j p_j v_j over the last axis (utils/stats.py:257-258; unused by the reference's scripts)."""
+    return (p * vals).sum(dim=-1)
+
+
+def compute_stats_batch(dataloader: DataLoader, x0_traj: Tensor, temp: Tensor) -> dict[str, Tensor]:
+    """Posterior entropy S = logZ' + <E'>/T - log N per query and temperature (utils/stats.py:261-292).
+    Returns {"entropy": (n_T, B)} on the CPU."""
+    eng = _engine_for(dataloader)
+    st = eng.noised_stats(x0_traj, temp)
+    return {"entropy": st["entropy"].cpu()}
+
+
+def compute_stats(dataloader: DataLoader, data_generator, temp: Tensor, n_samples: int) -> dict[str, Tensor]:
+    """Batch loop + mean over all queries (utils/stats.py:295-311)."""
+    acc: dict[str, list[Tensor]] = defaultdict(list)
+    with tqdm(total=n_samples, desc="Computing stats...") as pbar:
+        remaining = n_samples
+        while remaining > 0:
+            x0_traj = next(data_generator)[0]
+            for k, v in compute_stats_batch(dataloader, x0_traj, temp).items():
+                acc[k].append(v)
+            remaining -= len(x0_traj)
+            pbar.update(len(x0_traj))
+    stats = {k: torch.cat(v, dim=1).mean(dim=1) for k, v in acc.items()}
+    stats["temp"] = temp
+    return stats
+
+
+def extrapolate_entropy(temp: Tensor, entropy: Tensor, min_temp: float) -> tuple[Tensor, Tensor]:
+    """Log-linear continuation of the entropy curve below its steepest segment (utils/stats.py:314-322).
+    Tiny CPU post-processing on (n_T,) vectors."""
+    if temp[0] != min_temp:
+        temp = torch.cat([torch.full((1,), min_temp), temp])
+        entropy = torch.cat([entropy[:1].clone(), entropy])
+    log_t = temp.log()
+    slope = entropy.diff() / log_t.diff()
+    k = int(torch.argmax(slope))
+    k -= int(k == len(temp))
+    head = (log_t[:k] - log_t[k]) * slope[k] + entropy[k]
+    return temp, torch.cat((head, entropy[k:]), dim=0)

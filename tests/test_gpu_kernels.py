@@ -6,7 +6,7 @@ entropy, posterior mean and E_min within 1e-4 relative of the reference on ident
 fp64 oracle arbitrates when the reference's own fp32 cancellation noise is larger:
     |ours - ref64| <= max(rtol*|ref64| + atol, 2*|ref32 - ref64|, floor);  arg-min indices bit-exact.
 `floor` is the a-priori round-off of ANY fp32 evaluation of ||x||^2 - 2x.y + ||y||^2 (the reference's
-formula, utils/distance.py:21): a few units of 2^-24 * (||x||^2 + ||y||^2) on an energy, divided by T on the
+formula, utils/distance.py:21): 8 * 2^-24 * (||x||^2 + ||y||^2) on an energy, divided by T on the
 min-shifted exponents.  The reference's own outputs move by that much between BLAS builds, so no
 implementation can be held closer to the fp64 value than that.
 """
@@ -51,10 +51,10 @@ def oracle_rows(xq, data, temp_rows, aux=None):
         st = orc.boltzmann_rows(e, temp_rows.to(dt)[:, None], aux=None if aux is None else aux.to(dt))
         st["entropy"] = st["log_l"] + st["mean_e"] - math.log(len(data))
         res[name] = st
-    # fp32 round-off floor of the norm expansion: 4 * 2^-24 * (||x||^2 + max ||y||^2) on E, / T on e
+    # fp32 round-off floor of the norm expansion: 8 * 2^-24 * (||x||^2 + max ||y||^2) on E, / T on e
     xn = (xq.double().reshape(len(xq), -1) ** 2).sum(1)
     yn = (data.double().reshape(len(data), -1) ** 2).sum(1).max()
-    res["floor_E"] = 4 * 2.0 ** -24 * (xn + yn)
+    res["floor_E"] = 8 * 2.0 ** -24 * (xn + yn)
     res["floor_e"] = res["floor_E"] / temp_rows.double()
     return res
 

@@ -44,13 +44,15 @@ def main():
                                       n_splits=ns)
         run()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.iters):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
+        evs[0].record()
+        for i in range(a.iters):
             parts = run()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / a.iters
+        each = [evs[i].elapsed_time(evs[i + 1]) for i in range(a.iters)]
+        ms = sum(each) / a.iters
+        print("   per-iter ms:", " ".join(f"{v:.2f}" for v in each), flush=True)
         pairs = a.m * a.n
         terms = 3 if a.precision == "f16x3" else 1
         print(f"cfg cg={cg} plan(S,G,cg)={be.last_plan}: {ms:.3f} ms  {pairs / ms / 1e6:.2f} Gpairs/s  "
