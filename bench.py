@@ -226,6 +226,7 @@ def run_ours(args):
         step(i)
     barrier()
     backend.kernel_events = []
+    backend.phase_events = {} if os.environ.get("PDM_BENCH_PHASES") else None
     launches0 = backend.launches
     sampler = ClockSampler(local)
     if rank == 0:
@@ -243,6 +244,9 @@ def run_ours(args):
     ms_total = float(ms.item())
     launches = backend.launches - launches0
     # fused-kernel time from the CUDA events recorded around its launches on the launching stream
+    if backend.phase_events is not None and rank == 0:
+        print("phase ms/step:", {k: round(v / max(1, args.steps), 2) for k, v in backend.phase_totals().items()}, file=sys.stderr)
+    backend.phase_events = None
     kev = backend.kernel_events
     backend.kernel_events = None
     k_ms = sum(a.elapsed_time(bb) for a, bb, _ in kev)

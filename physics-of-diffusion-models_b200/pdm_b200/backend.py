@@ -40,6 +40,31 @@ class CudaBackend:
         self.launches = 0          # kernels of ours launched through this backend (bench reports it)
         self.kernel_events = None  # bench hook: list of (start, end, pairs) CUDA events around the fused kernel
 
+    # ---- optional phase timing (dev / bench): CUDA events on the launching stream ----------------
+    def phase(self, name: str):
+        """Context manager: when ``self.phase_events`` is a dict, records (start, end) events per phase."""
+        backend = self
+
+        class _Phase:
+            def __enter__(self_inner):
+                self_inner.on = getattr(backend, "phase_events", None) is not None
+                if self_inner.on:
+                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e0.record()
+
+            def __exit__(self_inner, *exc):
+                if self_inner.on:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    backend.phase_events.setdefault(name, []).append((self_inner.e0, e1))
+                return False
+
+        return _Phase()
+
+    def phase_totals(self) -> dict:
+        ev = getattr(self, "phase_events", None) or {}
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in ev.items()}
+
     # ---- helpers -------------------------------------------------------------------------------
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -187,10 +187,17 @@ class PosteriorEngine:
         """Statistics for ``rows`` query rows; returns (out (8, rows), argmin (rows,)) device tensors.
         Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional)."""
         precision = self.precision()
+        ph = getattr(self.backend, "phase", None)
+        if ph is None:
+            import contextlib
+            ph = lambda _n: contextlib.nullcontext()      # noqa: E731  (test doubles without phase timing)
         inv_temp = (1.0 / temp_rows.to(torch.float32)).contiguous()
-        prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
-        parts = self._local_partials(prep, rows, inv_temp, aux, precision)
-        return self._merge(parts, inv_temp)
+        with ph("prepare"):
+            prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
+        with ph("fused"):
+            parts = self._local_partials(prep, rows, inv_temp, aux, precision)
+        with ph("merge"):
+            return self._merge(parts, inv_temp)
 
     def stats(self, x: Tensor, temp_rows: Tensor, aux: Optional[Tensor] = None) -> dict:
         """Per-row Boltzmann statistics of explicit queries x (M, ...) at per-row temperatures."""
@@ -225,9 +232,14 @@ class PosteriorEngine:
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
-            noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
-            for i in range(nb):
-                noise[i].copy_(draw(t0 + i).reshape(b, -1))
+            ph = getattr(self.backend, "phase", None)
+            if ph is None:
+                import contextlib
+                ph = lambda _n: contextlib.nullcontext()  # noqa: E731
+            with ph("noise"):
+                noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
+                for i in range(nb):
+                    noise[i].copy_(draw(t0 + i).reshape(b, -1))
             if self.world > 1 and self.cfg.sync_noise:
                 import torch.distributed as dist
                 dist.broadcast(noise, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
