@@ -127,6 +127,18 @@ def draw_noised_queries(x0: Tensor, temp: Tensor, *, loader_iters: str = "none",
     return torch.stack(out).to(dtype)
 
 
+def draw_noise(shape, n_temps: int, *, loader_iters: str = "none") -> Tensor:
+    """The raw standard-normal draws behind ``draw_noised_queries`` (same RNG call order), (n_T, *shape)."""
+    out = []
+    if loader_iters == "once_before":
+        _dataloader_seed_draw()
+    for _ in range(n_temps):
+        out.append(torch.randn(*shape))
+        if loader_iters == "per_temp":
+            _dataloader_seed_draw()
+    return torch.stack(out)
+
+
 def entropy_batch(xt: Tensor, data: Tensor, temp: Tensor, *, chunk: Optional[int] = None,
                   dtype=torch.float32) -> Tensor:
     """``compute_stats_batch`` for given noised queries xt (n_T,B,...).

@@ -130,6 +130,9 @@ class PosteriorEngine:
     must present the same query rows, partial records are all-gathered and merged.
     """
 
+    # test hook: callable (temperature index, shape, device) -> standard-normal tensor replacing torch.randn
+    noise_hook = None
+
     def __init__(self, dataset: EmpiricalDataset, config: Optional[EngineConfig] = None, group=None):
         self.ds = dataset
         self.backend = dataset.backend
@@ -177,9 +180,10 @@ class PosteriorEngine:
         if self.world > 1:
             import torch.distributed as dist
             local = self.backend.reduce(parts, inv_temp)          # 32 B per row cross the link, not 32 B per split
-            gathered = torch.empty((self.world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-            dist.all_gather_into_tensor(gathered, local, group=self.group)
-            parts = gathered
+            gathered = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                                   device=local.device)
+            dist.all_gather_into_tensor(gathered, local, group=self.group)     # rank-major concatenation
+            parts = gathered.view((self.world,) + tuple(local.shape))
         return self.backend.merge(parts, inv_temp, self.ds.n_total)
 
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
@@ -228,6 +232,8 @@ class PosteriorEngine:
         n_t = temp.shape[0]
         t_per_block = max(1, self.rows_per_block() // b)
         outs, idxs = [], []
+        if noise_fn is None and PosteriorEngine.noise_hook is not None:
+            noise_fn = lambda i: PosteriorEngine.noise_hook(i, tuple(x0.shape), dev)     # noqa: E731
         draw = noise_fn if noise_fn is not None else (lambda i: torch.randn(*x0.shape, device=dev))
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)

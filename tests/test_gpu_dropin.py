@@ -1,0 +1,164 @@
+"""GPU parity of the reference-facing drop-in modules (utils.distance / utils.stats / utils.metric_utils /
+Scheduler.true_posterior_mean_x0 / DDPMTrue) against the reference's golden outputs and the fp64 oracle.
+The reference draws its noise on the device RNG; to feed IDENTICAL noised queries the engine's noise hook
+replays the CPU draws the golden run used (the noising itself, eps*sqrt(T)+x0, runs in our CUDA kernel and is
+bit-identical to torch's)."""
+import math
+
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+from conftest import load_golden
+from oracle import posterior as orc
+from oracle import synthetic as syn
+from test_gpu_kernels import arbitrated_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def replay_noise(cuda_device):
+    from pdm_b200 import PosteriorEngine
+    import utils.stats as ustats
+    ustats._ENGINES.clear()
+
+    def install(eps):
+        PosteriorEngine.noise_hook = staticmethod(lambda i, shape, dev: eps[i].reshape(shape).to(dev))
+    yield install
+    PosteriorEngine.noise_hook = None
+
+
+def _floor(xt, data, temp):
+    xn = (xt.double().reshape(xt.shape[0], xt.shape[1], -1) ** 2).sum(-1)
+    yn = (data.double().reshape(len(data), -1) ** 2).sum(1).max()
+    return 8 * 2.0 ** -24 * (xn + yn) / temp.double()[:, None]
+
+
+@pytest.mark.parametrize("name", ["stats_gmm.npz", "stats_images.npz", "stats_clustered.npz"])
+def test_compute_stats_batch(replay_noise, name):
+    import utils
+    g = load_golden(name)
+    torch.manual_seed(int(g["seed"]))
+    eps = orc.draw_noise(g["x0"].shape, len(g["temp"]), loader_iters="per_temp")
+    replay_noise(eps)
+    loader = DataLoader(TensorDataset(g["data"]), batch_size=int(g["dl_bs"]), shuffle=False)
+    ent = utils.compute_stats_batch(loader, g["x0"], g["temp"])["entropy"]
+    assert ent.device.type == "cpu" and ent.shape == g["entropy"].shape
+    ref64 = orc.entropy_batch(g["xt"], g["data"], g["temp"], dtype=torch.float64)
+    arbitrated_close(ent, g["entropy"], ref64, atol=2e-5, floor=2 * _floor(g["xt"], g["data"], g["temp"]),
+                     what=name + " entropy")
+
+
+@pytest.mark.parametrize("name", ["stats_gmm.npz", "stats_images.npz"])
+def test_compute_metric_stats_batch(replay_noise, name, capsys):
+    import utils
+    g = load_golden(name)
+    torch.manual_seed(int(g["seed"]))
+    eps = orc.draw_noise(g["x0"].shape, len(g["temp"]), loader_iters="once_before")
+    replay_noise(eps)
+    loader = DataLoader(TensorDataset(g["data"]), batch_size=int(g["dl_bs"]), shuffle=False)
+    sig = orc.knn_sigma_reg_sq(g["data"], int(g["knn_k"]), float(g["sigma_reg_scale"]))
+    xm = g["xt_metric"]
+    for tag, kw, okw in (("plain", {}, {}), ("global", {"regularize": True}, {"regularize": True}),
+                         ("knn", {"regularize": True, "adaptive_knn": True, "knn_k": int(g["knn_k"]),
+                                  "sigma_reg_scale": float(g["sigma_reg_scale"])},
+                          {"regularize": True, "sigma_reg_sq_per_point": sig})):
+        got = utils.compute_metric_stats_batch(loader, g["x0"], g["temp"], **kw)["metric_values"]
+        ref64 = orc.metric_batch(xm, g["data"], g["temp"], dtype=torch.float64, **okw)
+        st64 = orc.boltzmann_rows(0.5 * orc.pairwise_sqdist(xm[0].double(), g["data"].double()), g["temp"][0].double())
+        fl = (_floor(xm, g["data"], g["temp"]) * (1 + 2 * 10.0)).mean(1)
+        arbitrated_close(got, g[f"metric_{tag}"], ref64, atol=2e-5, floor=fl, what=f"{name} metric {tag}")
+    assert "Tr(Sigma0)=" in capsys.readouterr().out
+
+
+def test_knn_regulariser_on_gpu(cuda_device):
+    from utils.stats import _engine_for, _knn_sigma_reg_sq
+    g = load_golden("stats_images.npz")
+    loader = DataLoader(TensorDataset(g["data"]), batch_size=100, shuffle=False)
+    sig = _knn_sigma_reg_sq(_engine_for(loader), 5, 1.0).cpu()
+    torch.testing.assert_close(sig, orc.knn_sigma_reg_sq(g["data"], 5, 1.0), rtol=1e-4, atol=1e-6)
+
+
+def test_distance_dropin(cuda_device):
+    import utils
+    g = load_golden("distance.npz")
+    for dev in ("cpu", cuda_device):
+        x, y = g["x"].to(dev), g["y"].to(dev)
+        d = utils.compute_pw_dist_sqr(x, y)
+        assert d.device == x.device
+        arbitrated_close(d, g["pw_xy"], orc.pairwise_sqdist(g["x"].double(), g["y"].double()), atol=2e-5, what="pw_xy")
+    arbitrated_close(utils.compute_pw_dist_sqr(g["x"]), g["pw_xx"], orc.pairwise_sqdist(g["x"].double()), atol=2e-5,
+                     what="pw_xx")
+    torch.testing.assert_close(utils.norm_sqr(g["x"].reshape(7, -1)), g["norm_x"], rtol=2e-7, atol=0)
+    torch.testing.assert_close(utils.compute_gram_matrix(g["x"].reshape(7, -1), g["y"].reshape(11, -1)), g["gram_xy"],
+                               rtol=1e-5, atol=1e-5)
+    # nearest / second-nearest neighbour flow of scripts/analyze_cifar_nn.py:37-47: indices bit-exact
+    d = utils.compute_pw_dist_sqr(g["pts"].to(cuda_device))
+    d.fill_diagonal_(1e10)
+    nn1, i1 = d.min(dim=1)
+    assert torch.equal(i1.cpu(), g["nn1_idx"])
+    d.scatter_(1, i1.unsqueeze(1), 1e10)
+    assert torch.equal(d.min(dim=1).indices.cpu(), g["nn2_idx"])
+
+
+def test_denoiser_dropin(cuda_device):
+    from diffusion import DDPMTrue
+    from diffusion.scheduler import LinearBetaScheduler
+    g = load_golden("denoiser.npz")
+    sch = LinearBetaScheduler(float(g["min_temp"]), float(g["max_temp"]))
+    model = DDPMTrue(sch, "x0", g["data"]).to(cuda_device)
+    assert model.train_data.device.type == "cuda"
+    for i, tau in enumerate(g["taus"]):
+        xt = g[f"xt_{i}"].to(cuda_device)
+        got = model(xt, tau.view(1).to(cuda_device))
+        assert got.shape == xt.shape and got.device == xt.device and got.dtype == torch.float32
+        ref64 = orc.posterior_mean_x0(g[f"xt_{i}"], g[f"alpha_bar_{i}"], g["data"], dtype=torch.float64)
+        arbitrated_close(got, g[f"x0hat_{i}"], ref64, atol=2e-5, what=f"x0hat tau#{i}")
+        with torch.autocast("cuda", dtype=torch.float16):                  # autocast must not leak in (scheduler.py:58)
+            got16 = model(xt.half(), tau.view(1).to(cuda_device))
+        assert got16.dtype == torch.float32
+
+
+def test_denoiser_cifar_slice(cuda_device):
+    from diffusion.scheduler import LinearBetaScheduler
+    g = load_golden("cifar_slice.npz")
+    n, b = int(g["n"]), int(g["b"])
+    data = syn.uniform_images(n, (3, 32, 32), int(g["data_seed"]))
+    sch = LinearBetaScheduler(1e-4, 2.478e4)
+    ab = torch.sigmoid(-orc.linear_beta_log_temp(g["tau"], 1e-4, 2.478e4))
+    xq = ab.sqrt() * data[:b] + (1 - ab).sqrt() * torch.randn(b, 3, 32, 32, generator=syn.gen(int(g["q_seed"])))
+    got = sch.true_posterior_mean_x0(xq.to(cuda_device), g["tau"].to(cuda_device), data.to(cuda_device))
+    ref64 = orc.posterior_mean_x0(xq, ab, data, dtype=torch.float64)
+    arbitrated_close(got, g["x0hat"], ref64, atol=5e-5, what="cifar x0hat (tensor path)")
+
+
+def test_metric_utils_dropin(cuda_device):
+    import utils
+    g = load_golden("metric_utils.npz")
+    x, n_y = g["x"], int(g["n_y"])
+    idx, eps = g["idx"], g["eps"]
+    # feed the golden run's (idx, eps) draws: patch the two RNG calls of the module
+    import utils.metric_utils as mu
+
+    class _Replay:
+        def __enter__(self):
+            self.ri, self.rn = torch.randint, torch.randn
+            mu.torch.randint = lambda *a, **k: idx.to(k.get("device", "cpu"))
+            mu.torch.randn = lambda *a, **k: eps.to(k.get("device", "cpu"))
+
+        def __exit__(self, *exc):
+            mu.torch.randint, mu.torch.randn = self.ri, self.rn
+
+    with _Replay():
+        for i in range(3):
+            got = utils.compute_metric_scalar(float(g[f"scalar_log_sigma_sq_{i}"]), x, n_y)
+            torch.testing.assert_close(got, g[f"scalar_{i}"], rtol=2e-3, atol=2e-3)
+        got = utils.compute_metric_matrix(torch.diag(g["matrix_lambda"]), x, n_y)
+        torch.testing.assert_close(got, g["matrix"], rtol=5e-3, atol=5e-3)
+        got = utils.compute_rescaled_metric_matrix(g["rescaled_sigma"], x, n_y)
+        torch.testing.assert_close(got, g["rescaled"], rtol=5e-3, atol=5e-3)
+        xd = x.to(cuda_device)
+        got = utils.compute_metric_scalar(0.0, xd, n_y)
+        assert got.device.type == "cuda"
+        torch.testing.assert_close(got.cpu(), g["scalar_1"], rtol=2e-3, atol=2e-3)
