@@ -234,7 +234,7 @@ class PosteriorEngine:
         outs, idxs = [], []
         if noise_fn is None and PosteriorEngine.noise_hook is not None:
             noise_fn = lambda i: PosteriorEngine.noise_hook(i, tuple(x0.shape), dev)     # noqa: E731
-        draw = noise_fn if noise_fn is not None else (lambda i: torch.randn(*x0.shape, device=dev))
+        draw = noise_fn
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
@@ -245,7 +245,11 @@ class PosteriorEngine:
             with ph("noise"):
                 noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
                 for i in range(nb):
-                    noise[i].copy_(draw(t0 + i).reshape(b, -1))
+                    if draw is None:
+                        # same generator calls as torch.randn(*x0.shape, device=dev), written in place
+                        torch.randn(*x0.shape, device=dev, out=noise[i].view(x0.shape))
+                    else:
+                        noise[i].copy_(draw(t0 + i).reshape(b, -1))
             if self.world > 1 and self.cfg.sync_noise:
                 import torch.distributed as dist
                 dist.broadcast(noise, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
