@@ -277,10 +277,51 @@ __global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ 
                                                       const float* __restrict__ e_min, const float* __restrict__ l,
                                                       const float* __restrict__ inv_temp,
                                                       float* __restrict__ p32, int64_t ldp32,
-                                                      __half* __restrict__ ph, __half* __restrict__ pl, int64_t ldph) {
+                                                      __half* __restrict__ ph, __half* __restrict__ pl, int64_t ldph, int vec) {
     const int64_t row = blockIdx.y;
     const float m = e_min[row], it = inv_temp[row], inv_l = 1.f / l[row];
     const int64_t width = ph ? ldph : N;
+    if (vec) {
+        // 8 columns per thread: two 128-bit energy loads, one 128-bit store per fp16 plane
+        const int64_t groups = width >> 3;
+        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t j0 = g << 3;
+            float e[8];
+            if (j0 + 8 <= N) {
+                const float4 a = ldg_f4(energy + row * lde + j0), b = ldg_f4(energy + row * lde + j0 + 4);
+                e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = (j0 + k < N) ? __ldg(energy + row * lde + j0 + k) : INFINITY;
+            }
+            __half h[8], lo[8];
+            float pv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float ee = fminf((e[k] - m) * it, kMaxE);
+                pv[k] = (j0 + k < N) ? fast_exp2(-ee * kLog2e) * inv_l : 0.f;
+                split_f16(pv[k] * 16384.f, h[k], lo[k]);
+            }
+            if (ph) {
+                *reinterpret_cast<uint4*>(ph + row * ldph + j0) = *reinterpret_cast<uint4*>(h);
+                *reinterpret_cast<uint4*>(pl + row * ldph + j0) = *reinterpret_cast<uint4*>(lo);
+            }
+            if (p32 && j0 + 8 <= N) {
+                *reinterpret_cast<float4*>(p32 + row * ldp32 + j0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                *reinterpret_cast<float4*>(p32 + row * ldp32 + j0 + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+            } else if (p32) {
+                for (int k = 0; k < 8; ++k) if (j0 + k < N) p32[row * ldp32 + j0 + k] = pv[k];
+            }
+        }
+        // tail columns of an fp32-only output whose width is not a multiple of 8
+        if (!ph && blockIdx.x == 0) {
+            for (int64_t j = (groups << 3) + threadIdx.x; j < N; j += blockDim.x) {
+                const float ee = fminf((__ldg(energy + row * lde + j) - m) * it, kMaxE);
+                p32[row * ldp32 + j] = fast_exp2(-ee * kLog2e) * inv_l;
+            }
+        }
+        return;
+    }
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < width; j += (int64_t)gridDim.x * blockDim.x) {
         float p = 0.f;
         if (j < N) {
@@ -385,14 +426,16 @@ extern "C" int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t
     if (M == 0) return PDM_OK;
     PDM_REQUIRE(M <= 65535 * 1024LL, "pdm_weights_from_energy: M too large for one launch");
     const int64_t width = p_hi ? ldph : N;
+    const bool vec = lde % 4 == 0 && aligned16(energy) && (!p_hi || (aligned16(p_hi) && aligned16(p_lo))) &&
+                     (!p_f32 || (ldp32 % 4 == 0 && aligned16(p_f32)));
     for (int64_t r0 = 0; r0 < M; r0 += 65535) {
         const int64_t rows = std::min<int64_t>(65535, M - r0);
-        dim3 grid((unsigned)std::min<int64_t>(ceil_div(width, 256), 64), (unsigned)rows);
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div(width, vec ? 2048 : 256), 64), (unsigned)rows);
         weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(
             energy + r0 * lde, lde, rows, N, e_min + r0, l + r0, inv_temp + r0,
             p_f32 ? p_f32 + r0 * ldp32 : nullptr, ldp32,
             p_hi ? reinterpret_cast<__half*>(p_hi) + r0 * ldph : nullptr,
-            p_lo ? reinterpret_cast<__half*>(p_lo) + r0 * ldph : nullptr, ldph);
+            p_lo ? reinterpret_cast<__half*>(p_lo) + r0 * ldph : nullptr, ldph, vec ? 1 : 0);
         PDM_CUDA_CHECK(cudaGetLastError());
     }
     return PDM_OK;

@@ -187,14 +187,22 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                             const uint64_t a_lo = make_smem_desc_sw128(sb + kTileBytes);
                             const uint64_t b_hi = make_smem_desc_sw128(sb + (TERMS == 3 ? 2 : 1) * kTileBytes);
                             const uint64_t b_lo = make_smem_desc_sw128(sb + 3 * kTileBytes);
+                            // Small cross terms first: while the accumulator only holds them (2^-11 of the
+                            // final magnitude) the tensor core's truncation costs nothing; the four large
+                            // hi*hi products then go in last (16 fp16 = 32 bytes = 2 descriptor units per k).
+                            if (TERMS == 3) {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k) {
-                                const uint64_t ko = (uint64_t)(k * 2);   // 16 fp16 = 32 bytes = 2 descriptor units
-                                umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                                if (TERMS == 3) {
-                                    umma_f16<CG>(d_tmem, a_lo + ko, b_hi + ko, C::kIdesc, 1u);
+                                for (int k = 0; k < kBlockK / 16; ++k) {
+                                    const uint64_t ko = (uint64_t)(k * 2);
+                                    umma_f16<CG>(d_tmem, a_lo + ko, b_hi + ko, C::kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
                                     umma_f16<CG>(d_tmem, a_hi + ko, b_lo + ko, C::kIdesc, 1u);
                                 }
+                            }
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc,
+                                             (TERMS == 3 || kb > kb0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit<CG>(empty_bar(stage));                 // smem slot reusable once these retire
                             if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(as)); // chunk accumulator complete
@@ -213,6 +221,10 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const int row_in_cta = quarter * 32 + lane;
             const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
             uint32_t chunk_iter = 0;
+            // 128-bit stores of the dense outputs need 16-byte aligned rows
+            const bool out_vec = (EPI == EPI_STATS)
+                ? (p.energy_out && (p.lde % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.energy_out) & 15) == 0))
+                : ((p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0));
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
                 const int64_t grow = (int64_t)(mt * CG + (int)rank) * kRowsPerCta + row_in_cta;
                 const bool row_ok = grow < p.M;
@@ -288,18 +300,34 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                                 }
                                 if (p.energy_out && row_ok) {
                                     float* eo = p.energy_out + grow * p.lde + col0;
+                                    if (full_chunk && out_vec) {
 #pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        if (full_chunk || col0 + i < p.ncols) eo[i] = p.energy_mult * E[i];
+                                        for (int i = 0; i < 8; ++i)
+                                            reinterpret_cast<float4*>(eo)[i] =
+                                                make_float4(p.energy_mult * E[4 * i], p.energy_mult * E[4 * i + 1],
+                                                            p.energy_mult * E[4 * i + 2], p.energy_mult * E[4 * i + 3]);
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < 32; ++i)
+                                            if (full_chunk || col0 + i < p.ncols) eo[i] = p.energy_mult * E[i];
+                                    }
                                 }
                                 if (p.partials) state_add_chunk<32, AUX>(st, E, ax, p.index_offset + col0, 1, inv_t);
                             } else if (row_ok) {
                                 float* o = p.out + grow * p.ldo + col0;
+                                if (full_chunk && out_vec && !p.accumulate) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    if (full_chunk || col0 + i < p.ncols) {
-                                        const float r = p.out_scale * sums[c0 + i];
-                                        o[i] = p.accumulate ? o[i] + r : r;
+                                    for (int i = 0; i < 8; ++i)
+                                        reinterpret_cast<float4*>(o)[i] =
+                                            make_float4(p.out_scale * sums[c0 + 4 * i], p.out_scale * sums[c0 + 4 * i + 1],
+                                                        p.out_scale * sums[c0 + 4 * i + 2], p.out_scale * sums[c0 + 4 * i + 3]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) {
+                                        if (full_chunk || col0 + i < p.ncols) {
+                                            const float r = p.out_scale * sums[c0 + i];
+                                            o[i] = p.accumulate ? o[i] + r : r;
+                                        }
                                     }
                                 }
                             }

@@ -287,23 +287,34 @@ class PosteriorEngine:
                 vt = self.backend.transpose_split(values, vscale) + (vscale,)
         out = torch.empty(m, ds.d if values is None else values.shape[1], dtype=torch.float32, device=dev)
         step = max(128, min(m, self.cfg.max_energy_bytes // (ds.n * 8)))
+        ph = getattr(self.backend, "phase", None)
+        if ph is None:
+            import contextlib
+            ph = lambda _n: contextlib.nullcontext()      # noqa: E731
         for r0 in range(0, m, step):
             r1 = min(m, r0 + step)
             rows = r1 - r0
             inv_temp = (1.0 / temp_rows[r0:r1]).contiguous()
-            prep = self._prepare(xf[r0:r1], rows, None, None, None if post is None else post[r0:r1], precision, False)
-            energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
-            parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)
-            st, _ = self._merge(parts, inv_temp)
+            with ph("prepare"):
+                prep = self._prepare(xf[r0:r1], rows, None, None, None if post is None else post[r0:r1], precision, False)
+                energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
+            with ph("fused+energy"):
+                parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)
+            with ph("merge"):
+                st, _ = self._merge(parts, inv_temp)
             e_min, l = st[_cabi.OUT_E_MIN], st[_cabi.OUT_L]
             if tensor:
-                p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
-                yt_hi, yt_lo, yscale = vt if vt is not None else (ds.transposed_split() + (ds.scale,))
-                self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=out[r0:r1],
-                                        cta_group=self.cfg.cta_group)
+                with ph("weights"):
+                    p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
+                with ph("gemm2"):
+                    yt_hi, yt_lo, yscale = vt if vt is not None else (ds.transposed_split() + (ds.scale,))
+                    self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=out[r0:r1],
+                                            cta_group=self.cfg.cta_group)
             else:
-                p = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=False)
-                self.backend.weighted_mean_exact(p, ds.y if values is None else values, out=out[r0:r1])
+                with ph("weights"):
+                    p = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=False)
+                with ph("gemm2"):
+                    self.backend.weighted_mean_exact(p, ds.y if values is None else values, out=out[r0:r1])
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out, group=self.group)
