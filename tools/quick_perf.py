@@ -52,7 +52,12 @@ def main():
         torch.cuda.synchronize()
         each = [evs[i].elapsed_time(evs[i + 1]) for i in range(a.iters)]
         ms = sum(each) / a.iters
-        print("   per-iter ms:", " ".join(f"{v:.2f}" for v in each), flush=True)
+        if a.iters <= 12:
+            print("   per-iter ms:", " ".join(f"{v:.2f}" for v in each), flush=True)
+        else:
+            tail = each[len(each) // 2:]
+            print(f"   first {each[0]:.2f}  min {min(each):.2f}  steady(mean of last half) {sum(tail) / len(tail):.2f} ms", flush=True)
+            ms = sum(tail) / len(tail)
         pairs = a.m * a.n
         terms = 3 if a.precision == "f16x3" else 1
         print(f"cfg cg={cg} plan(S,G,cg)={be.last_plan}: {ms:.3f} ms  {pairs / ms / 1e6:.2f} Gpairs/s  "
