@@ -49,6 +49,9 @@ extern "C" {
 #define PDM_PREC_EXACT_F32  0   /* CUDA-core fp32 FMA (validation variant, small-d path)            */
 #define PDM_PREC_F16X3      1   /* tcgen05 kind::f16, split operands hi*hi + lo*hi + hi*lo, fp32 acc */
 #define PDM_PREC_F16X1      2   /* tcgen05 kind::f16, hi*hi only (11-bit operands; opt-in fast mode) */
+#define PDM_PREC_F16X2      3   /* tcgen05 kind::f16, q_hi*y_hi + q_lo*y_hi: for datasets that ARE an fp16
+                                   lattice (8-bit images: y*255 is an integer), y_lo == 0 and the third
+                                   product of F16X3 vanishes identically -- same accuracy, 2/3 of the MMAs */
 
 /* floats per partial record: m, l, A1, A2, AUX, argmin_lo(bits), argmin_hi(bits), reserved */
 #define PDM_PART_STRIDE 8
@@ -102,6 +105,14 @@ int pdm_prepare_rows(const float* src, int64_t src_rows, int64_t ld_src,
 
 /* max_k |x[r,k]| over the whole matrix -> out[0] (used once per dataset to pick its global 2^k). */
 int pdm_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream);
+
+/* Lattice test of a dataset against a candidate scale (8-bit images: Normalize(0.5, 0.5)(ToTensor(p)) * 255
+ * = 2p - 255 up to fp32 rounding, utils/data.py:43-52 of the reference):
+ *   out2[0] = max_j ||y_j - rint(y_j*scale)/scale||^2 / ||y_j||^2,   out2[1] = max |rint(y*scale)|.
+ * When out2[1] <= 2048 (fp16 holds the integers exactly) and out2[0] is below fp32 resolution, the lo part
+ * of the split carries nothing and PDM_PREC_F16X2 is exact to the same accuracy as PDM_PREC_F16X3. */
+int pdm_lattice_residual_f32(const float* y, int64_t n, int64_t d, int64_t ld, float scale, float* out2,
+                             pdm_stream_t stream);
 
 /* Transposed fp16 split of the dataset for the posterior-mean contraction:
  *   yt_hi/yt_lo[k, j] = split(y[j,k]*scale), shape (d, ldt), columns N..ldt-1 zero.  ldt % 8 == 0. */
@@ -190,7 +201,8 @@ int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t M, int64_t
 
 /* out (M, d) [+]= scale * (A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T), A (M, K) and B (d, K) fp16
  * K-major (lda, ldb multiples of 8).  For the posterior mean A = weights, B = transposed dataset,
- * K = N, scale = 2^-14 * y_inv_scale.  accumulate != 0 adds into `out`. */
+ * K = N, scale = 2^-14 * y_inv_scale.  accumulate != 0 adds into `out`.  b_lo == NULL drops the third
+ * product (lattice datasets, see pdm_lattice_residual_f32). */
 int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
                          const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
                          float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,

@@ -43,8 +43,9 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = "") -> str:
+    """``defines`` / ``out``: dev builds of kernel variants (lib/<out>.so, loaded with PDM_B200_LIB=<path>)."""
+    if not force and not is_stale() and not out:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
@@ -52,8 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [exe, "-c", os.path.join(CSRC, src), "-o", obj] + NVCC_FLAGS + extra
+        obj = os.path.join(OBJDIR, (out + "_" if out else "") + src.replace(".cu", ".o"))
+        cmd = [exe, "-c", os.path.join(CSRC, src), "-o", obj] + NVCC_FLAGS + extra + [f"-D{d}" for d in defines]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -63,18 +64,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB + ".tmp"
+    lib = os.path.join(LIBDIR, out + ".so") if out else LIB
+    tmp = lib + ".tmp"
     cmd = [exe, "-shared", "-o", tmp] + objs + ARCH + ["-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--define", action="append", default=[])
+    ap.add_argument("--out", type=str, default="")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, defines=a.define, out=a.out))

@@ -19,22 +19,34 @@ int cuda_fail(cudaError_t e, const char* what) {
     return PDM_ERR_CUDA;
 }
 
-int current_device_info(DeviceInfo* out) {
+// cudaGetDeviceProperties takes milliseconds (it walks the whole driver property table, and contends with
+// anything else that talks to the resource manager, e.g. a polling nvidia-smi); the three facts the
+// launchers need are read once per device with cudaDeviceGetAttribute and cached.
+int device_info(int dev, DeviceInfo* out) {
     static std::mutex mu;
     static DeviceInfo cache[64];
     static bool have[64] = {false};
-    int dev = 0;
-    PDM_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return PDM_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lock(mu);
     if (!have[dev]) {
-        cudaDeviceProp prop;
-        PDM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-        cache[dev] = DeviceInfo{prop.multiProcessorCount, prop.major, prop.minor};
+        int n = 0;
+        PDM_CUDA_CHECK(cudaGetDeviceCount(&n));
+        if (dev >= n) { set_error("no CUDA device %d (count %d)", dev, n); return PDM_ERR_CUDA; }
+        DeviceInfo d;
+        PDM_CUDA_CHECK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        PDM_CUDA_CHECK(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        PDM_CUDA_CHECK(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+        cache[dev] = d;
         have[dev] = true;
     }
     *out = cache[dev];
     return PDM_OK;
+}
+
+int current_device_info(DeviceInfo* out) {
+    int dev = 0;
+    PDM_CUDA_CHECK(cudaGetDevice(&dev));
+    return device_info(dev, out);
 }
 
 }  // namespace pdm
@@ -44,15 +56,11 @@ extern "C" const char* pdm_last_error(void) { return pdm::g_err; }
 extern "C" int pdm_abi_version(void) { return PDM_ABI_VERSION; }
 
 extern "C" int pdm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess) return pdm::cuda_fail(e, "cudaGetDeviceCount");
-    if (device < 0 || device >= n) { pdm::set_error("no CUDA device %d (count %d)", device, n); return PDM_ERR_CUDA; }
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) return pdm::cuda_fail(e, "cudaGetDeviceProperties");
-    if (sm_count) *sm_count = prop.multiProcessorCount;
-    if (cc_major) *cc_major = prop.major;
-    if (cc_minor) *cc_minor = prop.minor;
+    pdm::DeviceInfo d;
+    int rc = pdm::device_info(device, &d);
+    if (rc != PDM_OK) return rc;
+    if (sm_count) *sm_count = d.sm_count;
+    if (cc_major) *cc_major = d.cc_major;
+    if (cc_minor) *cc_minor = d.cc_minor;
     return PDM_OK;
 }

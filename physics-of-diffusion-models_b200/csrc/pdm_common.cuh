@@ -33,6 +33,7 @@ __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_
 // Cached per-device facts (sm count, cc).  Returns PDM_OK or an error.
 struct DeviceInfo { int sm_count; int cc_major; int cc_minor; };
 int current_device_info(DeviceInfo* out);
+int device_info(int device, DeviceInfo* out);
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kBigE  = 1.0e38f;     // energy of a masked (out-of-range) dataset column

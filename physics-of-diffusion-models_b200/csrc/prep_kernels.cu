@@ -189,6 +189,37 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------
+// lattice test: is every y*scale an integer the fp16 hi part holds exactly?  One warp per row:
+//   out[0] = max_j ||y_j - rint(y_j*scale)/scale||^2 / ||y_j||^2      out[1] = max |rint(y*scale)|
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lattice_residual_kernel(const float* __restrict__ y, int64_t n, int64_t d, int64_t ld,
+                                                               float scale, unsigned* __restrict__ out_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* p = y + row * ld;
+    const double inv = 1.0 / (double)scale;
+    double r2 = 0.0, y2 = 0.0;
+    float vmax = 0.f;
+    for (int64_t i = lane; i < d; i += 32) {
+        const float v = __ldg(p + i);
+        const float q = rintf(__fmul_rn(v, scale));        // what rn16(v*scale) holds when |q| <= 2048
+        const double r = (double)v - (double)q * inv;
+        r2 += r * r;
+        y2 += (double)v * v;
+        vmax = fmaxf(vmax, fabsf(q));
+    }
+    r2 = warp_reduce(r2, OpAddD());
+    y2 = warp_reduce(y2, OpAddD());
+    vmax = warp_reduce(vmax, OpMaxF());
+    if (lane == 0) {
+        const float ratio = y2 > 0.0 ? (float)(r2 / y2) : (r2 > 0.0 ? INFINITY : 0.f);
+        atomicMax(out_bits, __float_as_uint(ratio));
+        atomicMax(out_bits + 1, __float_as_uint(vmax));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // transposed fp16 split of the dataset: y (n, d) -> yt_hi/lo (d, ldt)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ y, int64_t n, int64_t d, int64_t ld,
@@ -387,6 +418,16 @@ extern "C" int pdm_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t l
     const int64_t total = rows * d;
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256 * 8), 148 * 16);
     absmax_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, rows, d, ld, reinterpret_cast<unsigned*>(out));
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_lattice_residual_f32(const float* y, int64_t n, int64_t d, int64_t ld, float scale, float* out2,
+                                        pdm_stream_t stream) {
+    PDM_REQUIRE(y && out2 && n > 0 && d > 0 && ld >= d && scale > 0.f, "pdm_lattice_residual_f32: bad arguments");
+    PDM_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), as_stream(stream)));
+    lattice_residual_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, as_stream(stream)>>>(y, n, d, ld, scale,
+                                                                                      reinterpret_cast<unsigned*>(out2));
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

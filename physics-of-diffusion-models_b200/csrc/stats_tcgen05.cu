@@ -22,6 +22,7 @@
 #include "online_stats.cuh"
 #include "sm100_ptx.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <stdlib.h>
 
@@ -37,10 +38,34 @@ constexpr int kAccStages = 2;
 constexpr int kEpiWarp0 = 4;                      // warps 0-3: producer / MMA / TMEM alloc / spare
 constexpr int kEpiWarps = 8;                      // warps 4-11: two warps per TMEM lane quarter
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
-constexpr int kRegsControl = 40;                  // setmaxnreg budgets: 128*40 + 256*232 == 384*168
+constexpr int kRegsControl = 40;                  // setmaxnreg budgets: 128*40 + 256*232 == 384*168 (the launch allocation)
 constexpr int kRegsEpilogue = 232;
+#ifndef PDM_SPIN_WAIT
+#define PDM_SPIN_WAIT 0                           // 1: MMA issuer and epilogue busy-poll their hand-off barriers
+                                                  // (measured on B200: slower -- the pollers steal issue slots and power)
+#endif
+#if PDM_SPIN_WAIT
+#define PDM_HANDOFF_WAIT(bar, parity, hint) mbar_wait_spin(bar, parity)
+#else
+#define PDM_HANDOFF_WAIT(bar, parity, hint) mbar_wait(bar, parity, hint)
+#endif
+#ifndef PDM_DRAIN_COLS
+#define PDM_DRAIN_COLS 32                         // columns per tcgen05.ld of the accumulator drain (32 or 64)
+#endif
 
 enum { EPI_STATS = 0, EPI_STORE = 1 };
+
+// Dev instrumentation (-DPDM_STALL_STATS): nanoseconds each role of every CTA spent blocked on its
+// barriers: [0] producer on smem-empty, [1] MMA on smem-full, [2] MMA on TMEM-empty, [3] epilogue warp 4
+// on TMEM-full, [4] kernel wall time.  Read + reset with pdm_debug_read_stalls.
+#ifdef PDM_STALL_STATS
+__device__ unsigned long long g_stall[160][8];
+#define PDM_STALL_BEGIN() const uint64_t _st0 = global_timer_ns()
+#define PDM_STALL_END(acc) (acc) += global_timer_ns() - _st0
+#else
+#define PDM_STALL_BEGIN() do {} while (0)
+#define PDM_STALL_END(acc) do {} while (0)
+#endif
 
 struct GemmParams {
     int64_t M;            // rows of A (queries)
@@ -63,9 +88,11 @@ template <int CG, int TERMS>
 struct Cfg {
     static constexpr int kBlockN = (CG == 2) ? 256 : 128;
     static constexpr int kColsPerThread = kBlockN / 2;          // two epilogue warps share a lane quarter
-    static constexpr int kTilesPerStage = (TERMS == 3) ? 4 : 2;
+    // stage layout: [A_hi][A_lo if TERMS >= 2][B_hi][B_lo if TERMS == 3]
+    static constexpr int kTilesPerStage = TERMS + 1;
+    static constexpr int kTileBHi = (TERMS >= 2) ? 2 : 1;
     static constexpr int kStageBytes = kTilesPerStage * kTileBytes;
-    static constexpr int kStages = (TERMS == 3) ? 3 : 6;
+    static constexpr int kStages = (TERMS == 3) ? 3 : (TERMS == 2) ? 4 : 6;
     static constexpr uint32_t kTmemCols = kAccStages * kBlockN;
     static constexpr uint32_t kIdesc = make_idesc_f16(128 * CG, kBlockN);
     static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
@@ -115,7 +142,8 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a_hi);
         prefetch_tensormap(&tm_b_hi);
-        if (TERMS == 3) { prefetch_tensormap(&tm_a_lo); prefetch_tensormap(&tm_b_lo); }
+        if (TERMS >= 2) prefetch_tensormap(&tm_a_lo);
+        if (TERMS == 3) prefetch_tensormap(&tm_b_lo);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
@@ -141,68 +169,78 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         if (active && warp == 0 && lane == 0) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
+            unsigned long long st_empty = 0; (void)st_empty;
+#ifdef PDM_STALL_STATS
+            const uint64_t t_begin = global_timer_ns();
+#endif
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
                 const int32_t a_row = (mt * CG + (int)rank) * kRowsPerCta;
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
                     const int32_t b_row = nt * kBlockN + (int)rank * kRowsPerCta;
                     for (int kb = 0; kb < p.num_kb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
+                        { PDM_STALL_BEGIN(); mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns); PDM_STALL_END(st_empty); }
                         const uint32_t dst = smem_base + (uint32_t)stage * C::kStageBytes;
                         const uint32_t fb = full_bar(stage);
                         const int32_t kc = kb * kBlockK;
                         if (CG == 1) {
                             mbar_arrive_expect_tx(fb, C::kStageBytes);
                             tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
-                            if (TERMS == 3) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
-                            tma_load_2d(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
+                            if (TERMS >= 2) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
+                            tma_load_2d(dst + C::kTileBHi * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
                             if (TERMS == 3) tma_load_2d(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
                         } else {
                             if (leader) mbar_arrive_expect_tx(fb, 2u * C::kStageBytes);
                             else mbar_arrive_remote(fb, 0);
                             tma_load_2d_pair(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
-                            if (TERMS == 3) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
-                            tma_load_2d_pair(dst + (TERMS == 3 ? 2 : 1) * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
+                            if (TERMS >= 2) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
+                            tma_load_2d_pair(dst + C::kTileBHi * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
                             if (TERMS == 3) tma_load_2d_pair(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
+#ifdef PDM_STALL_STATS
+            g_stall[blockIdx.x][0] = st_empty;
+            g_stall[blockIdx.x][4] = global_timer_ns() - t_begin;
+#endif
         } else if (active && warp == 1 && lane == 0 && leader) {
             // ===================== MMA issuer =====================
             int stage = 0; uint32_t phase = 0; uint32_t chunk_iter = 0;
+            unsigned long long st_full = 0, st_tempty = 0; (void)st_full; (void)st_tempty;
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
                     for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.flush_kb, ++chunk_iter) {
                         const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
-                        mbar_wait(tempty_bar(as), aphase ^ 1u, p.wait_hint_ns);      // epilogue has drained this accumulator
+                        // epilogue has drained this accumulator
+                        { PDM_STALL_BEGIN(); PDM_HANDOFF_WAIT(tempty_bar(as), aphase ^ 1u, p.wait_hint_ns); PDM_STALL_END(st_tempty); }
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + as * kBlockN;
                         const int kb1 = min(p.num_kb, kb0 + p.flush_kb);
                         for (int kb = kb0; kb < kb1; ++kb) {
-                            mbar_wait(full_bar(stage), phase, p.wait_hint_ns);
+                            { PDM_STALL_BEGIN(); PDM_HANDOFF_WAIT(full_bar(stage), phase, p.wait_hint_ns); PDM_STALL_END(st_full); }
                             tc_fence_after();
                             const uint32_t sb = smem_base + (uint32_t)stage * C::kStageBytes;
                             const uint64_t a_hi = make_smem_desc_sw128(sb);
                             const uint64_t a_lo = make_smem_desc_sw128(sb + kTileBytes);
-                            const uint64_t b_hi = make_smem_desc_sw128(sb + (TERMS == 3 ? 2 : 1) * kTileBytes);
+                            const uint64_t b_hi = make_smem_desc_sw128(sb + C::kTileBHi * kTileBytes);
                             const uint64_t b_lo = make_smem_desc_sw128(sb + 3 * kTileBytes);
                             // Small cross terms first: while the accumulator only holds them (2^-11 of the
                             // final magnitude) the tensor core's truncation costs nothing; the four large
                             // hi*hi products then go in last (16 fp16 = 32 bytes = 2 descriptor units per k).
-                            if (TERMS == 3) {
+                            if (TERMS >= 2) {
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k) {
                                     const uint64_t ko = (uint64_t)(k * 2);
                                     umma_f16<CG>(d_tmem, a_lo + ko, b_hi + ko, C::kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                                    umma_f16<CG>(d_tmem, a_hi + ko, b_lo + ko, C::kIdesc, 1u);
+                                    if (TERMS == 3) umma_f16<CG>(d_tmem, a_hi + ko, b_lo + ko, C::kIdesc, 1u);
                                 }
                             }
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t ko = (uint64_t)(k * 2);
                                 umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc,
-                                             (TERMS == 3 || kb > kb0 || k > 0) ? 1u : 0u);
+                                             (TERMS >= 2 || kb > kb0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit<CG>(empty_bar(stage));                 // smem slot reusable once these retire
                             if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(as)); // chunk accumulator complete
@@ -211,50 +249,83 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     }
                 }
             }
+#ifdef PDM_STALL_STATS
+            g_stall[blockIdx.x][1] = st_full;
+            g_stall[blockIdx.x][2] = st_tempty;
+#endif
         }
     } else {
         setmaxnreg_inc<kRegsEpilogue>();
         if (active) {
             // ===================== epilogue (8 warps) =====================
+            // Per k-block chunk: TMEM -> registers, round-to-nearest accumulation with packed FADD2.  Per tile:
+            // u = (|x|^2 - 2 x.y) + |y|^2 and the online statistics, two columns per instruction
+            // (online_stats.cuh, PackedState).
+            constexpr int CH = 32;                                // columns per statistics chunk
+            constexpr int NP = CH / 2;                            // float2 pairs per chunk
             const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
             const int half = (warp - kEpiWarp0) >> 2;             // which half of the tile's columns
             const int row_in_cta = quarter * 32 + lane;
             const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
             uint32_t chunk_iter = 0;
+            unsigned long long st_tfull = 0; (void)st_tfull;
             // 128-bit stores of the dense outputs need 16-byte aligned rows
             const bool out_vec = (EPI == EPI_STATS)
                 ? (p.energy_out && (p.lde % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.energy_out) & 15) == 0))
                 : ((p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0));
+            // |y_k| <= 4096 * y_inv_scale by construction of the split, so |y|^2 <= d_pad * (4096 y_inv_scale)^2
+            const float yn_bound = (float)(p.num_kb * kBlockK) * (4096.f * p.y_inv_scale) * (4096.f * p.y_inv_scale);
+            const float half_mult = 0.5f * p.energy_mult;
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
                 const int64_t grow = (int64_t)(mt * CG + (int)rank) * kRowsPerCta + row_in_cta;
                 const bool row_ok = grow < p.M;
-                float xn = 0.f, neg2inv = 0.f, inv_t = 1.f;
-                RowState st;
+                float xn = 0.f, neg2inv = 0.f, c2 = -0.5f * kLog2e;
+                bool safe = true;          // (u - 2m) * c2 cannot overflow for this row: no per-element clamp
+                PackedState st;
                 if (EPI == EPI_STATS) {
                     if (row_ok) {
                         xn = p.q_norm[grow];
                         neg2inv = -2.f * p.q_inv_scale[grow] * p.y_inv_scale;
-                        if (p.inv_temp) inv_t = p.inv_temp[grow];
+                        if (p.inv_temp) {
+                            const float inv_t = p.inv_temp[grow];
+                            c2 = -0.5f * kLog2e * inv_t;
+                            safe = inv_t * (xn + yn_bound) < 1.0e29f;
+                        }
                     }
-                    state_init(st);
+                    packed_init(st);
                 }
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
-                    float sums[CPT];
+                    float2 sums[CPT / 2];
 #pragma unroll
-                    for (int i = 0; i < CPT; ++i) sums[i] = 0.f;
+                    for (int i = 0; i < CPT / 2; ++i) sums[i] = make_float2(0.f, 0.f);
                     for (int ch = 0; ch < n_chunks; ++ch, ++chunk_iter) {
                         const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
-                        mbar_wait(tfull_bar(as), aphase, p.wait_hint_ns);
+                        { PDM_STALL_BEGIN(); PDM_HANDOFF_WAIT(tfull_bar(as), aphase, p.wait_hint_ns); PDM_STALL_END(st_tfull); }
                         tc_fence_after();
                         const uint32_t taddr = tmem_base + t_lane + as * kBlockN + half * CPT;
+#if PDM_DRAIN_COLS == 64
+#pragma unroll
+                        for (int c0 = 0; c0 < CPT; c0 += 64) {
+                            uint32_t v[64];
+                            tmem_ld_32x64(taddr + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                sums[c0 / 2 + i] = __fadd2_rn(sums[c0 / 2 + i],
+                                                              make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+                        }
+#else
 #pragma unroll
                         for (int c0 = 0; c0 < CPT; c0 += 32) {
                             uint32_t v[32];
                             tmem_ld_32x32(taddr + c0, v);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) sums[c0 + i] = __fadd_rn(sums[c0 + i], __uint_as_float(v[i]));
+                            for (int i = 0; i < 16; ++i)
+                                sums[c0 / 2 + i] = __fadd2_rn(sums[c0 / 2 + i],
+                                                              make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
                         }
+#endif
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -264,68 +335,95 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     }
                     // ---- the tile's Gram entries are complete in registers ----
                     const int64_t nbase = (int64_t)nt * kBlockN + half * CPT;
+                    // |y|^2 of the chunk after the current one is loaded while the current one is processed
+                    // (one chunk ahead only: the barrier below keeps ptxas from hoisting all of them)
+                    float4 yn_next[CH / 4];
+                    if (EPI == EPI_STATS && nbase + CH <= p.ncols) {
 #pragma unroll
-                    for (int c0 = 0; c0 < CPT; c0 += 32) {
+                        for (int i = 0; i < CH / 4; ++i) yn_next[i] = __ldg(reinterpret_cast<const float4*>(p.y_norm + nbase) + i);
+                    }
+#pragma unroll
+                    for (int c0 = 0; c0 < CPT; c0 += CH) {
                         const int64_t col0 = nbase + c0;
-                        if (col0 < p.ncols) {
-                            const bool full_chunk = col0 + 32 <= p.ncols;
-                            if (EPI == EPI_STATS) {
-                                float E[32], ax[32];
-                                if (full_chunk) {
-                                    const float4* yn4 = reinterpret_cast<const float4*>(p.y_norm + col0);
+                        float4 yn_cur[CH / 4];
+                        if (EPI == EPI_STATS) {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float4 y = __ldg(yn4 + i);
-                                        E[4 * i + 0] = y.x; E[4 * i + 1] = y.y; E[4 * i + 2] = y.z; E[4 * i + 3] = y.w;
+                            for (int i = 0; i < CH / 4; ++i) yn_cur[i] = yn_next[i];
+                            asm volatile("" ::: "memory");
+                            if (c0 + CH < CPT && col0 + 2 * CH <= p.ncols) {
+#pragma unroll
+                                for (int i = 0; i < CH / 4; ++i)
+                                    yn_next[i] = __ldg(reinterpret_cast<const float4*>(p.y_norm + col0 + CH) + i);
+                            }
+                        }
+                        if (col0 < p.ncols) {
+                            const bool full_chunk = col0 + CH <= p.ncols;
+                            if (EPI == EPI_STATS) {
+                                float2 u[NP], ax[NP];
+                                if (full_chunk) {
+                                    const float2 n2 = splat2(neg2inv), xv = splat2(xn);
+#pragma unroll
+                                    for (int i = 0; i < CH / 4; ++i) {
+                                        const float4 y = yn_cur[i];
+                                        u[2 * i] = __fadd2_rn(__ffma2_rn(sums[c0 / 2 + 2 * i], n2, xv), make_float2(y.x, y.y));
+                                        u[2 * i + 1] = __fadd2_rn(__ffma2_rn(sums[c0 / 2 + 2 * i + 1], n2, xv), make_float2(y.z, y.w));
                                     }
                                     if (AUX) {
                                         const float4* ax4 = reinterpret_cast<const float4*>(p.y_aux + col0);
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i) {
+                                        for (int i = 0; i < CH / 4; ++i) {
                                             const float4 y = __ldg(ax4 + i);
-                                            ax[4 * i + 0] = y.x; ax[4 * i + 1] = y.y; ax[4 * i + 2] = y.z; ax[4 * i + 3] = y.w;
+                                            ax[2 * i] = make_float2(y.x, y.y);
+                                            ax[2 * i + 1] = make_float2(y.z, y.w);
                                         }
                                     }
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        E[i] = 0.5f * __fadd_rn(fmaf(sums[c0 + i], neg2inv, xn), E[i]);
                                 } else {
 #pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        const bool ok = col0 + i < p.ncols;
-                                        const float yn = ok ? __ldg(p.y_norm + col0 + i) : 0.f;
-                                        if (AUX) ax[i] = ok ? __ldg(p.y_aux + col0 + i) : 0.f;
-                                        E[i] = ok ? 0.5f * __fadd_rn(fmaf(sums[c0 + i], neg2inv, xn), yn) : kBigE;
+                                    for (int i = 0; i < NP; ++i) {
+                                        const bool ok0 = col0 + 2 * i < p.ncols, ok1 = col0 + 2 * i + 1 < p.ncols;
+                                        const float y0 = ok0 ? __ldg(p.y_norm + col0 + 2 * i) : 0.f;
+                                        const float y1 = ok1 ? __ldg(p.y_norm + col0 + 2 * i + 1) : 0.f;
+                                        if (AUX) ax[i] = make_float2(ok0 ? __ldg(p.y_aux + col0 + 2 * i) : 0.f,
+                                                                     ok1 ? __ldg(p.y_aux + col0 + 2 * i + 1) : 0.f);
+                                        u[i].x = ok0 ? __fadd_rn(fmaf(sums[c0 / 2 + i].x, neg2inv, xn), y0) : 2.f * kBigE;
+                                        u[i].y = ok1 ? __fadd_rn(fmaf(sums[c0 / 2 + i].y, neg2inv, xn), y1) : 2.f * kBigE;
                                     }
                                 }
                                 if (p.energy_out && row_ok) {
                                     float* eo = p.energy_out + grow * p.lde + col0;
                                     if (full_chunk && out_vec) {
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i)
+                                        for (int i = 0; i < CH / 4; ++i)
                                             reinterpret_cast<float4*>(eo)[i] =
-                                                make_float4(p.energy_mult * E[4 * i], p.energy_mult * E[4 * i + 1],
-                                                            p.energy_mult * E[4 * i + 2], p.energy_mult * E[4 * i + 3]);
+                                                make_float4(half_mult * u[2 * i].x, half_mult * u[2 * i].y,
+                                                            half_mult * u[2 * i + 1].x, half_mult * u[2 * i + 1].y);
                                     } else {
 #pragma unroll
-                                        for (int i = 0; i < 32; ++i)
-                                            if (full_chunk || col0 + i < p.ncols) eo[i] = p.energy_mult * E[i];
+                                        for (int i = 0; i < NP; ++i) {
+                                            if (full_chunk || col0 + 2 * i < p.ncols) eo[2 * i] = half_mult * u[i].x;
+                                            if (full_chunk || col0 + 2 * i + 1 < p.ncols) eo[2 * i + 1] = half_mult * u[i].y;
+                                        }
                                     }
                                 }
-                                if (p.partials) state_add_chunk<32, AUX>(st, E, ax, p.index_offset + col0, 1, inv_t);
+                                if (p.partials) {
+                                    if (full_chunk && safe) packed_add_chunk<NP, AUX, false>(st, u, ax, p.index_offset + col0, c2);
+                                    else packed_add_chunk<NP, AUX, true>(st, u, ax, p.index_offset + col0, c2);
+                                }
                             } else if (row_ok) {
                                 float* o = p.out + grow * p.ldo + col0;
                                 if (full_chunk && out_vec && !p.accumulate) {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
+                                    for (int i = 0; i < CH / 4; ++i) {
+                                        const float2 a = sums[c0 / 2 + 2 * i], b = sums[c0 / 2 + 2 * i + 1];
                                         reinterpret_cast<float4*>(o)[i] =
-                                            make_float4(p.out_scale * sums[c0 + 4 * i], p.out_scale * sums[c0 + 4 * i + 1],
-                                                        p.out_scale * sums[c0 + 4 * i + 2], p.out_scale * sums[c0 + 4 * i + 3]);
+                                            make_float4(p.out_scale * a.x, p.out_scale * a.y, p.out_scale * b.x, p.out_scale * b.y);
+                                    }
                                 } else {
 #pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
+                                    for (int i = 0; i < CH; ++i) {
                                         if (full_chunk || col0 + i < p.ncols) {
-                                            const float r = p.out_scale * sums[c0 + i];
+                                            const float2 a = sums[c0 / 2 + i / 2];
+                                            const float r = p.out_scale * ((i & 1) ? a.y : a.x);
                                             o[i] = p.accumulate ? o[i] + r : r;
                                         }
                                     }
@@ -336,8 +434,11 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 }
                 // one partial record per (row, split, column half)
                 if (EPI == EPI_STATS && p.partials && row_ok)
-                    state_store(st, p.partials + (grow * (2 * p.n_splits) + 2 * sp + half) * PDM_PART_STRIDE);
+                    packed_store(st, p.partials + (grow * (2 * p.n_splits) + 2 * sp + half) * PDM_PART_STRIDE);
             }
+#ifdef PDM_STALL_STATS
+            if (warp == kEpiWarp0 && lane == 0) g_stall[blockIdx.x][3] = st_tfull;
+#endif
         }
     }
 
@@ -395,7 +496,13 @@ template <int CG, int TERMS, int EPI, bool AUX>
 static int launch_variant(const CUtensorMap* maps, const GemmParams& p, int sm_count, cudaStream_t stream) {
     using C = Cfg<CG, TERMS>;
     auto kern = fused_gemm_kernel<CG, TERMS, EPI, AUX>;
-    PDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    static std::atomic<uint64_t> configured{0};          // one bit per device ordinal (function attributes are per device)
+    int dev = 0;
+    PDM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!((configured.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
+        PDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
+    }
     const int pairs = sm_count / CG;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(pairs * CG));
@@ -419,19 +526,24 @@ static int dispatch(int cg, int terms, const CUtensorMap* maps, const GemmParams
     if (cg == 1 && terms == 3) return launch_variant<1, 3, EPI, AUX>(maps, p, sm_count, stream);
     if (cg == 2 && terms == 1) return launch_variant<2, 1, EPI, AUX>(maps, p, sm_count, stream);
     if (cg == 1 && terms == 1) return launch_variant<1, 1, EPI, AUX>(maps, p, sm_count, stream);
+    if (cg == 2 && terms == 2) return launch_variant<2, 2, EPI, AUX>(maps, p, sm_count, stream);
+    if (cg == 1 && terms == 2) return launch_variant<1, 2, EPI, AUX>(maps, p, sm_count, stream);
     set_error("unsupported cta_group %d / terms %d", cg, terms);
     return PDM_ERR_INVALID_ARG;
 }
 
-// k-blocks accumulated inside the tensor core between flushes (PDM_FLUSH_KB, default 1 = every 64 elements)
-static int flush_kb_setting() {
-    static int v = 0;
-    if (v == 0) {
+// k-blocks accumulated inside the tensor core between flushes.  Default: at most 16 MMAs per flush
+// (f16x3: every k-block = 12 MMAs; f16x2: every second = 16; measured on B200 both stay within ~4 ulp of the
+// row norms, the reference's own fp32 error).  PDM_FLUSH_KB overrides.
+static int flush_kb_setting(int terms) {
+    static int v = -1;
+    if (v < 0) {
         const char* e = getenv("PDM_FLUSH_KB");
-        v = e ? atoi(e) : 1;
-        if (v < 1) v = 1;
+        v = e ? atoi(e) : 0;
+        if (v < 0) v = 0;
     }
-    return v;
+    if (v > 0) return v;
+    return terms == 3 ? 1 : terms == 2 ? 2 : 4;
 }
 
 static uint32_t wait_hint_setting() {
@@ -486,23 +598,24 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     int rc = require_sm100(&info);
     if (rc != PDM_OK) return rc;
     const int cg = a.cta_group;
-    const int terms = a.precision == PDM_PREC_F16X3 ? 3 : 1;
+    const int terms = a.precision == PDM_PREC_F16X3 ? 3 : a.precision == PDM_PREC_F16X2 ? 2 : 1;
     PDM_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
     PDM_REQUIRE(a.q_hi && a.y_hi && a.q_inv_scale && a.y_inv_scale > 0.f, "tensor path: q_hi / y_hi / scales missing");
-    PDM_REQUIRE(terms == 1 || (a.q_lo && a.y_lo), "f16x3 needs the lo operands");
+    PDM_REQUIRE(terms < 2 || a.q_lo, "f16x2 / f16x3 need the lo part of the queries");
+    PDM_REQUIRE(terms < 3 || a.y_lo, "f16x3 needs the lo part of the dataset");
     PDM_REQUIRE((reinterpret_cast<uintptr_t>(a.y_norm) & 15) == 0 && (!a.y_aux || (reinterpret_cast<uintptr_t>(a.y_aux) & 15) == 0),
                 "y_norm / y_aux must be 16-byte aligned");
     PDM_REQUIRE(a.M < (1ll << 31) - 512 && a.N < (1ll << 31) - 512, "M and N must fit in int32 for the TMA coordinates");
     CUtensorMap maps[4];
     if ((rc = make_tile_map(&maps[0], a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
-    if ((rc = make_tile_map(&maps[1], terms == 3 ? a.q_lo : a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
+    if ((rc = make_tile_map(&maps[1], terms >= 2 ? a.q_lo : a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
     if ((rc = make_tile_map(&maps[2], a.y_hi, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
     if ((rc = make_tile_map(&maps[3], terms == 3 ? a.y_lo : a.y_hi, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
     const int block_n = cg == 2 ? 256 : 128;
     GemmParams p = {};
     p.M = a.M; p.ncols = a.N;
     p.num_kb = (int32_t)ceil_div(a.d, kBlockK);
-    p.flush_kb = flush_kb_setting();
+    p.flush_kb = flush_kb_setting(terms);
     p.wait_hint_ns = wait_hint_setting();
     p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
@@ -542,7 +655,7 @@ extern "C" int pdm_posterior_stats_plan(pdm_stats_args* a, int device, int64_t* 
         const int pairs = sm / cg;
         const int64_t m_tiles = std::max<int64_t>(1, ceil_div(a->M, 128 * cg)), n_tiles = ceil_div(a->N, cg == 2 ? 256 : 128);
         const int64_t k_pad = round_up(a->d, 64);
-        const int64_t a_tile_bytes = 128ll * cg * k_pad * 2 * (a->precision == PDM_PREC_F16X3 ? 2 : 1);
+        const int64_t a_tile_bytes = 128ll * cg * k_pad * 2 * (a->precision == PDM_PREC_F16X1 ? 1 : 2);
         int g = a->m_group, s = a->n_splits;
         if (g <= 0 && s <= 0) tc::plan_schedule(pairs, m_tiles, n_tiles, a_tile_bytes, &g, &s);
         else if (g <= 0) g = (int)std::max<int64_t>(1, std::min<int64_t>(pairs / s, m_tiles));
@@ -567,6 +680,7 @@ extern "C" int pdm_posterior_stats(const pdm_stats_args* a, pdm_stream_t stream)
     switch (a->precision) {
         case PDM_PREC_EXACT_F32: return launch_exact_stats(*a, as_stream(stream));
         case PDM_PREC_F16X3:
+        case PDM_PREC_F16X2:
         case PDM_PREC_F16X1: return tc::launch_tensor_stats(*a, as_stream(stream));
         default: set_error("unknown precision %d", a->precision); return PDM_ERR_INVALID_ARG;
     }
@@ -576,7 +690,8 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
                                     const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
                                     float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
                                     pdm_stream_t stream) {
-    PDM_REQUIRE(a_hi && a_lo && b_hi && b_lo && out && M >= 0 && d > 0 && K > 0 && ldo >= d, "pdm_split_gemm_f16x3: bad arguments");
+    PDM_REQUIRE(a_hi && a_lo && b_hi && out && M >= 0 && d > 0 && K > 0 && ldo >= d, "pdm_split_gemm_f16x3: bad arguments");
+    const int terms = b_lo ? 3 : 2;
     if (M == 0) return PDM_OK;
     DeviceInfo info;
     int rc = tc::require_sm100(&info);
@@ -588,12 +703,12 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     if ((rc = tc::make_tile_map(&maps[0], a_hi, M, K, lda)) != PDM_OK) return rc;
     if ((rc = tc::make_tile_map(&maps[1], a_lo, M, K, lda)) != PDM_OK) return rc;
     if ((rc = tc::make_tile_map(&maps[2], b_hi, d, K, ldb)) != PDM_OK) return rc;
-    if ((rc = tc::make_tile_map(&maps[3], b_lo, d, K, ldb)) != PDM_OK) return rc;
+    if ((rc = tc::make_tile_map(&maps[3], b_lo ? b_lo : b_hi, d, K, ldb)) != PDM_OK) return rc;
     const int block_n = cg == 2 ? 256 : 128;
     tc::GemmParams p = {};
     p.M = M; p.ncols = d;
     p.num_kb = (int32_t)ceil_div(K, tc::kBlockK);
-    p.flush_kb = tc::flush_kb_setting();
+    p.flush_kb = tc::flush_kb_setting(terms);
     p.wait_hint_ns = tc::wait_hint_setting();
     p.m_tiles = (int32_t)ceil_div(M, (int64_t)tc::kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(d, block_n);
@@ -602,5 +717,30 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     p.n_splits = (int32_t)std::min<int64_t>(p.n_tiles, pairs);
     p.m_group = (int32_t)std::max<int64_t>(1, std::min<int64_t>(pairs / p.n_splits, p.m_tiles));
     p.out = out; p.ldo = ldo; p.out_scale = scale; p.accumulate = accumulate;
-    return tc::dispatch<tc::EPI_STORE, false>(cg, 3, maps, p, info.sm_count, as_stream(stream));
+    return tc::dispatch<tc::EPI_STORE, false>(cg, terms, maps, p, info.sm_count, as_stream(stream));
 }
+
+#ifdef PDM_STALL_STATS
+// dev builds only: copy the per-CTA stall counters (160 x 8 uint64) to the host and clear them
+extern "C" int pdm_debug_read_stalls(unsigned long long* out_host) {
+    PDM_CUDA_CHECK(cudaDeviceSynchronize());
+    PDM_CUDA_CHECK(cudaMemcpyFromSymbol(out_host, pdm::tc::g_stall, sizeof(unsigned long long) * 160 * 8));
+    static unsigned long long zeros[160 * 8] = {0};
+    PDM_CUDA_CHECK(cudaMemcpyToSymbol(pdm::tc::g_stall, zeros, sizeof(zeros)));
+    return PDM_OK;
+}
+// how many 2-CTA clusters of the f16x3 statistics kernel can be co-resident on the current device
+extern "C" int pdm_debug_max_clusters(int* out) {
+    using C = pdm::tc::Cfg<2, 3>;
+    auto kern = pdm::tc::fused_gemm_kernel<2, 3, pdm::tc::EPI_STATS, false>;
+    PDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(pdm::tc::kThreads); cfg.dynamicSmemBytes = C::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PDM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(out, kern, &cfg));
+    return PDM_OK;
+}
+#endif

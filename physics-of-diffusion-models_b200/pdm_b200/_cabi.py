@@ -11,10 +11,10 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libpdm_b200.so")
+LIB_PATH = os.environ.get("PDM_B200_LIB") or os.path.join(PKG_ROOT, "lib", "libpdm_b200.so")   # env: dev variants
 
 PDM_OK = 0
-PREC_EXACT_F32, PREC_F16X3, PREC_F16X1 = 0, 1, 2
+PREC_EXACT_F32, PREC_F16X3, PREC_F16X1, PREC_F16X2 = 0, 1, 2, 3
 PART_STRIDE = 8
 OUT_E_MIN, OUT_LOG_L, OUT_MEAN_E, OUT_MEAN_E2, OUT_VAR_E, OUT_AUX_MEAN, OUT_ENTROPY, OUT_L = range(8)
 OUT_ROWS = 8
@@ -48,6 +48,7 @@ SIGNATURES = {
     "pdm_row_norms_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "pdm_prepare_rows": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _I64, _I64, _F, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "pdm_absmax_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
+    "pdm_lattice_residual_f32": (C.c_int, [_P, _I64, _I64, _I64, _F, _P, _P]),
     "pdm_transpose_split_f16": (C.c_int, [_P, _I64, _I64, _I64, _F, _P, _P, _I64, _P]),
     "pdm_column_moments_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P]),
     "pdm_posterior_stats_plan": (C.c_int, [C.POINTER(StatsArgs), C.c_int, C.POINTER(C.c_int64)]),

@@ -12,7 +12,8 @@ from torch import Tensor
 from . import _cabi
 from ._cabi import PdmError, StatsArgs, check
 
-PRECISIONS = {"exact": _cabi.PREC_EXACT_F32, "f16x3": _cabi.PREC_F16X3, "f16x1": _cabi.PREC_F16X1}
+PRECISIONS = {"exact": _cabi.PREC_EXACT_F32, "f16x3": _cabi.PREC_F16X3, "f16x1": _cabi.PREC_F16X1,
+              "f16x2": _cabi.PREC_F16X2}
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
@@ -91,6 +92,15 @@ class CudaBackend:
         out = torch.empty(1, dtype=torch.float32, device=self.device)
         check(self.lib.pdm_absmax_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
                                       self._stream()), "pdm_absmax_f32")
+        self.launches += 1
+        return out
+
+    def lattice_residual(self, y: Tensor, scale: float) -> Tensor:
+        """(max_j ||y_j - rint(y_j s)/s||^2 / ||y_j||^2,  max |rint(y s)|) as a 2-element device tensor."""
+        y = self._f32(y)
+        out = torch.empty(2, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_lattice_residual_f32(y.data_ptr(), y.shape[0], y.shape[1], y.stride(0), float(scale),
+                                                out.data_ptr(), self._stream()), "pdm_lattice_residual_f32")
         self.launches += 1
         return out
 
@@ -228,13 +238,13 @@ class CudaBackend:
         self.launches += 1
         return p
 
-    def split_gemm(self, a_hi: Tensor, a_lo: Tensor, b_hi: Tensor, b_lo: Tensor, k: int, scale: float,
+    def split_gemm(self, a_hi: Tensor, a_lo: Tensor, b_hi: Tensor, b_lo: Optional[Tensor], k: int, scale: float,
                    out: Optional[Tensor] = None, accumulate: bool = False, cta_group: int = 0) -> Tensor:
         m, d = a_hi.shape[0], b_hi.shape[0]
         if out is None:
             out = torch.empty(m, d, dtype=torch.float32, device=self.device)
         check(self.lib.pdm_split_gemm_f16x3(a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), m, b_hi.data_ptr(),
-                                            b_lo.data_ptr(), b_hi.stride(0), d, k, float(scale), out.data_ptr(),
+                                            _ptr(b_lo), b_hi.stride(0), d, k, float(scale), out.data_ptr(),
                                             out.stride(0), int(accumulate), cta_group, self._stream()),
               "pdm_split_gemm_f16x3")
         self.launches += 1

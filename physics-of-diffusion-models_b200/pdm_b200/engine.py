@@ -45,11 +45,47 @@ def pow2_scale_for(absmax: float) -> float:
     return math.ldexp(1.0, max(-100, min(100, 12 - e)))
 
 
+# ||y_j - hi_j/s|| <= 2^-22 ||y_j|| for every row: the dropped part is a few units of fp32 round-off of the row
+# itself (for pixel data hi/s IS the exact pixel value and the residue is the fp32 rounding of the transform);
+# worst case it moves an energy by 2^-23 (||x||^2 + ||y||^2), 1/4 of the round-off floor of the parity contract.
+LATTICE_RATIO_MAX = 2.0 ** -44
+LATTICE_INT_MAX = 2048.0           # fp16 holds integers up to 2^11 exactly
+
+
+def lattice_candidates(absmax: float) -> list[float]:
+    """Scales s for which y*s could be an fp16-exact integer lattice: the 8-bit pixel grid behind
+    ToTensor / Normalize(0.5, 0.5) (utils/data.py:43-52 of the reference: s = 255 * 2^k) and dyadic data (s = 2^k),
+    largest first, restricted to absmax * s <= 2048."""
+    if not (absmax > 0.0) or math.isinf(absmax) or math.isnan(absmax):
+        return []
+    out = []
+    for base in (1.0, 255.0):
+        k = math.floor(math.log2(LATTICE_INT_MAX / (absmax * base)))
+        for kk in range(k, k - 4, -1):
+            s = base * 2.0 ** kk
+            if absmax * s <= LATTICE_INT_MAX and 2.0 ** -100 < s < 2.0 ** 100:
+                out.append(s)
+    return out
+
+
+def detect_lattice_scale(backend, y: Tensor, absmax: Optional[float] = None) -> float:
+    """The scale under which the rows of y are an fp16-exact lattice, or 0.0."""
+    if absmax is None:
+        absmax = float(backend.absmax(y).item())
+    for s in lattice_candidates(absmax):
+        ratio, vmax = backend.lattice_residual(y, s).tolist()
+        if ratio <= LATTICE_RATIO_MAX and vmax <= LATTICE_INT_MAX:
+            return s
+    return 0.0
+
+
 class EmpiricalDataset:
     """A (shard of a) training set resident on one GPU."""
 
     def __init__(self, data: Tensor, *, backend=None, index_offset: int = 0, n_total: Optional[int] = None,
-                 global_absmax: Optional[float] = None):
+                 global_absmax: Optional[float] = None, lattice_scale: Optional[float] = None):
+        """``global_absmax`` / ``lattice_scale``: whole-dataset facts when ``data`` is one shard of a row-sharded
+        set (every rank must use the same scale; lattice_scale 0.0 = not a lattice, None = detect on ``data``)."""
         self.backend = backend if backend is not None else default_backend()
         dev = self.backend.device
         flat = data.reshape(data.shape[0], -1)
@@ -60,19 +96,31 @@ class EmpiricalDataset:
         self.n_total = int(n_total) if n_total is not None else self.n
         self.y_norm = self.backend.row_norms(self.y)
         self._global_absmax = global_absmax
+        self._lattice = lattice_scale
         self._split = None
         self._tsplit = None
         self._moments = None
         self._scale = None
 
     # -- lazily built device-side views ----------------------------------------------------------
+    def _absmax(self) -> float:
+        if self._global_absmax is None:
+            self._global_absmax = float(self.backend.absmax(self.y).item())
+        return self._global_absmax
+
+    @property
+    def lattice_scale(self) -> float:
+        """s > 0 when y*s is an fp16-exact integer lattice (8-bit image data): the lo part of the split is
+        empty and the two-product mode f16x2 loses nothing.  0.0 otherwise."""
+        if self._lattice is None:
+            detect = getattr(self.backend, "lattice_residual", None)
+            self._lattice = detect_lattice_scale(self.backend, self.y, self._absmax()) if detect is not None else 0.0
+        return self._lattice
+
     @property
     def scale(self) -> float:
         if self._scale is None:
-            amax = self._global_absmax
-            if amax is None:
-                amax = float(self.backend.absmax(self.y).item())
-            self._scale = pow2_scale_for(amax)
+            self._scale = self.lattice_scale or pow2_scale_for(self._absmax())
         return self._scale
 
     def split(self):
@@ -106,7 +154,7 @@ class EmpiricalDataset:
 
 @dataclass
 class EngineConfig:
-    precision: str = "auto"            # auto | exact | f16x3 | f16x1
+    precision: str = "auto"            # auto | exact | f16x3 | f16x2 (lattice datasets only) | f16x1
     tensor_min_dim: int = 256          # auto: below this the exact CUDA-core kernel is used
     cta_group: int = 0                 # 0 = library default (2)
     m_group: int = 0
@@ -148,9 +196,14 @@ class PosteriorEngine:
         p = self.cfg.precision
         if p == "auto":
             tensor_ok = getattr(self.backend, "supports_tensor_path", lambda: False)()
-            return "f16x3" if (self.ds.d >= self.cfg.tensor_min_dim and tensor_ok) else "exact"
-        if p not in ("exact", "f16x3", "f16x1"):
+            if not (self.ds.d >= self.cfg.tensor_min_dim and tensor_ok):
+                return "exact"
+            return "f16x2" if self.ds.lattice_scale > 0 else "f16x3"
+        if p not in ("exact", "f16x3", "f16x2", "f16x1"):
             raise PdmError(f"unknown precision {p!r}")
+        if p == "f16x2" and not self.ds.lattice_scale > 0:
+            raise PdmError("precision f16x2 drops the lo part of the dataset split: it needs a dataset that is an "
+                           "fp16-exact lattice (EmpiricalDataset.lattice_scale > 0), e.g. 8-bit images")
         return p
 
     def rows_per_block(self, row_multiple: int = 1) -> int:
@@ -173,7 +226,9 @@ class PosteriorEngine:
                   energy_out=energy_out, energy_mult=energy_mult)
         if precision == "exact":
             return self.backend.posterior_stats(q=prep["x"], y=ds.y, **kw)
-        return self.backend.posterior_stats(q_split=(prep["hi"], prep["lo"], prep["inv_scale"]), y_split=ds.split(),
+        y_hi, y_lo = ds.split()
+        return self.backend.posterior_stats(q_split=(prep["hi"], prep["lo"], prep["inv_scale"]),
+                                            y_split=(y_hi, None if precision == "f16x2" else y_lo),
                                             y_inv_scale=1.0 / ds.scale, **kw)
 
     def _merge(self, parts: Tensor, inv_temp: Tensor):
@@ -308,6 +363,8 @@ class PosteriorEngine:
                     p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
                 with ph("gemm2"):
                     yt_hi, yt_lo, yscale = vt if vt is not None else (ds.transposed_split() + (ds.scale,))
+                    if vt is None and precision == "f16x2":
+                        yt_lo = None                      # lattice dataset: weights_hi.Y + weights_lo.Y is all there is
                     self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=out[r0:r1],
                                             cta_group=self.cfg.cta_group)
             else:

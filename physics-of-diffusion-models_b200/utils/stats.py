@@ -30,7 +30,7 @@ from torch.utils.data import DataLoader
 from tqdm import tqdm
 
 from pdm_b200 import EmpiricalDataset, PosteriorEngine
-from pdm_b200.engine import default_backend
+from pdm_b200.engine import default_backend, detect_lattice_scale
 
 _ENGINES: dict[int, tuple] = {}
 
@@ -59,8 +59,11 @@ def _engine_for(dataloader: DataLoader) -> PosteriorEngine:
     if world > 1:
         per = (n_total + world - 1) // world
         lo, hi = rank * per, min(n_total, (rank + 1) * per)
-        amax = float(data.abs().max().item())
-        ds = EmpiricalDataset(data[lo:hi], backend=backend, index_offset=lo, n_total=n_total, global_absmax=amax)
+        flat = data.reshape(n_total, -1).to(torch.float32).contiguous()
+        amax = float(backend.absmax(flat).item())
+        lattice = detect_lattice_scale(backend, flat, amax)      # every rank must agree on the operand scale
+        ds = EmpiricalDataset(data[lo:hi], backend=backend, index_offset=lo, n_total=n_total, global_absmax=amax,
+                              lattice_scale=lattice)
         ds.full_moments_source = data          # Tr Sigma_0 is a whole-dataset quantity
     else:
         ds = EmpiricalDataset(data, backend=backend)

@@ -254,3 +254,88 @@ def test_pairwise_dense(backend):
     assert torch.equal(i1, g["nn1_idx"])
     d.scatter_(1, i1[:, None], 1e10)
     assert torch.equal(d.min(1).indices, g["nn2_idx"])
+
+
+# ------------------------------------------------------------------------------------------------
+# lattice datasets (8-bit images through ToTensor + Normalize(0.5, 0.5), utils/data.py:43-52): two-product mode
+# ------------------------------------------------------------------------------------------------
+def pixel_images(n, d, g):
+    px = torch.randint(0, 256, (n, d), generator=g, dtype=torch.uint8)
+    return (px.float() / 255 - 0.5) / 0.5                      # what the reference's transform pipeline yields
+
+
+def test_lattice_detection(backend):
+    from pdm_b200 import EmpiricalDataset
+    from pdm_b200.engine import detect_lattice_scale
+    g = syn.gen(21)
+    dev = backend.device
+    img = pixel_images(300, 192, g)
+    s = detect_lattice_scale(backend, img.to(dev))
+    assert s == 2040.0                                          # 255 * 2^3: y*s = 8*(2p - 255), |.| <= 2040
+    assert detect_lattice_scale(backend, (img * 0.5 + 0.5).to(dev)) == 2040.0      # ToTensor only: y*s = 8p
+    assert detect_lattice_scale(backend, (torch.randint(0, 2, (50, 64), generator=g).float()).to(dev)) == 2048.0   # dyadic
+    assert detect_lattice_scale(backend, (torch.rand(300, 192, generator=g) * 2 - 1).to(dev)) == 0.0
+    one_off = img.clone()
+    one_off[17, 5] += 1e-4                                      # a single off-lattice value disqualifies the set
+    assert detect_lattice_scale(backend, one_off.to(dev)) == 0.0
+    ds = EmpiricalDataset(img, backend=backend)
+    assert ds.lattice_scale == 2040.0 and ds.scale == 2040.0
+    hi, lo = ds.split()
+    assert torch.equal(hi.cpu().float()[:, :192], torch.round(img * 2040.0))
+    assert lo.cpu().float().abs().max() < 1e-3                  # nothing but fp32 rounding residue
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tensor_stats_lattice_two_products(backend, cta_group):
+    """f16x2 (q_hi.y_hi + q_lo.y_hi) on 8-bit image data: same tolerance contract as f16x3."""
+    g = syn.gen(22)
+    for (m, n, d) in ((200, 700, 192), (300, 1000, 3072)):
+        data = pixel_images(n, d, g)
+        x0 = data[torch.randint(0, n, (m,), generator=g)]
+        t_rows = torch.logspace(-3, 3, m)
+        xq = x0 + t_rows.sqrt()[:, None] * torch.randn(m, d, generator=g)
+        aux = torch.rand(n, generator=g) * 0.1
+        ref = oracle_rows(xq, data, t_rows, aux=aux)
+        dev = backend.device
+        y = data.to(dev)
+        x = xq.to(dev)
+        inv_t = (1.0 / t_rows).to(dev)
+        ys = backend.prepare_rows(y, n, fixed_scale=2040.0, want_norms=False)
+        prep = backend.prepare_rows(x, m)
+        for splits, grp in ((0, 0), (3, 2)):
+            parts = backend.posterior_stats(precision="f16x2", M=m, N=n, d=d, q_norm=prep["norms"],
+                                            y_norm=backend.row_norms(y), inv_temp=inv_t,
+                                            q_split=(prep["hi"], prep["lo"], prep["inv_scale"]), y_split=(ys["hi"], None),
+                                            y_inv_scale=1.0 / 2040.0, y_aux=aux.to(dev), cta_group=cta_group,
+                                            n_splits=splits, m_group=grp)
+            out, argmin = backend.merge(parts, inv_t, n)
+            check_stats(out.cpu(), argmin.cpu(), ref, aux=True, what=f"f16x2 cg={cta_group} ({m},{n},{d}) S={splits}")
+
+
+def test_engine_picks_two_products_for_images(backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig, PdmError
+    g = syn.gen(23)
+    n, d, m = 600, 3 * 16 * 16, 96
+    data = pixel_images(n, d, g).view(n, 3, 16, 16)
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=backend), EngineConfig())
+    assert eng.precision() == "f16x2"
+    t_rows = torch.logspace(-2, 2, m)
+    xq = data[:m].reshape(m, -1) + t_rows.sqrt()[:, None] * torch.randn(m, d, generator=g)
+    ref = oracle_rows(xq, data.reshape(n, -1), t_rows)
+    st = eng.stats(xq, t_rows)
+    arbitrated_close(st["entropy"], ref["f32"]["entropy"], ref["f64"]["entropy"], atol=2e-5, floor=2 * ref["floor_e"],
+                     what="engine f16x2 entropy")
+    agree = ref["f32"]["argmin"] == ref["f64"]["argmin"]
+    assert torch.equal(st["argmin"].cpu()[agree], ref["f64"]["argmin"][agree])
+    # posterior mean: weights_hi.Y + weights_lo.Y only
+    got = eng.posterior_mean(xq, t_rows).cpu()
+    e64 = 0.5 * orc.pairwise_sqdist(xq.double(), data.reshape(n, -1).double())
+    p64 = torch.softmax(-(e64 - e64.min(1, keepdim=True).values) / t_rows.double()[:, None], dim=1)
+    ref_mean = p64 @ data.reshape(n, -1).double()
+    e32 = 0.5 * orc.pairwise_sqdist(xq, data.reshape(n, -1))
+    p32 = torch.softmax(-(e32 - e32.min(1, keepdim=True).values) / t_rows[:, None], dim=1)
+    arbitrated_close(got, p32 @ data.reshape(n, -1), ref_mean, atol=2e-5, what="engine f16x2 posterior mean")
+    # forcing the two-product mode on continuous data is an error, not a silent loss of accuracy
+    cont = EmpiricalDataset(torch.rand(300, 256, generator=g) * 2 - 1, backend=backend)
+    with pytest.raises(PdmError):
+        PosteriorEngine(cont, EngineConfig(precision="f16x2")).precision()

@@ -191,3 +191,28 @@ def test_synthetic_generators():
     assert utils.generate_dataset("hypersphere", 8).shape == (80, 8)
     with pytest.raises(ValueError):
         utils.generate_dataset("nope")
+
+
+def test_lattice_candidates_and_detection():
+    """Host logic of the lattice (8-bit image) detection: candidate scales and the acceptance rule."""
+    from pdm_b200.engine import lattice_candidates, detect_lattice_scale, LATTICE_RATIO_MAX
+
+    c = lattice_candidates(1.0)
+    assert c[0] == 2048.0 and c[4:8] == [2040.0, 1020.0, 510.0, 255.0]
+    assert all(s * 1.0 <= 2048.0 for s in c)
+    assert lattice_candidates(0.0) == [] and lattice_candidates(float("inf")) == []
+    assert lattice_candidates(3.0)[0] == 512.0 and lattice_candidates(3.0)[4] == 510.0      # 3 * 510 = 1530 <= 2048
+
+    class Probe:                                                # answers like pdm_lattice_residual_f32 would
+        def __init__(self, good):
+            self.good, self.asked = good, []
+
+        def lattice_residual(self, y, s):
+            self.asked.append(s)
+            return torch.tensor([0.0 if s in self.good else 1e-9, 2040.0])
+
+    y = torch.zeros(4, 4)
+    p = Probe({510.0, 255.0})
+    assert detect_lattice_scale(p, y, absmax=1.0) == 510.0 and p.asked[-3:] == [2040.0, 1020.0, 510.0]
+    assert detect_lattice_scale(Probe(set()), y, absmax=1.0) == 0.0
+    assert LATTICE_RATIO_MAX == 2.0 ** -44
