@@ -73,6 +73,7 @@ struct GemmParams {
     int32_t num_kb;       // number of 64-element k blocks
     int32_t flush_kb;     // k blocks accumulated inside the tensor core before a flush to registers
     uint32_t wait_hint_ns; // suspend-time hint of mbarrier.try_wait
+    uint64_t hint_a, hint_b;   // L2 eviction-priority hints of the A (query) and B (dataset) tile loads
     int32_t m_tiles;      // row super-tiles of 128*CG rows
     int32_t n_tiles;      // column tiles of kBlockN
     int32_t m_group, n_splits;
@@ -184,17 +185,17 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         const int32_t kc = kb * kBlockK;
                         if (CG == 1) {
                             mbar_arrive_expect_tx(fb, C::kStageBytes);
-                            tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
-                            if (TERMS >= 2) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
-                            tma_load_2d(dst + C::kTileBHi * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
-                            if (TERMS == 3) tma_load_2d(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
+                            tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, p.hint_a);
+                            if (TERMS >= 2) tma_load_2d(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, p.hint_a);
+                            tma_load_2d(dst + C::kTileBHi * kTileBytes, &tm_b_hi, fb, kc, b_row, p.hint_b);
+                            if (TERMS == 3) tma_load_2d(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, p.hint_b);
                         } else {
                             if (leader) mbar_arrive_expect_tx(fb, 2u * C::kStageBytes);
                             else mbar_arrive_remote(fb, 0);
-                            tma_load_2d_pair(dst, &tm_a_hi, fb, kc, a_row, kEvictNormal);
-                            if (TERMS >= 2) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, kEvictNormal);
-                            tma_load_2d_pair(dst + C::kTileBHi * kTileBytes, &tm_b_hi, fb, kc, b_row, kEvictNormal);
-                            if (TERMS == 3) tma_load_2d_pair(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, kEvictNormal);
+                            tma_load_2d_pair(dst, &tm_a_hi, fb, kc, a_row, p.hint_a);
+                            if (TERMS >= 2) tma_load_2d_pair(dst + kTileBytes, &tm_a_lo, fb, kc, a_row, p.hint_a);
+                            tma_load_2d_pair(dst + C::kTileBHi * kTileBytes, &tm_b_hi, fb, kc, b_row, p.hint_b);
+                            if (TERMS == 3) tma_load_2d_pair(dst + 3 * kTileBytes, &tm_b_lo, fb, kc, b_row, p.hint_b);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
@@ -546,6 +547,15 @@ static int flush_kb_setting(int terms) {
     return terms == 3 ? 1 : terms == 2 ? 2 : 4;
 }
 
+// L2 eviction priority of the tile loads: PDM_HINT_A / PDM_HINT_B = normal | first | last
+static uint64_t evict_hint_setting(const char* name, uint64_t dflt) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    if (e[0] == 'f') return ptx::kEvictFirst;
+    if (e[0] == 'l') return ptx::kEvictLast;
+    return ptx::kEvictNormal;
+}
+
 static uint32_t wait_hint_setting() {
     static long v = -1;
     if (v < 0) {
@@ -566,27 +576,36 @@ static int require_sm100(DeviceInfo* info) {
     return PDM_OK;
 }
 
-// Pick (m_group, n_splits).  Every CTA group walks ceil(m_tiles/G) * ceil(n_tiles/S) tiles, so the
-// schedule's length is that product (tile quantisation); among the shortest schedules prefer the one whose
-// G live A tiles stay inside an L2 budget (they are re-read from L2 for every column tile) and, after
-// that, the larger G (fewer partial records per row).
+// Pick (m_group, n_splits) = (G, S).  Every CTA group walks ceil(m_tiles/G) * ceil(n_tiles/S) tiles: that product
+// is the schedule's length (tile quantisation).  The dataset is streamed from HBM once per ROUND (= ceil(m_tiles/G)
+// of them) as long as the G live A tiles stay in L2, so among the schedules within 12 % of the shortest one whose A
+// tiles fit a 52 MB L2 budget the one with the fewest rounds wins: the kernel runs at the chip's power cap, where a
+// few idle SMs cost nothing and HBM traffic does (B200, C2 block: (S,G) = (4,16) reads 23 GB per launch,
+// (9,8) 57 GB, same run time).  If nothing fits, the shortest schedule is taken.
 void plan_schedule(int pairs, int64_t m_tiles, int64_t n_tiles, int64_t a_tile_bytes, int* m_group, int* n_splits) {
-    const int64_t budget = 48ll << 20;
+    const int64_t budget = 52ll << 20;
     const int64_t g_cap = std::max<int64_t>(1, budget / std::max<int64_t>(1, a_tile_bytes));
-    int best_g = 1, best_s = 1;
-    int64_t best_steps = -1;
-    bool best_fits = false;
+    int64_t min_steps = -1;
     for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
-        for (int64_t g = std::min<int64_t>(pairs / s, m_tiles); g >= 1; --g) {
-            const int64_t steps = ceil_div(m_tiles, g) * ceil_div(n_tiles, (int64_t)s);
-            const bool fits = g <= g_cap;
-            bool better = best_steps < 0;
-            if (!better) {
-                // allow 2% longer schedules if they keep the A tiles inside the L2 budget
-                const double cost = steps * (fits ? 1.0 : 1.02), bcost = best_steps * (best_fits ? 1.0 : 1.02);
-                better = cost < bcost || (cost == bcost && g > best_g);
+        const int64_t g = std::min<int64_t>(pairs / s, m_tiles);
+        const int64_t steps = ceil_div(m_tiles, g) * ceil_div(n_tiles, (int64_t)s);
+        if (min_steps < 0 || steps < min_steps) min_steps = steps;
+    }
+    int best_g = 0, best_s = 0;
+    int64_t best_rounds = 0, best_steps = 0;
+    for (int pass = 0; pass < 2 && best_g == 0; ++pass) {         // pass 0: inside the L2 budget; pass 1: anything
+        for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
+            for (int64_t g = std::min<int64_t>(pairs / s, m_tiles); g >= 1; --g) {
+                if (pass == 0 && g > g_cap) continue;
+                const int64_t steps = ceil_div(m_tiles, g) * ceil_div(n_tiles, (int64_t)s);
+                if (pass == 0 && steps * 100 > min_steps * 112) continue;
+                const int64_t rounds = ceil_div(m_tiles, g);
+                const bool better = best_g == 0 ||
+                    (pass == 0 ? (rounds < best_rounds || (rounds == best_rounds && steps < best_steps) ||
+                                  (rounds == best_rounds && steps == best_steps && g < best_g))
+                               : (steps < best_steps || (steps == best_steps && g > best_g)));
+                if (better) { best_g = (int)g; best_s = s; best_rounds = rounds; best_steps = steps; }
             }
-            if (better) { best_steps = steps; best_g = (int)g; best_s = s; best_fits = fits; }
         }
     }
     *m_group = best_g;
@@ -617,6 +636,8 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.num_kb = (int32_t)ceil_div(a.d, kBlockK);
     p.flush_kb = flush_kb_setting(terms);
     p.wait_hint_ns = wait_hint_setting();
+    p.hint_a = evict_hint_setting("PDM_HINT_A", kEvictNormal);
+    p.hint_b = evict_hint_setting("PDM_HINT_B", kEvictNormal);
     p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
     p.m_group = a.m_group; p.n_splits = a.n_splits;
@@ -710,6 +731,8 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     p.num_kb = (int32_t)ceil_div(K, tc::kBlockK);
     p.flush_kb = tc::flush_kb_setting(terms);
     p.wait_hint_ns = tc::wait_hint_setting();
+    p.hint_a = tc::evict_hint_setting("PDM_HINT_A", ptx::kEvictNormal);
+    p.hint_b = tc::evict_hint_setting("PDM_HINT_B", ptx::kEvictNormal);
     p.m_tiles = (int32_t)ceil_div(M, (int64_t)tc::kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(d, block_n);
     // every (row tile, column tile) is an independent output tile: spread column tiles first
