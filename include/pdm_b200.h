@@ -213,6 +213,23 @@ int pdm_weighted_mean_exact_f32(const float* p, int64_t ldp, int64_t M, int64_t 
                                 const float* y, int64_t ldy, int64_t d,
                                 float* out, int64_t ldo, int32_t accumulate, pdm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward pass of K8 (autograd through Scheduler.true_posterior_mean_x0, which
+ * scripts/optimize_schedule.py:57-91,151 differentiates with respect to the noise schedule).
+ * With x0_hat = sum_j p_j y_j, upstream gradient g, s_j = y_j.g and a = sum_j p_j s_j:
+ *     d x0_hat / d q . g = Cov_p(s, y) / T   = sum_j p_j (s_j - a) y_j / T            (q = the VE query)
+ *     d x0_hat / d T . g = Cov_p(s, e) / T   = sum_j p_j (s_j - a) e_j / T            (e_j = (E_j - m)/T)
+ * This entry point turns the stored energy tile and S = g.Y^T (from pdm_split_gemm_f16x3 or
+ * pdm_weighted_mean_exact_f32; s_scale[r] is an optional per-row factor on S) into the centred weights
+ *     w[r,j] = p_rj (s_rj - a_r)   and   sums[r] = (a_r, sum_j w_rj e_rj);
+ * the caller contracts w with the dataset like the forward weights.  (Centring first: the uncentred form
+ * sum p s y - a x0_hat cancels to zero at low T and its round-off would be amplified by 1/T.)
+ * ------------------------------------------------------------------------------------------- */
+int pdm_denoiser_backward_weights(const float* energy, int64_t lde, const float* sdot, int64_t lds,
+                                  int64_t M, int64_t N, const float* e_min, const float* l,
+                                  const float* inv_temp, const float* s_scale,
+                                  float* w, int64_t ldw, float* sums, pdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

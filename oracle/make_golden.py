@@ -125,6 +125,37 @@ def golden_denoiser(ref):
     _save("denoiser.npz", **out)
 
 
+def golden_denoiser_grad(ref):
+    """Autograd of the UNMODIFIED reference through Scheduler.true_posterior_mean_x0 (what
+    scripts/optimize_schedule.py:57-91,151 relies on): gradients with respect to xt and to tau."""
+    sch = ref.scheduler.LinearBetaScheduler(1e-4, 2.478e4)
+    g = syn.gen(51)
+    cases = {
+        "img": syn.uniform_images(256, (3, 8, 8), 52),                       # d = 192: exact CUDA-core path
+        "wide": syn.uniform_images(384, (5, 8, 8), 53),                      # d = 320: tensor path
+        "gmm1d": (torch.randn(2000, generator=g) * 0.01 +
+                  torch.tensor([-1.1, -0.9, 0.9, 1.1])[torch.randint(0, 4, (2000,), generator=g)]).view(2000, 1, 1, 1),
+    }
+    taus = torch.tensor([0.08, 0.35, 0.5, 0.7, 0.93])
+    out = {"taus": taus, "min_temp": 1e-4, "max_temp": 2.478e4, "cases": np.array(sorted(cases))}
+    for name, data in cases.items():
+        out[f"{name}_data"] = data
+        for i, tau in enumerate(taus):
+            ab = sch.alpha_bar_from_tau(tau)
+            x0 = data[torch.randint(0, len(data), (12,), generator=g)]
+            xt = (ab.sqrt() * x0 + (1 - ab).sqrt() * torch.randn(x0.shape, generator=g)).requires_grad_(True)
+            t = tau.view(1).clone().requires_grad_(True)
+            up = torch.randn(x0.shape, generator=g)
+            x0hat = sch.true_posterior_mean_x0(xt, t, data)
+            x0hat.backward(up)
+            out[f"{name}_xt_{i}"] = xt.detach()
+            out[f"{name}_up_{i}"] = up
+            out[f"{name}_x0hat_{i}"] = x0hat.detach()
+            out[f"{name}_gxt_{i}"] = xt.grad
+            out[f"{name}_gtau_{i}"] = t.grad
+    _save("denoiser_grad.npz", **out)
+
+
 def golden_metric_utils(ref):
     g = syn.gen(41)
     x = torch.randn(200, 3, generator=g) * torch.tensor([1.0, 0.5, 2.0])
@@ -174,12 +205,13 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    golden_distance(ref)
-    golden_stats(ref)
-    golden_outer_loops(ref)
-    golden_denoiser(ref)
-    golden_metric_utils(ref)
-    golden_cifar_slice(ref)
+    todo = {"distance": golden_distance, "stats": golden_stats, "outer_loops": golden_outer_loops,
+            "denoiser": golden_denoiser, "denoiser_grad": golden_denoiser_grad, "metric_utils": golden_metric_utils,
+            "cifar_slice": golden_cifar_slice}
+    only = sys.argv[1:]                      # python -m oracle.make_golden [name ...]: regenerate a subset
+    for name, fn in todo.items():
+        if not only or name in only:
+            fn(ref)
     return 0
 
 

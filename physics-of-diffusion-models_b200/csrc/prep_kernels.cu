@@ -369,6 +369,39 @@ __global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward of the ideal denoiser: with p_j = exp(-e_j)/l, e_j = (E_j - m)/T and s_j = s_scale * S_j (= y_j . g),
+//   a = sum_j p_j s_j,   w_j = p_j (s_j - a),   sums = (a, sum_j w_j e_j)            one block per query row
+// Centring s before the contraction keeps sum_j w_j y_j = Cov_p(s, y) free of the cancellation
+// sum p s y - a x0_hat, which the caller would otherwise amplify by 1/T.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) denoiser_backward_weights_kernel(
+    const float* __restrict__ energy, int64_t lde, const float* __restrict__ sdot, int64_t lds, int64_t N,
+    const float* __restrict__ e_min, const float* __restrict__ l, const float* __restrict__ inv_temp,
+    const float* __restrict__ s_scale, float* __restrict__ w, int64_t ldw, float* __restrict__ sums) {
+    __shared__ double red_d[32];
+    const int64_t row = blockIdx.x;
+    const float m = e_min[row], it = inv_temp[row], inv_l = 1.f / l[row], sc = s_scale ? s_scale[row] : 1.f;
+    const float* er = energy + row * lde;
+    const float* sr = sdot + row * lds;
+    float* wr = w + row * ldw;
+    double a = 0.0;
+    for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
+        const float e = fminf((__ldg(er + j) - m) * it, kMaxE);
+        a += (double)(fast_exp2(-e * kLog2e) * inv_l) * (double)(sc * __ldg(sr + j));
+    }
+    const float af = (float)block_reduce(a, OpAddD(), 0.0, red_d);
+    double b = 0.0;
+    for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
+        const float e = fminf((__ldg(er + j) - m) * it, kMaxE);
+        const float wj = fast_exp2(-e * kLog2e) * inv_l * (sc * __ldg(sr + j) - af);
+        wr[j] = wj;
+        b += (double)wj * e;
+    }
+    b = block_reduce(b, OpAddD(), 0.0, red_d);
+    if (threadIdx.x == 0) { sums[2 * row] = af; sums[2 * row + 1] = (float)b; }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace pdm
@@ -479,5 +512,19 @@ extern "C" int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t
             p_lo ? reinterpret_cast<__half*>(p_lo) + r0 * ldph : nullptr, ldph, vec ? 1 : 0);
         PDM_CUDA_CHECK(cudaGetLastError());
     }
+    return PDM_OK;
+}
+
+extern "C" int pdm_denoiser_backward_weights(const float* energy, int64_t lde, const float* sdot, int64_t lds,
+                                             int64_t M, int64_t N, const float* e_min, const float* l,
+                                             const float* inv_temp, const float* s_scale,
+                                             float* w, int64_t ldw, float* sums, pdm_stream_t stream) {
+    PDM_REQUIRE(energy && sdot && e_min && l && inv_temp && w && sums && M >= 0 && N > 0 && lde >= N && lds >= N && ldw >= N,
+                "pdm_denoiser_backward_weights: bad arguments");
+    if (M == 0) return PDM_OK;
+    PDM_REQUIRE(M < (1ll << 31), "pdm_denoiser_backward_weights: M too large for one launch");
+    denoiser_backward_weights_kernel<<<(unsigned)M, 256, 0, as_stream(stream)>>>(energy, lde, sdot, lds, N, e_min, l, inv_temp,
+                                                                                s_scale, w, ldw, sums);
+    PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

@@ -78,17 +78,49 @@ class Scheduler(ABC):
 
     @torch.autocast(device_type="cuda", enabled=False)
     def true_posterior_mean_x0(self, xt: Tensor, tau: Tensor, data: Tensor) -> Tensor:
-        if torch.is_grad_enabled() and (xt.requires_grad or (isinstance(tau, Tensor) and tau.requires_grad)):
-            raise NotImplementedError(
-                "true_posterior_mean_x0 on the B200 engine has no backward pass yet (needed only by "
-                "scripts/optimize_schedule.py); call it under torch.no_grad()")
         x = xt.float()
         b = x.shape[0]
         alpha_bar = self.alpha_bar_from_tau(tau).float().reshape(-1)
         if alpha_bar.numel() not in (1, b):
             raise ValueError(f"tau must be scalar-like or hold one value per sample, got {alpha_bar.numel()} for batch {b}")
-        alpha_bar = alpha_bar.expand(b)
-        temp_rows = ((1 - alpha_bar) / alpha_bar).clamp_min(1e-30)
         eng = _engine_for_data(data)
-        x0_hat = eng.posterior_mean(x, temp_rows, post=alpha_bar.rsqrt())
-        return x0_hat.to(x.device).view_as(x)
+        if torch.is_grad_enabled() and (x.requires_grad or alpha_bar.requires_grad):
+            return _IdealDenoiser.apply(x, alpha_bar, eng)       # scripts/optimize_schedule.py differentiates this
+        return _denoise(eng, x, alpha_bar)
+
+
+def _denoise(eng: PosteriorEngine, x: Tensor, alpha_bar: Tensor) -> Tensor:
+    ab = alpha_bar.detach().expand(x.shape[0])
+    temp_rows = ((1 - ab) / ab).clamp_min(1e-30)
+    return eng.posterior_mean(x.detach(), temp_rows, post=ab.rsqrt()).to(x.device).view_as(x)
+
+
+class _IdealDenoiser(torch.autograd.Function):
+    """x0_hat(xt, alpha_bar) with its vector-Jacobian product on the engine.  In the VE variables
+    q = xt / sqrt(ab), T = (1 - ab)/ab the posterior is p_j ~ exp(-||q - y_j||^2 / 2T), so
+        d x0_hat / d q = Cov_p(y) / T,        d x0_hat / d T = Cov_p(E, y) / T^2,
+    chained through dq/dxt = ab^-1/2, dq/dab = -xt ab^-3/2 / 2, dT/dab = -1/ab^2.  ``data`` is a constant."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, alpha_bar: Tensor, eng: PosteriorEngine) -> Tensor:
+        out = _denoise(eng, x, alpha_bar)
+        ctx.eng = eng
+        ctx.save_for_backward(x.detach(), alpha_bar.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        x, alpha_bar = ctx.saved_tensors
+        b = x.shape[0]
+        ab = alpha_bar.expand(b)
+        temp_rows = ((1 - ab) / ab).clamp_min(1e-30)
+        g_q, g_t = ctx.eng.posterior_mean_backward(x, temp_rows, ab.rsqrt(), grad_out.float())
+        g_q = g_q.to(x.device).view_as(x)
+        g_t = g_t.to(x.device)
+        lead = (-1,) + (1,) * (x.ndim - 1)
+        grad_x = g_q * ab.rsqrt().view(lead) if ctx.needs_input_grad[0] else None
+        grad_ab = None
+        if ctx.needs_input_grad[1]:
+            per_row = -0.5 * (g_q * x).reshape(b, -1).sum(1) * ab.pow(-1.5) - g_t / (ab * ab)
+            grad_ab = per_row.sum().reshape(alpha_bar.shape) if alpha_bar.numel() == 1 else per_row.reshape(alpha_bar.shape)
+        return grad_x, grad_ab, None

@@ -20,6 +20,11 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _ld(t: Tensor) -> int:
+    """Leading dimension in elements (a single-row matrix may carry any stride(0))."""
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[-1])
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -82,7 +87,7 @@ class CudaBackend:
     def row_norms(self, x: Tensor) -> Tensor:
         x = self._f32(x)
         out = torch.empty(x.shape[0], dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_row_norms_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
+        check(self.lib.pdm_row_norms_f32(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), out.data_ptr(),
                                          self._stream()), "pdm_row_norms_f32")
         self.launches += 1
         return out
@@ -90,7 +95,7 @@ class CudaBackend:
     def absmax(self, x: Tensor) -> Tensor:
         x = self._f32(x)
         out = torch.empty(1, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_absmax_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
+        check(self.lib.pdm_absmax_f32(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), out.data_ptr(),
                                       self._stream()), "pdm_absmax_f32")
         self.launches += 1
         return out
@@ -99,7 +104,7 @@ class CudaBackend:
         """(max_j ||y_j - rint(y_j s)/s||^2 / ||y_j||^2,  max |rint(y s)|) as a 2-element device tensor."""
         y = self._f32(y)
         out = torch.empty(2, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_lattice_residual_f32(y.data_ptr(), y.shape[0], y.shape[1], y.stride(0), float(scale),
+        check(self.lib.pdm_lattice_residual_f32(y.data_ptr(), y.shape[0], y.shape[1], _ld(y), float(scale),
                                                 out.data_ptr(), self._stream()), "pdm_lattice_residual_f32")
         self.launches += 1
         return out
@@ -123,8 +128,8 @@ class CudaBackend:
             out["lo"] = torch.empty(rows, ldh, dtype=torch.float16, device=self.device)
             out["inv_scale"] = torch.empty(rows, dtype=torch.float32, device=self.device)
         check(self.lib.pdm_prepare_rows(
-            src.data_ptr(), src.shape[0], src.stride(0),
-            _ptr(noise), noise.stride(0) if noise is not None else 0, _ptr(sigma), _ptr(post),
+            src.data_ptr(), src.shape[0], _ld(src),
+            _ptr(noise), _ld(noise) if noise is not None else 0, _ptr(sigma), _ptr(post),
             rows, d, float(fixed_scale),
             _ptr(out["x"]), d, _ptr(out["norms"]),
             _ptr(out["hi"]), _ptr(out["lo"]), ldh, _ptr(out["inv_scale"]), self._stream()), "pdm_prepare_rows")
@@ -137,7 +142,7 @@ class CudaBackend:
         ldt = _round_up(n, 8)
         hi = torch.empty(d, ldt, dtype=torch.float16, device=self.device)
         lo = torch.empty(d, ldt, dtype=torch.float16, device=self.device)
-        check(self.lib.pdm_transpose_split_f16(y.data_ptr(), n, d, y.stride(0), float(scale), hi.data_ptr(),
+        check(self.lib.pdm_transpose_split_f16(y.data_ptr(), n, d, _ld(y), float(scale), hi.data_ptr(),
                                                lo.data_ptr(), ldt, self._stream()), "pdm_transpose_split_f16")
         self.launches += 1
         return hi, lo
@@ -148,7 +153,7 @@ class CudaBackend:
         s = torch.empty(d, dtype=torch.float64, device=self.device)
         s2 = torch.empty(d, dtype=torch.float64, device=self.device)
         mm = torch.empty(2, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_column_moments_f32(y.data_ptr(), n, d, y.stride(0), s.data_ptr(), s2.data_ptr(),
+        check(self.lib.pdm_column_moments_f32(y.data_ptr(), n, d, _ld(y), s.data_ptr(), s2.data_ptr(),
                                               mm.data_ptr(), self._stream()), "pdm_column_moments_f32")
         self.launches += 2
         return s, s2, mm
@@ -167,12 +172,12 @@ class CudaBackend:
         keep = [q_norm, y_norm, inv_temp, y_aux, q, y, q_split, y_split, energy_out]
         if precision == "exact":
             q, y = self._f32(q), self._f32(y)
-            a.q, a.ldq, a.y, a.ldy = q.data_ptr(), q.stride(0), y.data_ptr(), y.stride(0)
+            a.q, a.ldq, a.y, a.ldy = q.data_ptr(), _ld(q), y.data_ptr(), _ld(y)
         else:
             q_hi, q_lo, q_inv = q_split
             y_hi, y_lo = y_split
-            a.q_hi, a.q_lo, a.ldqh, a.q_inv_scale = q_hi.data_ptr(), _ptr(q_lo), q_hi.stride(0), q_inv.data_ptr()
-            a.y_hi, a.y_lo, a.ldyh, a.y_inv_scale = y_hi.data_ptr(), _ptr(y_lo), y_hi.stride(0), float(y_inv_scale)
+            a.q_hi, a.q_lo, a.ldqh, a.q_inv_scale = q_hi.data_ptr(), _ptr(q_lo), _ld(q_hi), q_inv.data_ptr()
+            a.y_hi, a.y_lo, a.ldyh, a.y_inv_scale = y_hi.data_ptr(), _ptr(y_lo), _ld(y_hi), float(y_inv_scale)
         a.q_norm, a.y_norm, a.inv_temp, a.y_aux = q_norm.data_ptr(), y_norm.data_ptr(), _ptr(inv_temp), _ptr(y_aux)
         nfloats = C.c_int64()
         check(self.lib.pdm_posterior_stats_plan(C.byref(a), self.device.index or 0, C.byref(nfloats)),
@@ -182,7 +187,7 @@ class CudaBackend:
             partials = torch.empty(M, a.records_per_row, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
             a.partials = partials.data_ptr()
         if energy_out is not None:
-            a.energy_out, a.lde, a.energy_mult = energy_out.data_ptr(), energy_out.stride(0), float(energy_mult)
+            a.energy_out, a.lde, a.energy_mult = energy_out.data_ptr(), _ld(energy_out), float(energy_mult)
         if self.kernel_events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -203,7 +208,7 @@ class CudaBackend:
         g, m, s, _ = parts.shape
         out = torch.empty(_cabi.OUT_ROWS, m, dtype=torch.float32, device=self.device)
         argmin = torch.empty(m, dtype=torch.int64, device=self.device)
-        check(self.lib.pdm_merge_partials(parts.data_ptr(), m, g, parts.stride(0), s, parts.stride(1),
+        check(self.lib.pdm_merge_partials(parts.data_ptr(), m, g, _ld(parts), s, parts.stride(1),
                                           inv_temp.data_ptr(), n_total, out.data_ptr(), argmin.data_ptr(),
                                           self._stream()), "pdm_merge_partials")
         self.launches += 1
@@ -214,7 +219,7 @@ class CudaBackend:
         parts = parts.contiguous()
         m, s, _ = parts.shape
         out = torch.empty(m, 1, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_reduce_partials(parts.data_ptr(), m, 1, 0, s, parts.stride(0), inv_temp.data_ptr(),
+        check(self.lib.pdm_reduce_partials(parts.data_ptr(), m, 1, 0, s, _ld(parts), inv_temp.data_ptr(),
                                            out.data_ptr(), self._stream()), "pdm_reduce_partials")
         self.launches += 1
         return out
@@ -226,13 +231,13 @@ class CudaBackend:
             ld = _round_up(n, 8)
             hi = torch.empty(m, ld, dtype=torch.float16, device=self.device)
             lo = torch.empty(m, ld, dtype=torch.float16, device=self.device)
-            check(self.lib.pdm_weights_from_energy(energy.data_ptr(), energy.stride(0), m, n, e_min.data_ptr(),
+            check(self.lib.pdm_weights_from_energy(energy.data_ptr(), _ld(energy), m, n, e_min.data_ptr(),
                                                    l.data_ptr(), inv_temp.data_ptr(), None, 0, hi.data_ptr(),
                                                    lo.data_ptr(), ld, self._stream()), "pdm_weights_from_energy")
             self.launches += 1
             return hi, lo
         p = torch.empty(m, n, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_weights_from_energy(energy.data_ptr(), energy.stride(0), m, n, e_min.data_ptr(),
+        check(self.lib.pdm_weights_from_energy(energy.data_ptr(), _ld(energy), m, n, e_min.data_ptr(),
                                                l.data_ptr(), inv_temp.data_ptr(), p.data_ptr(), n, None, None, 0,
                                                self._stream()), "pdm_weights_from_energy")
         self.launches += 1
@@ -243,9 +248,9 @@ class CudaBackend:
         m, d = a_hi.shape[0], b_hi.shape[0]
         if out is None:
             out = torch.empty(m, d, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_split_gemm_f16x3(a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), m, b_hi.data_ptr(),
-                                            _ptr(b_lo), b_hi.stride(0), d, k, float(scale), out.data_ptr(),
-                                            out.stride(0), int(accumulate), cta_group, self._stream()),
+        check(self.lib.pdm_split_gemm_f16x3(a_hi.data_ptr(), a_lo.data_ptr(), _ld(a_hi), m, b_hi.data_ptr(),
+                                            _ptr(b_lo), _ld(b_hi), d, k, float(scale), out.data_ptr(),
+                                            _ld(out), int(accumulate), cta_group, self._stream()),
               "pdm_split_gemm_f16x3")
         self.launches += 1
         return out
@@ -255,8 +260,21 @@ class CudaBackend:
         d = y.shape[1]
         if out is None:
             out = torch.empty(m, d, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_weighted_mean_exact_f32(p.data_ptr(), p.stride(0), m, n, y.data_ptr(), y.stride(0), d,
-                                                   out.data_ptr(), out.stride(0), int(accumulate), self._stream()),
+        check(self.lib.pdm_weighted_mean_exact_f32(p.data_ptr(), _ld(p), m, n, y.data_ptr(), _ld(y), d,
+                                                   out.data_ptr(), _ld(out), int(accumulate), self._stream()),
               "pdm_weighted_mean_exact_f32")
         self.launches += 1
         return out
+
+    def denoiser_backward_weights(self, energy: Tensor, sdot: Tensor, e_min: Tensor, l: Tensor, inv_temp: Tensor,
+                                  s_scale: Optional[Tensor] = None):
+        """Centred weights w = p * (s - a) (M, N), s = s_scale * sdot, a = sum_j p_j s_j, and sums (M, 2) = (a, sum w e)."""
+        m, n = energy.shape
+        w = torch.empty(m, n, dtype=torch.float32, device=self.device)
+        sums = torch.empty(m, 2, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_denoiser_backward_weights(energy.data_ptr(), _ld(energy), sdot.data_ptr(), _ld(sdot),
+                                                     m, n, e_min.data_ptr(), l.data_ptr(), inv_temp.data_ptr(),
+                                                     _ptr(s_scale), w.data_ptr(), _ld(w), sums.data_ptr(),
+                                                     self._stream()), "pdm_denoiser_backward_weights")
+        self.launches += 1
+        return w, sums

@@ -99,6 +99,7 @@ class EmpiricalDataset:
         self._lattice = lattice_scale
         self._split = None
         self._tsplit = None
+        self._yt = None
         self._moments = None
         self._scale = None
 
@@ -134,6 +135,12 @@ class EmpiricalDataset:
         if self._tsplit is None:
             self._tsplit = self.backend.transpose_split(self.y, self.scale)
         return self._tsplit
+
+    def transposed(self) -> Tensor:
+        """y^T (d, n) fp32, for the exact-path contraction g . Y^T of the denoiser's backward pass."""
+        if self._yt is None:
+            self._yt = self.y.t().contiguous()
+        return self._yt
 
     def moments(self):
         """(column sums, column sums of squares, [min, max]) -- fp64 / fp32 device tensors."""
@@ -376,6 +383,55 @@ class PosteriorEngine:
             import torch.distributed as dist
             dist.all_reduce(out, group=self.group)
         return out
+
+    def posterior_mean_backward(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor], grad_out: Tensor):
+        """Vector-Jacobian product of ``posterior_mean`` (no ``values``): for upstream gradient g (M, d) returns
+        (g_q (M, d), g_T (M,)), the gradients with respect to the VE query rows q = x * post and to the per-row
+        temperature.  The energies are recomputed (nothing of size M x N is kept between forward and backward):
+            s_j = y_j . g,  a = sum_j p_j s_j,   g_q = sum_j p_j (s_j - a) y_j / T = Cov_p(s, y) / T,
+            g_T = sum_j p_j (s_j - a) e_j / T = Cov_p(s, e) / T        with e_j = (E_j - E_min) / T."""
+        if self.world > 1:
+            raise PdmError("posterior_mean_backward is not available with a sharded dataset yet")
+        dev = self.backend.device
+        ds = self.ds
+        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        g = grad_out.reshape(grad_out.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        m = xf.shape[0]
+        temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
+        if post is not None:
+            post = post.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
+        precision = self.precision()
+        tensor = precision != "exact"
+        g_q = torch.empty(m, ds.d, dtype=torch.float32, device=dev)
+        g_t = torch.empty(m, dtype=torch.float32, device=dev)
+        step = max(128, min(m, self.cfg.max_energy_bytes // (ds.n * 12)))      # energy, S and w tiles
+        for r0 in range(0, m, step):
+            r1 = min(m, r0 + step)
+            rows = r1 - r0
+            inv_temp = (1.0 / temp_rows[r0:r1]).contiguous()
+            prep = self._prepare(xf[r0:r1], rows, None, None, None if post is None else post[r0:r1], precision, False)
+            energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
+            parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)
+            st, _ = self._merge(parts, inv_temp)
+            e_min, l = st[_cabi.OUT_E_MIN], st[_cabi.OUT_L]
+            if tensor:
+                y_hi, y_lo = ds.split()
+                gp = self.backend.prepare_rows(g[r0:r1], rows, want_norms=False)
+                sdot = self.backend.split_gemm(gp["hi"], gp["lo"], y_hi, None if precision == "f16x2" else y_lo, ds.d,
+                                               1.0 / ds.scale, cta_group=self.cfg.cta_group)      # (rows, n) * 2^k_row
+                w, sums = self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp, gp["inv_scale"])
+                wp = self.backend.prepare_rows(w, rows, want_norms=False)
+                yt_hi, yt_lo = ds.transposed_split()
+                acc = self.backend.split_gemm(wp["hi"], wp["lo"], yt_hi, None if precision == "f16x2" else yt_lo, ds.n,
+                                              1.0 / ds.scale, cta_group=self.cfg.cta_group)
+                acc = acc * wp["inv_scale"][:, None]
+            else:
+                sdot = self.backend.weighted_mean_exact(g[r0:r1], ds.transposed())
+                w, sums = self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp)
+                acc = self.backend.weighted_mean_exact(w, ds.y)
+            g_q[r0:r1] = acc * inv_temp[:, None]
+            g_t[r0:r1] = sums[:, 1] * inv_temp
+        return g_q, g_t
 
     # -- dense distances (callers of compute_pw_dist_sqr index / min / scatter the matrix) -----------
     def pairwise_sqdist(self, x: Tensor) -> Tensor:

@@ -152,3 +152,11 @@ class FakeBackend:
         else:
             out.copy_(r)
         return out
+
+    def denoiser_backward_weights(self, energy, sdot, e_min, l, inv_temp, s_scale=None):
+        e = (energy - e_min[:, None]) * inv_temp[:, None]
+        p = torch.exp(-e) / l[:, None]
+        s = sdot if s_scale is None else sdot * s_scale[:, None]
+        a = (p * s).sum(1)
+        w = p * (s - a[:, None])
+        return w, torch.stack([a, (w * e).sum(1)], dim=1)

@@ -162,3 +162,103 @@ def test_metric_utils_dropin(cuda_device):
         got = utils.compute_metric_scalar(0.0, xd, n_y)
         assert got.device.type == "cuda"
         torch.testing.assert_close(got.cpu(), g["scalar_1"], rtol=2e-3, atol=2e-3)
+
+
+def _grad_close(ours, ref32, ref64, rel, what, floor=0.0):
+    """Gradients: within `rel` of the gradient's own scale (max |ref64|) plus an absolute round-off floor, or within
+    twice the reference's own fp32 error."""
+    ours, ref32, ref64 = ours.detach().double().cpu(), ref32.detach().double().cpu(), ref64.detach().double().cpu()
+    tol = torch.maximum(torch.full_like(ref64, rel * (ref64.abs().max().item() + 1e-12) + 1e-7 + floor),
+                        2 * (ref32 - ref64).abs())
+    err = (ours - ref64).abs()
+    assert (err <= tol).all(), f"{what}: worst err {err.max().item():.3e} vs scale {ref64.abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("case", ["img", "wide", "gmm1d"])
+def test_denoiser_backward_matches_reference_autograd(cuda_device, case):
+    """loss.backward() through DDPMTrue / Scheduler.true_posterior_mean_x0 (scripts/optimize_schedule.py:57-91,151):
+    engine VJP against the reference's own autograd gradients (golden) with the fp64 oracle as arbiter."""
+    import diffusion.scheduler.scheduler as sched
+    from diffusion import DDPMTrue
+    from diffusion.scheduler import LinearBetaScheduler
+    sched._DENOISER_ENGINES.clear()
+    g = load_golden("denoiser_grad.npz")
+    sch = LinearBetaScheduler(float(g["min_temp"]), float(g["max_temp"]))
+    data = g[f"{case}_data"].to(cuda_device)
+    model = DDPMTrue(sch, "x0", data)
+    for i, tau in enumerate(g["taus"]):
+        x = g[f"{case}_xt_{i}"].to(cuda_device).requires_grad_(True)
+        t = tau.view(1).to(cuda_device).requires_grad_(True)
+        up = g[f"{case}_up_{i}"]
+        out = model(x, t)
+        assert out.requires_grad and out.shape == x.shape and out.device == x.device
+        out.backward(up.to(cuda_device))
+        x64 = g[f"{case}_xt_{i}"].double().requires_grad_(True)
+        t64 = tau.view(1).double().requires_grad_(True)
+        ref = orc.posterior_mean_x0(x64, sch.alpha_bar_from_tau(t64), g[f"{case}_data"], dtype=torch.float64)
+        ref.backward(up.double())
+        arbitrated_close(out, g[f"{case}_x0hat_{i}"], ref.detach(), atol=2e-5, what=f"{case} x0hat tau#{i}")
+        # the weights move by (round-off of an fp32 energy)/T, and the gradient (a covariance under those weights,
+        # over T) moves with them: allow that on top of the 2e-4 of the gradient's scale
+        ab = sch.alpha_bar_from_tau(tau.double())
+        q = g[f"{case}_xt_{i}"].double().reshape(len(up), -1) / ab.sqrt()
+        yn = (g[f"{case}_data"].double().reshape(len(data), -1) ** 2).sum(1).max()
+        floor_e = (8 * 2.0 ** -24 * ((q ** 2).sum(1).max() + yn) / ((1 - ab) / ab)).item()
+        # Cov_p(s, y)/T is a sum of p_j (s_j - a) y_j with s_j = y_j . g evaluated in fp32: near a delta posterior the
+        # difference s_j - a cancels, leaving ulp(max |s|) * max |y| / T (times dq/dxt = ab^-1/2) of round-off
+        yflat = g[f"{case}_data"].double().reshape(len(data), -1)
+        s_max = (up.double().reshape(len(up), -1) @ yflat.t()).abs().max().item()
+        floor_g = 8 * 2.0 ** -24 * s_max * yflat.abs().max().item() / ((1 - ab) / ab).item() / ab.sqrt().item()
+        _grad_close(x.grad, g[f"{case}_gxt_{i}"], x64.grad, 2e-4 + 2 * floor_e, f"{case} grad xt tau#{i}", floor=floor_g)
+        # d/dtau sums g_q . xt over the whole batch (B * d terms carrying the round-off above) times |d ab / d tau|
+        tq = tau.view(1).double().requires_grad_(True)
+        dab = torch.autograd.grad(sch.alpha_bar_from_tau(tq).sum(), tq)[0].abs().item()
+        floor_t = (math.sqrt(up.numel()) * (floor_g / 8) * ab.sqrt().item() * g[f"{case}_xt_{i}"].abs().max().item()
+                   * 0.5 * ab.item() ** -1.5 * dab)
+        _grad_close(t.grad, g[f"{case}_gtau_{i}"], t64.grad, 1e-3 + 4 * floor_e, f"{case} grad tau tau#{i}", floor=floor_t)
+    eng = sched._engine_for_data(data)
+    assert eng.precision() == ("f16x3" if case == "wide" else "exact")
+
+
+def test_denoiser_backward_lattice_and_sampler_chain(cuda_device):
+    """Two-product (8-bit image) mode under autograd, through a two-step differentiable DDIM chain like
+    optimize_schedule.py's DifferentiableSampler: gradient with respect to the schedule's log-temperatures."""
+    import diffusion.scheduler.scheduler as sched
+    from diffusion import DDPMTrue, DDPMPredictions
+    from diffusion.scheduler import LinearBetaScheduler, cast_log_temp
+    sched._DENOISER_ENGINES.clear()
+    gen = torch.Generator().manual_seed(5)
+    n, shape = 500, (4, 8, 8)
+    px = torch.randint(0, 256, (n, *shape), generator=gen, dtype=torch.uint8)
+    data = (px.float() / 255 - 0.5) / 0.5
+    sch = LinearBetaScheduler(1e-4, 2.478e4)
+    x_init = torch.randn(16, *shape, generator=gen)
+
+    def chain(model, log_temp, x0, dtype):
+        xt = x0.to(dtype)
+        for idx in (1, 0):
+            tau = sch.tau_from_log_temp(log_temp[idx]).clip(0, 1)
+            ab = cast_log_temp(sch.alpha_bar_from_tau(tau), xt)
+            pred = DDPMPredictions(model(xt, tau.view(1)), xt, ab, "x0")
+            prev_ab = cast_log_temp(sch.alpha_bar_from_tau(sch.tau_from_log_temp(log_temp[idx - 1]).clip(0, 1)), xt) \
+                if idx > 0 else torch.ones_like(ab) * (1 - 1e-6)
+            xt = prev_ab.sqrt() * pred.x0 + (1 - prev_ab).sqrt() * pred.eps
+        return xt
+
+    model = DDPMTrue(sch, "x0", data.to(cuda_device))
+    lt = torch.tensor([-1.0, 1.5], device=cuda_device, requires_grad=True)
+    out = chain(model, lt, x_init.to(cuda_device), torch.float32)
+    loss = (out ** 2).mean()
+    loss.backward()
+    assert sched._engine_for_data(model.train_data).precision() == "f16x2"
+
+    class Ref64(torch.nn.Module):
+        def forward(self, xt, tau):
+            return orc.posterior_mean_x0(xt, sch.alpha_bar_from_tau(tau), data, dtype=torch.float64)
+
+    lt64 = torch.tensor([-1.0, 1.5], dtype=torch.float64, requires_grad=True)
+    out64 = chain(Ref64(), lt64, x_init, torch.float64)
+    loss64 = (out64 ** 2).mean()
+    loss64.backward()
+    assert abs(loss.item() - loss64.item()) <= 1e-4 * abs(loss64.item()) + 1e-6
+    assert (lt.grad.double().cpu() - lt64.grad).abs().max().item() <= 2e-3 * lt64.grad.abs().max().item() + 1e-7

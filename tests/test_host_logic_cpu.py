@@ -147,9 +147,42 @@ def test_denoiser_dropin(fake):
         torch.testing.assert_close(got, g[f"x0hat_{i}"], rtol=2e-3, atol=2e-4)
         pred = model.get_predictions(g[f"xt_{i}"], sch.log_temp_from_tau(tau.view(1)))
         torch.testing.assert_close(pred.x0, g[f"x0hat_{i}"], rtol=2e-3, atol=2e-4)
-    x = g["xt_0"].clone().requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        sch.true_posterior_mean_x0(x, g["taus"][:1], g["data"])
+
+
+def test_denoiser_backward_chain_rule(fake):
+    """Autograd through Scheduler.true_posterior_mean_x0 (scripts/optimize_schedule.py differentiates the sampler
+    with respect to the schedule): engine VJP + chain rule against torch autograd on the fp64 oracle."""
+    from diffusion.scheduler import LinearBetaScheduler
+    g = load_golden("denoiser.npz")
+    sch = LinearBetaScheduler(float(g["min_temp"]), float(g["max_temp"]))
+    data = g["data"]
+    gen = torch.Generator().manual_seed(3)
+    for i in (0, len(g["taus"]) // 2, len(g["taus"]) - 1):
+        xt = g[f"xt_{i}"][:24]
+        up = torch.randn(xt.shape, generator=gen)
+        for per_sample in (False, True):
+            tau0 = g["taus"][i].double().clamp(1e-3, 1 - 1e-3)
+            tau = (tau0.repeat(len(xt)) if per_sample else tau0.view(1)).float().requires_grad_(True)
+            x = xt.clone().requires_grad_(True)
+            out = sch.true_posterior_mean_x0(x, tau, data)
+            out.backward(up)
+            # oracle: the reference's formula in fp64 under torch autograd
+            x64 = xt.double().requires_grad_(True)
+            tau64 = tau.detach().double().requires_grad_(True)
+            ab64 = sch.alpha_bar_from_tau(tau64)
+            if per_sample:      # the reference's formula takes one noise level per call: evaluate row by row
+                ref = torch.cat([orc.posterior_mean_x0(x64[r:r + 1], ab64[r:r + 1], data, dtype=torch.float64)
+                                 for r in range(len(xt))])
+            else:
+                ref = orc.posterior_mean_x0(x64, ab64, data, dtype=torch.float64)
+            ref.backward(up.double())
+            torch.testing.assert_close(out.detach().double(), ref.detach(), rtol=2e-3, atol=2e-4)
+            scale = x64.grad.abs().max().item() + 1e-12
+            assert (x.grad.double() - x64.grad).abs().max().item() <= 2e-3 * scale + 1e-6
+            tscale = tau64.grad.abs().max().item() + 1e-12
+            assert (tau.grad.double() - tau64.grad).abs().max().item() <= 5e-3 * tscale + 1e-6
+    # no graph is built when nothing requires grad
+    assert not sch.true_posterior_mean_x0(g["xt_0"], g["taus"][:1], data).requires_grad
 
 
 def test_distance_dropin(fake):

@@ -137,3 +137,25 @@ def test_cifar_slice():
     xq = ab.sqrt() * x0 + (1 - ab).sqrt() * torch.randn(b, 3, 32, 32, generator=syn.gen(int(g["q_seed"])))
     assert xq.double().sum().item() == float(g["xq_checksum"])
     assert torch.equal(orc.posterior_mean_x0(xq, ab, data), g["x0hat"])
+
+
+def test_oracle_denoiser_gradients_match_reference_autograd():
+    """The oracle's ideal denoiser, differentiated by torch autograd, against the gradients the UNMODIFIED reference
+    produced for the same inputs (tests/golden/denoiser_grad.npz, oracle/make_golden.py:golden_denoiser_grad)."""
+    import math
+    g = load_golden("denoiser_grad.npz")
+    scale, gamma = 1 + float(g["min_temp"]), math.log((1 + float(g["max_temp"])) / (1 + float(g["min_temp"])))
+    for name in [str(c) for c in g["cases"]]:
+        data = g[f"{name}_data"]
+        for i, tau in enumerate(g["taus"]):
+            x = g[f"{name}_xt_{i}"].clone().requires_grad_(True)
+            t = tau.view(1).clone().requires_grad_(True)
+            log_temp = ((t.pow(2) * gamma).exp() * scale - 1).log()       # diffusion/scheduler/linear.py:11-13
+            ab = torch.sigmoid(-log_temp)
+            out = orc.posterior_mean_x0(x, ab, data)
+            out.backward(g[f"{name}_up_{i}"])
+            torch.testing.assert_close(out.detach(), g[f"{name}_x0hat_{i}"], rtol=1e-5, atol=1e-6)
+            gs = g[f"{name}_gxt_{i}"].abs().max().item()
+            assert (x.grad - g[f"{name}_gxt_{i}"]).abs().max().item() <= 1e-4 * gs + 1e-7, (name, i)
+            ts = g[f"{name}_gtau_{i}"].abs().max().item()
+            assert (t.grad - g[f"{name}_gtau_{i}"]).abs().max().item() <= 1e-3 * ts + 1e-6, (name, i)
