@@ -252,6 +252,7 @@ def run_ours(args):
                 backend.launches - launches0, phases, clk)
 
     ms_total, k_ms, k_pairs, launches, phases, clocks = measure(eng, x0, ClockSampler(local) if rank == 0 else None)
+    plan = list(getattr(backend, "last_plan", ()))       # (n_splits, m_group, cta_group) of the headline launches
     if phases is not None and rank == 0:
         print("phase ms/step:", {k: round(v / max(1, args.steps), 2) for k, v in phases.items()}, file=sys.stderr)
     pairs_per_step = b * n_t * n
@@ -282,6 +283,36 @@ def run_ours(args):
                         "unit": UNIT, "ms_per_step": ms_px / max(1, args.steps), "kernel_algorithmic_tflops": ach_px,
                         "kernel_ms_per_step": k_ms_px / max(1, args.steps)}
         del eng_px, ds_px, x0_px
+        torch.cuda.empty_cache()
+
+    # ---- ideal-denoiser step at the sampling shape (config C5: B = 10 000 queries) --------
+    # One call of PosteriorEngine.posterior_mean = what DDPMTrue.forward runs per sampling step: distances +
+    # statistics, weights, and the weighted mean (two contractions: 4*d algorithmic flop per pair).
+    denoiser_line = None
+    if os.environ.get("PDM_BENCH_DENOISER", "1") == "1":
+        mq = env_int("PDM_BENCH_DENOISER_M", 10_000)
+        torch.manual_seed(11)
+        ab = torch.tensor(0.5, device=dev)
+        xq = ab.sqrt() * data_full[torch.randint(0, n, (mq,), device=dev)] + (1 - ab).sqrt() * torch.randn(mq, d, device=dev)
+        t_rows = ((1 - ab) / ab).expand(mq)
+        post = ab.rsqrt().expand(mq)
+        for _ in range(max(1, args.warmup)):
+            eng.posterior_mean(xq, t_rows, post=post)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            x0_hat = eng.posterior_mean(xq, t_rows, post=post)
+        d1.record()
+        barrier()
+        dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
+        if world > 1:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        dms = float(dms.item()) / max(1, args.steps)
+        denoiser_line = {"workload": f"C5 step: {mq} queries x N={n}, d={d} (posterior mean, VP form)", "precision": precision,
+                         "ms_per_step": dms, "value": mq * n / (dms * 1e-3), "unit": UNIT,
+                         "algorithmic_tflops": 4.0 * d * mq * n / (dms * 1e-3) / 1e12, "flops_per_pair": 4 * d}
+        del xq, x0_hat
         torch.cuda.empty_cache()
 
     # ---- e2e through the reference-facing API with host inputs --------------------------------
@@ -326,7 +357,7 @@ def run_ours(args):
                                    "(compute_stats_batch)", "N": n, "d": d, "B": b, "n_T": n_t,
                        "precision": precision, "sharding": f"dataset rows / {world}",
                        "l2": "inputs (dataset 614 MB + queries) exceed the 126 MB L2; no flush needed",
-                       "plan_splits_group_cta": list(getattr(backend, "last_plan", ()))},
+                       "plan_splits_group_cta": plan},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "utils.stats.compute_stats_batch(dataloader, x0_traj, temp), dataset cached on device "
                            "after the first call"},
@@ -337,6 +368,9 @@ def run_ours(args):
                          "peak_source": peaks["source"], "flops_per_pair": 2 * d},
             "clocks": clocks,
         }
+        if denoiser_line is not None:
+            denoiser_line["roofline_frac"] = denoiser_line["algorithmic_tflops"] / peaks["tflops"]
+            line["denoiser_step"] = denoiser_line
         if lattice_line is not None:
             peak = peaks["tflops"]
             lattice_line["roofline_frac"] = lattice_line["kernel_algorithmic_tflops"] / peak
