@@ -79,6 +79,24 @@ def measured_peaks():
     return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel at the bench's block shape, from
+    the committed `ncu --set full` summary (profiles/, captured with PDM_BENCH_NT=56 = one block of the C2 step)."""
+    path = os.path.join(ROOT, "profiles", "r1_fused_gemm_ncu_full_bench_block.csv")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    try:
+        with open(path) as f:
+            for ln in f:
+                parts = ln.strip().split(",")
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(parts[1]) * unit.get(parts[2], 1.0)
+                    seen += 1
+    except OSError:
+        return None
+    return total if seen == 2 else None
+
+
 class ClockSampler:
     """nvidia-smi samples of SM clock / throttle reasons while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -363,7 +381,10 @@ def run_ours(args):
                            "after the first call"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["tflops"], "traffic": None, "kernel": "pdm::tc::fused_gemm_kernel",
+                         "frac": ach / peaks["tflops"], "traffic": profiled_traffic() if (world == 1 and n_t * b >= 57344) else None,
+                         "traffic_note": "HBM bytes per launch (57344 query rows x full dataset) from profiles/r1_fused_gemm_ncu_full_bench_block.csv; "
+                                         "algorithmic minimum 1.3e9 (operands once)",
+                         "kernel": "pdm::tc::fused_gemm_kernel",
                          "executed_tflops": terms * ach, "kernel_ms_per_step": k_ms / max(1, args.steps),
                          "peak_source": peaks["source"], "flops_per_pair": 2 * d},
             "clocks": clocks,
