@@ -390,7 +390,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if denoiser_line is not None:
-            denoiser_line["roofline_frac"] = denoiser_line["algorithmic_tflops"] / peaks["tflops"]
+            denoiser_line["roofline_frac"] = denoiser_line["algorithmic_tflops"] / (peaks["tflops"] * world)
             line["denoiser_step"] = denoiser_line
         if lattice_line is not None:
             peak = peaks["tflops"]
