@@ -168,8 +168,10 @@ class EngineConfig:
     n_splits: int = 0
     max_query_bytes: int = 2 << 30     # scratch budget for one block of query rows (noise + split)
     max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
-    sync_noise: bool = True            # sharded runs: broadcast rank 0's noise (set False when every rank
-                                       # seeds its generator identically and draws the same stream)
+    sync_noise: bool = True            # sharded runs: make every rank draw rank 0's noise stream (set False when
+                                       # every rank seeds its generator identically)
+    slice_noise: bool = True           # sharded CUDA runs: each rank draws + prepares 1/world of the query rows and
+                                       # the prepared operands are all-gathered (False: every rank draws everything)
 
     @staticmethod
     def from_env() -> "EngineConfig":
@@ -249,17 +251,20 @@ class PosteriorEngine:
         return self.backend.merge(parts, inv_temp, self.ds.n_total)
 
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
-                    sigma: Optional[Tensor] = None, post: Optional[Tensor] = None, aux: Optional[Tensor] = None):
+                    sigma: Optional[Tensor] = None, post: Optional[Tensor] = None, aux: Optional[Tensor] = None,
+                    prep: Optional[dict] = None):
         """Statistics for ``rows`` query rows; returns (out (8, rows), argmin (rows,)) device tensors.
-        Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional)."""
+        Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional); ``prep`` passes
+        already prepared operands (rank-sliced preparation of a sharded run) instead."""
         precision = self.precision()
         ph = getattr(self.backend, "phase", None)
         if ph is None:
             import contextlib
             ph = lambda _n: contextlib.nullcontext()      # noqa: E731  (test doubles without phase timing)
         inv_temp = (1.0 / temp_rows.to(torch.float32)).contiguous()
-        with ph("prepare"):
-            prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
+        if prep is None:
+            with ph("prepare"):
+                prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
         with ph("fused"):
             parts = self._local_partials(prep, rows, inv_temp, aux, precision)
         with ph("merge"):
@@ -297,6 +302,10 @@ class PosteriorEngine:
         if noise_fn is None and PosteriorEngine.noise_hook is not None:
             noise_fn = lambda i: PosteriorEngine.noise_hook(i, tuple(x0.shape), dev)     # noqa: E731
         draw = noise_fn
+        sliced = self.world > 1 and draw is None and dev.type == "cuda" and self.cfg.slice_noise
+        if sliced:
+            t_per_block = max(self.world, t_per_block // self.world * self.world)
+            self._sync_generator(dev)
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
@@ -304,6 +313,14 @@ class PosteriorEngine:
             if ph is None:
                 import contextlib
                 ph = lambda _n: contextlib.nullcontext()  # noqa: E731
+            if sliced:
+                t_rows = temp[t0:t1].repeat_interleave(b)
+                with ph("noise+prepare+gather"):
+                    prep = self._sliced_prepare(x0, x0f, temp[t0:t1], dev)
+                o, i = self.stats_block(x0f, nb * b, t_rows, aux=aux, prep=prep)
+                outs.append(o)
+                idxs.append(i)
+                continue
             with ph("noise"):
                 noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
                 for i in range(nb):
@@ -324,6 +341,67 @@ class PosteriorEngine:
         res = {k: out[j].view(n_t, b) for j, k in enumerate(STAT_KEYS)}
         res["argmin"] = (torch.cat(idxs) if len(idxs) > 1 else idxs[0]).view(n_t, b)
         return res
+
+    # -- sharded runs: every rank draws and prepares 1/world of the query rows -----------------------
+    _RANDN_OFFSETS: dict = {}
+
+    @staticmethod
+    def _randn_offset_step(shape: tuple, dev: torch.device) -> int:
+        """By how much one ``torch.randn(*shape, device=dev)`` advances the Philox offset of the CUDA generator
+        (a function of numel and the device; measured on a scratch generator, never guessed)."""
+        key = (int(math.prod(shape)), str(dev))
+        step = PosteriorEngine._RANDN_OFFSETS.get(key)
+        if step is None:
+            g = torch.Generator(device=dev)
+            g.manual_seed(0)
+            o0 = g.get_offset()
+            torch.randn(*shape, device=dev, generator=g)
+            step = g.get_offset() - o0
+            PosteriorEngine._RANDN_OFFSETS[key] = step
+        return step
+
+    def _sync_generator(self, dev: torch.device) -> None:
+        """Give every rank rank 0's CUDA generator state (seed and offset), so that each can draw its slice of the
+        one noise stream a single-GPU run would draw."""
+        if not self.cfg.sync_noise:
+            return
+        import torch.distributed as dist
+        state = torch.cuda.get_rng_state(dev).to(dev)
+        dist.broadcast(state, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        torch.cuda.set_rng_state(state.cpu(), dev)
+
+    def _sliced_prepare(self, x0: Tensor, x0f: Tensor, temps: Tensor, dev: torch.device) -> dict:
+        """Operands of the rows (t, b), t in ``temps``: this rank draws the noise of its ceil(nb/world) temperatures
+        by positioning the generator at the offset those calls have in the full stream (torch.randn per temperature,
+        utils/stats.py:74, :273), prepares them, and the ranks all-gather the prepared operands.  The generator ends
+        where a single-GPU run would leave it."""
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group)
+        nb, b = temps.shape[0], x0f.shape[0]
+        k = (nb + self.world - 1) // self.world
+        lo, hi = min(nb, rank * k), min(nb, (rank + 1) * k)
+        gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        step = self._randn_offset_step(tuple(x0.shape), dev)
+        base = gen.get_offset()
+        noise = torch.zeros(k, b, self.ds.d, dtype=torch.float32, device=dev)
+        for j in range(lo, hi):
+            gen.set_offset(base + j * step)
+            torch.randn(*x0.shape, device=dev, out=noise[j - lo].view(x0.shape))
+        gen.set_offset(base + nb * step)
+        my_t = torch.ones(k, dtype=torch.float32, device=dev)
+        my_t[:hi - lo] = temps[lo:hi]
+        precision = self.precision()
+        local = self._prepare(x0f, k * b, noise.view(k * b, -1), my_t.repeat_interleave(b).sqrt(), None, precision, False)
+        del noise
+        out = {}
+        for key, t in local.items():
+            if t is None:
+                out[key] = None
+                continue
+            full = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(full, t.contiguous(), group=self.group)
+            out[key] = full[:nb * b]
+        return out
 
     # -- posterior mean ---------------------------------------------------------------------------
     def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None,

@@ -262,3 +262,17 @@ def test_denoiser_backward_lattice_and_sampler_chain(cuda_device):
     loss64.backward()
     assert abs(loss.item() - loss64.item()) <= 1e-4 * abs(loss64.item()) + 1e-6
     assert (lt.grad.double().cpu() - lt64.grad).abs().max().item() <= 2e-3 * lt64.grad.abs().max().item() + 1e-7
+
+
+def test_sharded_sliced_noise_two_gpus(cuda_device):
+    """Row-sharded dataset + rank-sliced noise draw against the unsharded engine (needs >= 2 GPUs; tools/check_sharded_gpu.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_sharded_gpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
