@@ -103,6 +103,25 @@ int pdm_prepare_rows(const float* src, int64_t src_rows, int64_t ld_src,
                      uint16_t* hi, uint16_t* lo, int64_t ldh, float* inv_scale,
                      pdm_stream_t stream);
 
+/* Noised queries regenerated in-kernel from torch's CUDA Philox stream, straight into operands: for draw t
+ * (= one `torch.randn(b, d)` of utils/stats.py:74, :273 at Philox offset `offset + t*offset_step`) and element (r, k)
+ *     v = fl(fl(eps * sigma[t]) + x0[r, k])            row t*b + r of the outputs
+ * with eps bit-identical to what torch.randn would have written (same thread <-> element map, same cuRAND
+ * device functions; `draw_threads` = 256 * grid of that torch launch).  Outputs: x_out fp32 (optional) and/or the
+ * fp16 hi/lo split with inv_scale, scaled by the per-row power of two given by the bound max|x0_r| + 6.8 sigma[t]
+ * (ldh == d, d % 8 == 0).  Row norms of the split operands: pdm_split_row_norms.  Replaces the torch.randn launch +
+ * pdm_prepare_rows pair (12 B/element less HBM traffic); the host checks bit-identity against torch.randn once. */
+int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t offset_step, int64_t draw_threads,
+                           const float* x0, int64_t b, int64_t d, int64_t ld_x0,
+                           const float* sigma, int64_t n_draws, const float* x0_absmax,
+                           float* x_out, int64_t ldx,
+                           uint16_t* hi, uint16_t* lo, int64_t ldh, float* inv_scale, pdm_stream_t stream);
+/* norms[r] = ||(hi_r + lo_r) * inv_scale[r]||^2 (fp64 accumulate): the norm of exactly the vector the MMAs see. */
+int pdm_split_row_norms(const uint16_t* hi, const uint16_t* lo, int64_t ldh, const float* inv_scale,
+                        int64_t rows, int64_t d, float* norms, pdm_stream_t stream);
+/* out[r] = max_k |x[r,k]|. */
+int pdm_row_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream);
+
 /* max_k |x[r,k]| over the whole matrix -> out[0] (used once per dataset to pick its global 2^k). */
 int pdm_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream);
 

@@ -1,0 +1,150 @@
+// Noised queries straight into tensor-core operands: the standard-normal draws of torch.randn are regenerated
+// in-kernel, element for element, instead of being written to HBM by torch and read back by pdm_prepare_rows.
+//
+// The reference noises its queries with `torch.randn(...) * t.sqrt() + x0` once per temperature (utils/stats.py:74,
+// :273).  On a CUDA device torch.randn(numel) runs a grid-stride kernel of G = 256 * min(SMs * (maxThreadsPerSM/256),
+// ceil(numel/256)) threads; thread idx owns the Philox4x32-10 subsequence idx of (seed, offset) and its k-th
+// curand_normal4 call fills elements idx + G*ii + 4*G*k, ii = 0..3 (ATen/native/cuda/DistributionTemplates.h:
+// calc_execution_policy + distribution_elementwise_grid_stride_kernel).  This kernel walks the same index map with the
+// same cuRAND device functions, so the values are bit-identical to torch's; the host verifies that once per device
+// against torch.randn itself and falls back to torch.randn + pdm_prepare_rows if it ever is not (pdm_b200/engine.py).
+//
+// One launch covers n_draws temperatures (blockIdx.y): v = fl(fl(eps * sigma_t) + x0[b, k]) (torch's two roundings),
+// operand split with the per-row power-of-two scale derived from the a-priori bound |v| <= max|x0_b| + 6.8 sigma_t
+// (|eps| <= sqrt(-2 ln 2^-33) = 6.76 for 32-bit Box-Muller), so no pass over the row is needed before the split.
+#include "pdm_common.cuh"
+
+#include <curand_kernel.h>
+
+namespace pdm {
+
+struct NoisedParams {
+    unsigned long long seed, offset, offset_step;
+    long long draw_threads;             // G: threads of the torch.randn launch being reproduced
+    const float* x0; long long b, d, ld_x0;
+    const float* sigma;                 // [n_draws]
+    const float* x0_absmax;             // [b]
+    float* x_out; long long ldx;        // optional fp32 rows
+    __half* hi; __half* lo; long long ldh; float* inv_scale;   // optional operand split
+};
+
+__device__ __forceinline__ float bound_scale(float bound) {
+    int e = 0;
+    if (!(bound > 0.f) || !(bound < INFINITY)) return 1.f;
+    frexpf(bound, &e);                                  // bound = f * 2^e, f in [0.5, 1)
+    e = max(-100, min(100, 12 - e));
+    return ldexpf(1.f, e);                              // bound * scale in [2^11, 2^12)
+}
+
+__global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // < draw_threads by construction
+    const long long t = blockIdx.y;
+    const long long numel = p.b * p.d;
+    const long long G = p.draw_threads;
+    const float sig = p.sigma[t];
+    curandStatePhilox4_32_10_t st;
+    curand_init(p.seed, (unsigned long long)idx, p.offset + (unsigned long long)t * p.offset_step, &st);
+    for (long long base = idx; base < numel; base += 4 * G) {       // same trip structure as torch's rounded_size loop
+        const float4 r = curand_normal4(&st);
+        const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const long long li = base + G * ii;
+            if (li >= numel) continue;
+            const long long b = li / p.d, k = li - b * p.d;
+            const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(p.x0 + b * p.ld_x0 + k));
+            const long long row = t * p.b + b;
+            if (p.x_out) p.x_out[row * p.ldx + k] = v;
+            if (p.hi) {
+                const float scale = bound_scale(__fadd_rn(__ldg(p.x0_absmax + b), 6.8f * sig));
+                const float vs = v * scale;
+                const __half h = __float2half_rn(vs);
+                p.hi[row * p.ldh + k] = h;
+                p.lo[row * p.ldh + k] = __float2half_rn(vs - __half2float(h));
+                if (k == 0) p.inv_scale[row] = 1.f / scale;
+            }
+        }
+    }
+}
+
+// ||(hi + lo) * inv_scale||^2 per row, fp64 accumulation: the norm of exactly the vector the tensor cores see.
+__global__ void __launch_bounds__(256) split_row_norms_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                              long long ldh, const float* __restrict__ inv_scale,
+                                                              long long rows, long long d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const __half2* h2 = reinterpret_cast<const __half2*>(hi + row * ldh);
+    const __half2* l2 = reinterpret_cast<const __half2*>(lo + row * ldh);
+    double acc = 0.0;
+    for (long long i = lane; i < (d >> 1); i += 32) {              // d is even on this path (ldh % 8 == 0 == d % 8)
+        const float2 a = __half22float2(h2[i]), c = __half22float2(l2[i]);
+        const double x = (double)a.x + (double)c.x, y = (double)a.y + (double)c.y;
+        acc += x * x + y * y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const double s = (double)inv_scale[row];
+        out[row] = (float)(acc * s * s);
+    }
+}
+
+__global__ void __launch_bounds__(256) row_absmax_kernel(const float* __restrict__ x, long long rows, long long d, long long ld,
+                                                         float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float m = 0.f;
+    for (long long i = lane; i < d; i += 32) m = fmaxf(m, fabsf(__ldg(x + row * ld + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[row] = m;
+}
+
+}  // namespace pdm
+
+using namespace pdm;
+
+extern "C" int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t offset_step, int64_t draw_threads,
+                                      const float* x0, int64_t b, int64_t d, int64_t ld_x0,
+                                      const float* sigma, int64_t n_draws, const float* x0_absmax,
+                                      float* x_out, int64_t ldx,
+                                      uint16_t* hi, uint16_t* lo, int64_t ldh, float* inv_scale, pdm_stream_t stream) {
+    PDM_REQUIRE(x0 && sigma && b > 0 && d > 0 && ld_x0 >= d && n_draws >= 0, "pdm_noised_rows_philox: bad arguments");
+    PDM_REQUIRE(draw_threads > 0 && draw_threads % 256 == 0 && draw_threads / 256 <= 0x7fffffffll,
+                "pdm_noised_rows_philox: draw_threads must be a positive multiple of 256");
+    PDM_REQUIRE(b * d < (1ll << 31), "pdm_noised_rows_philox: one draw must stay below 2^31 elements (torch splits larger ones)");
+    PDM_REQUIRE(x_out || hi, "pdm_noised_rows_philox: no output requested");
+    PDM_REQUIRE(!x_out || ldx >= d, "pdm_noised_rows_philox: ldx < d");
+    PDM_REQUIRE((hi == nullptr) == (lo == nullptr), "pdm_noised_rows_philox: hi and lo go together");
+    PDM_REQUIRE(!hi || (x0_absmax && inv_scale && ldh == d && d % 8 == 0),
+                "pdm_noised_rows_philox: the split needs x0_absmax, inv_scale and ldh == d with d %% 8 == 0");
+    PDM_REQUIRE(n_draws <= 65535, "pdm_noised_rows_philox: at most 65535 draws per launch");
+    if (n_draws == 0) return PDM_OK;
+    NoisedParams p{seed, offset, offset_step, draw_threads, x0, b, d, ld_x0, sigma, x0_absmax, x_out, ldx,
+                   reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ldh, inv_scale};
+    dim3 grid((unsigned)(draw_threads / 256), (unsigned)n_draws);
+    noised_rows_philox_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_split_row_norms(const uint16_t* hi, const uint16_t* lo, int64_t ldh, const float* inv_scale,
+                                   int64_t rows, int64_t d, float* norms, pdm_stream_t stream) {
+    PDM_REQUIRE(hi && lo && inv_scale && norms && rows >= 0 && d > 0 && ldh >= d && d % 2 == 0 && ldh % 2 == 0,
+                "pdm_split_row_norms: bad arguments");
+    if (rows == 0) return PDM_OK;
+    split_row_norms_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), ldh, inv_scale, rows, d, norms);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_row_absmax_f32(const float* x, int64_t rows, int64_t d, int64_t ld, float* out, pdm_stream_t stream) {
+    PDM_REQUIRE(x && out && rows >= 0 && d > 0 && ld >= d, "pdm_row_absmax_f32: bad arguments");
+    if (rows == 0) return PDM_OK;
+    row_absmax_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(x, rows, d, ld, out);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}

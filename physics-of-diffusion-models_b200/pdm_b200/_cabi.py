@@ -47,6 +47,10 @@ SIGNATURES = {
     "pdm_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pdm_row_norms_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "pdm_prepare_rows": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _I64, _I64, _F, _P, _I64, _P, _P, _P, _I64, _P, _P]),
+    "pdm_noised_rows_philox": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, _I64, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _I64,
+                                         _P, _P, _I64, _P, _P]),
+    "pdm_split_row_norms": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P, _P]),
+    "pdm_row_absmax_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "pdm_absmax_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "pdm_lattice_residual_f32": (C.c_int, [_P, _I64, _I64, _I64, _F, _P, _P]),
     "pdm_transpose_split_f16": (C.c_int, [_P, _I64, _I64, _I64, _F, _P, _P, _I64, _P]),

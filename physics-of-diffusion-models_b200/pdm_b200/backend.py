@@ -109,6 +109,54 @@ class CudaBackend:
         self.launches += 1
         return out
 
+    # ---- noised rows from torch's Philox stream ---------------------------------------------------
+    def randn_launch_threads(self, numel: int) -> int:
+        """Threads of the kernel torch.randn(numel) launches on this device (calc_execution_policy of
+        ATen/native/cuda/DistributionTemplates.h): 256 * min(SMs * (maxThreadsPerSM // 256), ceil(numel / 256))."""
+        props = torch.cuda.get_device_properties(self.device)
+        blocks = min(props.multi_processor_count * (props.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+        return 256 * max(1, blocks)
+
+    def row_absmax(self, x: Tensor) -> Tensor:
+        x = self._f32(x)
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_row_absmax_f32(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), out.data_ptr(), self._stream()),
+              "pdm_row_absmax_f32")
+        self.launches += 1
+        return out
+
+    def noised_rows_philox(self, seed: int, offset: int, offset_step: int, x0: Tensor, sigma: Tensor, *,
+                           x0_absmax: Optional[Tensor] = None, want_x: bool = False, want_split: bool = True) -> dict:
+        """Rows (t, r) = fl(fl(randn * sigma[t]) + x0[r]) for the draws t at Philox offsets offset + t*offset_step;
+        same keys as prepare_rows."""
+        x0, sigma = self._f32(x0), self._f32(sigma)
+        b, d = x0.shape
+        n = sigma.shape[0]
+        rows = n * b
+        out = {"x": None, "norms": None, "hi": None, "lo": None, "inv_scale": None}
+        if want_x:
+            out["x"] = torch.empty(rows, d, dtype=torch.float32, device=self.device)
+        if want_split:
+            if x0_absmax is None:
+                x0_absmax = self.row_absmax(x0)
+            out["hi"] = torch.empty(rows, d, dtype=torch.float16, device=self.device)
+            out["lo"] = torch.empty(rows, d, dtype=torch.float16, device=self.device)
+            out["inv_scale"] = torch.empty(rows, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_noised_rows_philox(
+            seed, offset, offset_step, self.randn_launch_threads(b * d), x0.data_ptr(), b, d, _ld(x0), sigma.data_ptr(), n,
+            _ptr(x0_absmax), _ptr(out["x"]), d, _ptr(out["hi"]), _ptr(out["lo"]), d, _ptr(out["inv_scale"]),
+            self._stream()), "pdm_noised_rows_philox")
+        self.launches += 1
+        out["norms"] = torch.empty(rows, dtype=torch.float32, device=self.device)
+        if want_split:
+            check(self.lib.pdm_split_row_norms(out["hi"].data_ptr(), out["lo"].data_ptr(), d, out["inv_scale"].data_ptr(),
+                                               rows, d, out["norms"].data_ptr(), self._stream()), "pdm_split_row_norms")
+        else:
+            check(self.lib.pdm_row_norms_f32(out["x"].data_ptr(), rows, d, d, out["norms"].data_ptr(), self._stream()),
+                  "pdm_row_norms_f32")
+        self.launches += 1
+        return out
+
     # ---- row preparation -----------------------------------------------------------------------
     def prepare_rows(self, src: Tensor, rows: int, *, noise: Optional[Tensor] = None, sigma: Optional[Tensor] = None,
                      post: Optional[Tensor] = None, fixed_scale: float = 0.0, want_x: bool = False,

@@ -170,6 +170,8 @@ class EngineConfig:
     max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
     sync_noise: bool = True            # sharded runs: make every rank draw rank 0's noise stream (set False when
                                        # every rank seeds its generator identically)
+    fused_noise: bool = True           # regenerate torch.randn's Philox stream inside the operand kernel (bit-identical,
+                                       # verified once per device) instead of torch.randn + pdm_prepare_rows
     slice_noise: bool = True           # sharded CUDA runs: each rank draws + prepares 1/world of the query rows and
                                        # the prepared operands are all-gathered (False: every rank draws everything)
 
@@ -303,6 +305,8 @@ class PosteriorEngine:
             noise_fn = lambda i: PosteriorEngine.noise_hook(i, tuple(x0.shape), dev)     # noqa: E731
         draw = noise_fn
         sliced = self.world > 1 and draw is None and dev.type == "cuda" and self.cfg.slice_noise
+        fused = draw is None and self._fused_noise_usable(x0, dev)
+        x0_absmax = self.backend.row_absmax(x0f) if fused and self.precision() != "exact" else None
         if sliced:
             t_per_block = max(self.world, t_per_block // self.world * self.world)
             self._sync_generator(dev)
@@ -316,8 +320,19 @@ class PosteriorEngine:
             if sliced:
                 t_rows = temp[t0:t1].repeat_interleave(b)
                 with ph("noise+prepare+gather"):
-                    prep = self._sliced_prepare(x0, x0f, temp[t0:t1], dev)
+                    prep = self._sliced_prepare(x0, x0f, temp[t0:t1], dev, fused, x0_absmax)
                 o, i = self.stats_block(x0f, nb * b, t_rows, aux=aux, prep=prep)
+                outs.append(o)
+                idxs.append(i)
+                continue
+            if fused:
+                with ph("noise+prepare"):
+                    gen = self._cuda_generator(dev)
+                    step_off = self._randn_offset_step(tuple(x0.shape), dev)
+                    base = gen.get_offset()
+                    prep = self._fused_prepare(gen.initial_seed(), base, step_off, x0f, temp[t0:t1], x0_absmax)
+                    gen.set_offset(base + nb * step_off)
+                o, i = self.stats_block(x0f, nb * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep)
                 outs.append(o)
                 idxs.append(i)
                 continue
@@ -370,7 +385,45 @@ class PosteriorEngine:
         dist.broadcast(state, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
         torch.cuda.set_rng_state(state.cpu(), dev)
 
-    def _sliced_prepare(self, x0: Tensor, x0f: Tensor, temps: Tensor, dev: torch.device) -> dict:
+    @staticmethod
+    def _cuda_generator(dev: torch.device):
+        return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+
+    _FUSED_NOISE_OK: dict = {}
+
+    def _fused_noise_usable(self, x0: Tensor, dev: torch.device) -> bool:
+        """The in-kernel Philox path reproduces torch.randn bit for bit on this device (checked once, against
+        torch.randn itself, for two shapes, a non-zero offset and consecutive draws) and the shape is one it covers."""
+        if not self.cfg.fused_noise or dev.type != "cuda" or not hasattr(self.backend, "noised_rows_philox"):
+            return False
+        if x0.numel() >= 2 ** 31 or (self.precision() != "exact" and self.ds.d % 8 != 0):
+            return False
+        key = str(dev)
+        ok = PosteriorEngine._FUSED_NOISE_OK.get(key)
+        if ok is None:
+            ok = True
+            try:
+                for shape in ((48, 3072), (5, 331)):
+                    g = torch.Generator(device=dev)
+                    g.manual_seed(20240229)
+                    g.set_offset(24)
+                    step = self._randn_offset_step(shape, dev)
+                    want = torch.stack([torch.randn(*shape, device=dev, generator=g) for _ in range(3)])
+                    got = self.backend.noised_rows_philox(20240229, 24, step, torch.zeros(shape, device=dev),
+                                                          torch.ones(3, device=dev), want_x=True, want_split=False)["x"]
+                    ok = ok and torch.equal(got.view(3, *shape), want) and g.get_offset() == 24 + 3 * step
+            except Exception:       # noqa: BLE001  (any surprise in torch's generator API: use torch.randn itself)
+                ok = False
+            PosteriorEngine._FUSED_NOISE_OK[key] = ok
+        return ok
+
+    def _fused_prepare(self, seed: int, offset: int, step: int, x0f: Tensor, temps: Tensor, x0_absmax) -> dict:
+        tensor = self.precision() != "exact"
+        return self.backend.noised_rows_philox(seed, offset, step, x0f, temps.sqrt().contiguous(), x0_absmax=x0_absmax,
+                                               want_x=not tensor, want_split=tensor)
+
+    def _sliced_prepare(self, x0: Tensor, x0f: Tensor, temps: Tensor, dev: torch.device, fused: bool = False,
+                        x0_absmax=None) -> dict:
         """Operands of the rows (t, b), t in ``temps``: this rank draws the noise of its ceil(nb/world) temperatures
         by positioning the generator at the offset those calls have in the full stream (torch.randn per temperature,
         utils/stats.py:74, :273), prepares them, and the ranks all-gather the prepared operands.  The generator ends
@@ -380,19 +433,22 @@ class PosteriorEngine:
         nb, b = temps.shape[0], x0f.shape[0]
         k = (nb + self.world - 1) // self.world
         lo, hi = min(nb, rank * k), min(nb, (rank + 1) * k)
-        gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        gen = self._cuda_generator(dev)
         step = self._randn_offset_step(tuple(x0.shape), dev)
         base = gen.get_offset()
-        noise = torch.zeros(k, b, self.ds.d, dtype=torch.float32, device=dev)
-        for j in range(lo, hi):
-            gen.set_offset(base + j * step)
-            torch.randn(*x0.shape, device=dev, out=noise[j - lo].view(x0.shape))
-        gen.set_offset(base + nb * step)
         my_t = torch.ones(k, dtype=torch.float32, device=dev)
         my_t[:hi - lo] = temps[lo:hi]
-        precision = self.precision()
-        local = self._prepare(x0f, k * b, noise.view(k * b, -1), my_t.repeat_interleave(b).sqrt(), None, precision, False)
-        del noise
+        if fused:
+            local = self._fused_prepare(gen.initial_seed(), base + lo * step, step, x0f, my_t, x0_absmax)
+        else:
+            noise = torch.zeros(k, b, self.ds.d, dtype=torch.float32, device=dev)
+            for j in range(lo, hi):
+                gen.set_offset(base + j * step)
+                torch.randn(*x0.shape, device=dev, out=noise[j - lo].view(x0.shape))
+            local = self._prepare(x0f, k * b, noise.view(k * b, -1), my_t.repeat_interleave(b).sqrt(), None,
+                                  self.precision(), False)
+            del noise
+        gen.set_offset(base + nb * step)
         out = {}
         for key, t in local.items():
             if t is None:

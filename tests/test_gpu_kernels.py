@@ -339,3 +339,64 @@ def test_engine_picks_two_products_for_images(backend):
     cont = EmpiricalDataset(torch.rand(300, 256, generator=g) * 2 - 1, backend=backend)
     with pytest.raises(PdmError):
         PosteriorEngine(cont, EngineConfig(precision="f16x2")).precision()
+
+
+# ------------------------------------------------------------------------------------------------
+# noise regenerated in-kernel from torch's Philox stream
+# ------------------------------------------------------------------------------------------------
+def test_philox_rows_bit_identical_to_torch_randn(backend):
+    """pdm_noised_rows_philox writes exactly torch.randn(...) * sqrt(T) + x0 (utils/stats.py:74, :273), draw after draw."""
+    from pdm_b200 import PosteriorEngine
+    dev = backend.device
+    gen = torch.cuda.default_generators[dev.index or 0]
+    for shape in ((1024, 3072), (256, 3, 32, 32), (7, 333), (2, 8)):
+        torch.manual_seed(77)
+        torch.rand(5, device=dev)                                # move the stream off offset 0
+        x0 = torch.rand(*shape, device=dev) * 2 - 1
+        temps = torch.logspace(-3, 3, 5, device=dev)
+        seed, base = gen.initial_seed(), gen.get_offset()
+        want = torch.stack([torch.randn(*shape, device=dev) * t.sqrt() + x0 for t in temps])
+        after = gen.get_offset()
+        step = PosteriorEngine._randn_offset_step(tuple(shape), dev)
+        assert after == base + len(temps) * step
+        b = shape[0]
+        x0f = x0.reshape(b, -1).contiguous()
+        got = backend.noised_rows_philox(seed, base, step, x0f, temps.sqrt().contiguous(), want_x=True,
+                                         want_split=x0f.shape[1] % 8 == 0)
+        assert torch.equal(got["x"].view(len(temps), *shape), want), f"shape {shape}"
+        if got["hi"] is not None:
+            v = want.reshape(len(temps) * b, -1).double()
+            rec = (got["hi"].double() + got["lo"].double()) * got["inv_scale"].double()[:, None]
+            amax = v.abs().max(1).values[:, None]
+            assert ((rec - v).abs() <= amax * 2.0 ** -20).all()              # bound-scaled split: >= 21 bits of the row max
+            assert (got["hi"].float().abs().max() <= 4096)
+            nref = (rec ** 2).sum(1)
+            assert ((got["norms"].double() - nref).abs() <= 1.2e-7 * nref).all()
+
+
+def test_fused_noise_engine_matches_unfused(backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = syn.gen(31)
+    n, b, d = 3000, 96, 512
+    data = torch.rand(n, d, generator=g) * 2 - 1
+    x0 = data[:b].clone()
+    temps = torch.logspace(-3, 3, 23)
+    ds = EmpiricalDataset(data, backend=backend)
+    dev = backend.device
+    gen = torch.cuda.default_generators[dev.index or 0]
+    res = {}
+    for fused in (True, False):
+        cfg = EngineConfig(max_query_bytes=8 * b * d * 12)          # a few temperatures per block
+        cfg.fused_noise = fused
+        eng = PosteriorEngine(ds, cfg)
+        torch.manual_seed(5)
+        res[fused] = (eng.noised_stats(x0, temps), gen.get_offset())
+    assert PosteriorEngine._FUSED_NOISE_OK.get(str(dev)) is True, "in-kernel Philox path failed its bit-identity self-check"
+    (sf, of), (su, ou) = res[True], res[False]
+    assert of == ou                                               # the generator ends where torch.randn would leave it
+    assert torch.equal(sf["argmin"], su["argmin"])
+    xn = (x0.double() ** 2).sum(1)[None, :] + d * temps.double()[:, None]
+    floor = 8 * 2.0 ** -24 * (xn + (data.double() ** 2).sum(1).max()) / temps.double()[:, None]
+    for k in ("log_l", "mean_e", "entropy"):
+        err = (sf[k].double() - su[k].double()).abs().cpu()
+        assert (err <= torch.maximum(1e-4 * su[k].double().abs().cpu() + 2e-5, floor)).all(), k
