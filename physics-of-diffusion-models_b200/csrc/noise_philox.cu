@@ -36,33 +36,45 @@ __device__ __forceinline__ float bound_scale(float bound) {
     return ldexpf(1.f, e);                              // bound * scale in [2^11, 2^12)
 }
 
+// inv_scale[t*b + r] = 2^-k of row (t, r), from the bound max|x0_r| + 6.8 sigma_t
+__global__ void __launch_bounds__(256) noised_row_scales_kernel(const float* __restrict__ x0_absmax, const float* __restrict__ sigma,
+                                                                long long b, long long rows, float* __restrict__ inv_scale) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const long long t = row / b, r = row - t * b;
+    inv_scale[row] = 1.f / bound_scale(__fadd_rn(x0_absmax[r], 6.8f * sigma[t]));
+}
+
+// 32-bit index arithmetic throughout (one draw stays below 2^31 elements); (row, column) of the four elements a
+// curand_normal4 call fills are advanced incrementally instead of divided out.
 __global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // < draw_threads by construction
-    const long long t = blockIdx.y;
-    const long long numel = p.b * p.d;
-    const long long G = p.draw_threads;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;                   // < draw_threads by construction
+    const unsigned t = blockIdx.y;
+    const unsigned numel = (unsigned)(p.b * p.d), G = (unsigned)p.draw_threads, d = (unsigned)p.d;
+    const unsigned gq = G / d, gr = G - gq * d;                                   // G = gq * d + gr
     const float sig = p.sigma[t];
+    const long long row0 = (long long)t * p.b;
     curandStatePhilox4_32_10_t st;
     curand_init(p.seed, (unsigned long long)idx, p.offset + (unsigned long long)t * p.offset_step, &st);
-    for (long long base = idx; base < numel; base += 4 * G) {       // same trip structure as torch's rounded_size loop
+    unsigned li = idx, b = idx / d, k = idx - (idx / d) * d;
+    while (li < numel) {                                // same trip structure as torch's rounded_size loop
         const float4 r = curand_normal4(&st);
         const float rv[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
-            const long long li = base + G * ii;
-            if (li >= numel) continue;
-            const long long b = li / p.d, k = li - b * p.d;
-            const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(p.x0 + b * p.ld_x0 + k));
-            const long long row = t * p.b + b;
-            if (p.x_out) p.x_out[row * p.ldx + k] = v;
-            if (p.hi) {
-                const float scale = bound_scale(__fadd_rn(__ldg(p.x0_absmax + b), 6.8f * sig));
-                const float vs = v * scale;
-                const __half h = __float2half_rn(vs);
-                p.hi[row * p.ldh + k] = h;
-                p.lo[row * p.ldh + k] = __float2half_rn(vs - __half2float(h));
-                if (k == 0) p.inv_scale[row] = 1.f / scale;
+            if (li < numel) {
+                const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(p.x0 + (long long)b * p.ld_x0 + k));
+                const long long row = row0 + b;
+                if (p.x_out) p.x_out[row * p.ldx + k] = v;
+                if (p.hi) {
+                    const float vs = v * __frcp_rn(__ldg(p.inv_scale + row));     // exact: inv_scale is a power of two
+                    const __half h = __float2half_rn(vs);
+                    p.hi[row * p.ldh + k] = h;
+                    p.lo[row * p.ldh + k] = __float2half_rn(vs - __half2float(h));
+                }
             }
+            li += G; b += gq; k += gr;                  // next element of this call: G further on
+            if (k >= d) { k -= d; ++b; }
         }
     }
 }
@@ -124,6 +136,11 @@ extern "C" int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t o
     if (n_draws == 0) return PDM_OK;
     NoisedParams p{seed, offset, offset_step, draw_threads, x0, b, d, ld_x0, sigma, x0_absmax, x_out, ldx,
                    reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ldh, inv_scale};
+    if (hi) {
+        const int64_t rows = n_draws * b;
+        noised_row_scales_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(x0_absmax, sigma, b, rows, inv_scale);
+        PDM_CUDA_CHECK(cudaGetLastError());
+    }
     dim3 grid((unsigned)(draw_threads / 256), (unsigned)n_draws);
     noised_rows_philox_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
     PDM_CUDA_CHECK(cudaGetLastError());

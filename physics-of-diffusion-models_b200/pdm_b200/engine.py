@@ -387,6 +387,7 @@ class PosteriorEngine:
 
     @staticmethod
     def _cuda_generator(dev: torch.device):
+        torch.cuda.init()                       # torch.cuda.default_generators is filled by the lazy initialisation
         return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
 
     _FUSED_NOISE_OK: dict = {}

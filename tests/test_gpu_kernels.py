@@ -348,7 +348,7 @@ def test_philox_rows_bit_identical_to_torch_randn(backend):
     """pdm_noised_rows_philox writes exactly torch.randn(...) * sqrt(T) + x0 (utils/stats.py:74, :273), draw after draw."""
     from pdm_b200 import PosteriorEngine
     dev = backend.device
-    gen = torch.cuda.default_generators[dev.index or 0]
+    gen = PosteriorEngine._cuda_generator(dev)
     for shape in ((1024, 3072), (256, 3, 32, 32), (7, 333), (2, 8)):
         torch.manual_seed(77)
         torch.rand(5, device=dev)                                # move the stream off offset 0
@@ -383,7 +383,8 @@ def test_fused_noise_engine_matches_unfused(backend):
     temps = torch.logspace(-3, 3, 23)
     ds = EmpiricalDataset(data, backend=backend)
     dev = backend.device
-    gen = torch.cuda.default_generators[dev.index or 0]
+    gen = PosteriorEngine._cuda_generator(dev)
+    gen = PosteriorEngine._cuda_generator(dev)
     res = {}
     for fused in (True, False):
         cfg = EngineConfig(max_query_bytes=8 * b * d * 12)          # a few temperatures per block

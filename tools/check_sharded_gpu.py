@@ -33,7 +33,7 @@ def main():
     amax = float(data.abs().max().item())
     lat = detect_lattice_scale(be, data, amax)
     full = PosteriorEngine(EmpiricalDataset(data, backend=be), EngineConfig(max_query_bytes=96 << 20))
-    gen = torch.cuda.default_generators[local]
+    gen = PosteriorEngine._cuda_generator(dev)
     ok = True
 
     def run(engine, seed):
