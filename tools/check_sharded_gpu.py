@@ -42,7 +42,8 @@ def main():
         return st, gen.get_offset()
 
     ref, off_ref = run(full, 123)
-    for slice_noise, sync, seed in ((True, False, 123), (False, False, 123), (True, True, 123 if rank == 0 else 999 + rank)):
+    other = 123 if rank == 0 else 999 + rank                  # with sync_noise every rank must end up on rank 0's stream
+    for slice_noise, sync, seed in ((True, False, 123), (False, False, 123), (True, True, other), (False, True, other)):
         cfg = EngineConfig(max_query_bytes=96 << 20)          # several blocks of temperatures
         cfg.slice_noise, cfg.sync_noise = slice_noise, sync
         shard = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=n, global_absmax=amax, lattice_scale=lat)
