@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 constexpr uint64_t kWatchdogNs = 4000000000ull;   // 4 s: far beyond any legitimate wait in these kernels
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
-    uint32_t done = 0;
+    uint32_t done = 0, fails = 0;
     uint64_t t0 = 0;
     while (true) {
         asm volatile(
@@ -62,11 +62,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
         if (done) break;
-        const uint64_t now = global_timer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > kWatchdogNs) {
-            printf("pdm_b200: mbarrier watchdog (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-            __trap();
+        if ((++fails & 63u) == 0) {                       // the watchdog clock is read once per 64 timed-out waits
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWatchdogNs) {
+                printf("pdm_b200: mbarrier watchdog (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+                __trap();
+            }
         }
     }
 }

@@ -269,7 +269,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const int row_in_cta = quarter * 32 + lane;
             const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
             uint32_t chunk_iter = 0;
-            unsigned long long st_tfull = 0; (void)st_tfull;
+            unsigned long long st_tfull = 0, st_stats = 0; (void)st_tfull; (void)st_stats;
             // 128-bit stores of the dense outputs need 16-byte aligned rows
             const bool out_vec = (EPI == EPI_STATS)
                 ? (p.energy_out && (p.lde % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.energy_out) & 15) == 0))
@@ -335,6 +335,9 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         }
                     }
                     // ---- the tile's Gram entries are complete in registers ----
+#ifdef PDM_STALL_STATS
+                    const uint64_t t_stats0 = global_timer_ns();
+#endif
                     const int64_t nbase = (int64_t)nt * kBlockN + half * CPT;
                     // |y|^2 of the chunk after the current one is loaded while the current one is processed
                     // (one chunk ahead only: the barrier below keeps ptxas from hoisting all of them)
@@ -432,13 +435,16 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                             }
                         }
                     }
+#ifdef PDM_STALL_STATS
+                    st_stats += global_timer_ns() - t_stats0;
+#endif
                 }
                 // one partial record per (row, split, column half)
                 if (EPI == EPI_STATS && p.partials && row_ok)
                     packed_store(st, p.partials + (grow * (2 * p.n_splits) + 2 * sp + half) * PDM_PART_STRIDE);
             }
 #ifdef PDM_STALL_STATS
-            if (warp == kEpiWarp0 && lane == 0) g_stall[blockIdx.x][3] = st_tfull;
+            if (warp == kEpiWarp0 && lane == 0) { g_stall[blockIdx.x][3] = st_tfull; g_stall[blockIdx.x][5] = st_stats; }
 #endif
         }
     }

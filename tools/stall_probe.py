@@ -51,7 +51,7 @@ def main():
             t = torch.tensor(list(buf), dtype=torch.float64).view(160, 8)[:148] / 1e6
             lead = t[0::2]          # leader CTAs carry the MMA counters
             print(f"  {e0.elapsed_time(e1):8.3f} | {t[:, 0].mean():7.3f} {lead[:, 1].mean():7.3f} {lead[:, 2].mean():7.3f} "
-                  f"{t[:, 3].mean():7.3f} | {t[:, 4].max():7.3f}   (max over CTAs: {t[:, 0].max():.2f} {lead[:, 1].max():.2f} "
+                  f"{t[:, 3].mean():7.3f} | {t[:, 4].max():7.3f} | stats phase {t[:, 5].mean():6.3f}   (max over CTAs: {t[:, 0].max():.2f} {lead[:, 1].max():.2f} "
                   f"{lead[:, 2].max():.2f} {t[:, 3].max():.2f})", flush=True)
 
 
