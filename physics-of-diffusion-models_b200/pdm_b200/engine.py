@@ -37,6 +37,11 @@ def _env_int(name: str, default: int = 0) -> int:
     return int(v) if v else default
 
 
+def _flat2d(t: Tensor) -> Tensor:
+    """(rows, everything else) -- also for tensors without rows, where reshape(0, -1) is ambiguous."""
+    return t.reshape(t.shape[0], math.prod(t.shape[1:]))
+
+
 def pow2_scale_for(absmax: float) -> float:
     """2^k with absmax * 2^k in [2^11, 2^12): the fp16 hi part keeps 11 bits, hi+lo 22 bits."""
     if not (absmax > 0.0) or math.isinf(absmax) or math.isnan(absmax):
@@ -88,7 +93,7 @@ class EmpiricalDataset:
         set (every rank must use the same scale; lattice_scale 0.0 = not a lattice, None = detect on ``data``)."""
         self.backend = backend if backend is not None else default_backend()
         dev = self.backend.device
-        flat = data.reshape(data.shape[0], -1)
+        flat = _flat2d(data)
         self.y = flat.to(device=dev, dtype=torch.float32).contiguous()
         self.item_shape = tuple(data.shape[1:])
         self.n, self.d = self.y.shape
@@ -273,12 +278,20 @@ class PosteriorEngine:
         with ph("merge"):
             return self._merge(parts, inv_temp)
 
+    @staticmethod
+    def _empty_stats(shape: tuple, dev: torch.device) -> dict:
+        res = {k: torch.empty(shape, dtype=torch.float32, device=dev) for k in STAT_KEYS}
+        res["argmin"] = torch.empty(shape, dtype=torch.int64, device=dev)
+        return res
+
     def stats(self, x: Tensor, temp_rows: Tensor, aux: Optional[Tensor] = None) -> dict:
         """Per-row Boltzmann statistics of explicit queries x (M, ...) at per-row temperatures."""
         dev = self.backend.device
-        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
         temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(xf.shape[0]).contiguous()
         outs, idxs = [], []
+        if xf.shape[0] == 0:
+            return self._empty_stats((0,), dev)
         step = self.rows_per_block()
         for r0 in range(0, xf.shape[0], step):
             r1 = min(xf.shape[0], r0 + step)
@@ -297,9 +310,11 @@ class PosteriorEngine:
         order -- the reference's RNG stream (utils/stats.py:74, :273).  Returns tensors of shape (n_T, B)."""
         dev = self.backend.device
         b = x0.shape[0]
-        x0f = x0.reshape(b, -1).to(device=dev, dtype=torch.float32).contiguous()
+        x0f = _flat2d(x0).to(device=dev, dtype=torch.float32).contiguous()
         temp = temp.to(device=dev, dtype=torch.float32).reshape(-1)
         n_t = temp.shape[0]
+        if b == 0 or n_t == 0:
+            return self._empty_stats((n_t, b), dev)
         t_per_block = max(1, self.rows_per_block() // b)
         outs, idxs = [], []
         if noise_fn is None and PosteriorEngine.noise_hook is not None:
@@ -470,7 +485,7 @@ class PosteriorEngine:
         ``values`` (N, dv) replaces y_j in the weighted sum (posterior mean of arbitrary per-point vectors)."""
         dev = self.backend.device
         ds = self.ds
-        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
         m = xf.shape[0]
         temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
         if post is not None:
@@ -479,7 +494,7 @@ class PosteriorEngine:
         tensor = precision != "exact"
         vt = None
         if values is not None:
-            values = values.reshape(values.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+            values = _flat2d(values).to(device=dev, dtype=torch.float32).contiguous()
             if values.shape[0] != ds.n:
                 raise PdmError("values must have one row per dataset row")
             if tensor:
@@ -532,8 +547,8 @@ class PosteriorEngine:
             raise PdmError("posterior_mean_backward is not available with a sharded dataset yet")
         dev = self.backend.device
         ds = self.ds
-        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
-        g = grad_out.reshape(grad_out.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
+        g = _flat2d(grad_out).to(device=dev, dtype=torch.float32).contiguous()
         m = xf.shape[0]
         temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(m).contiguous()
         if post is not None:
@@ -575,7 +590,7 @@ class PosteriorEngine:
     def pairwise_sqdist(self, x: Tensor) -> Tensor:
         """Dense (M, N) squared distances ||x_b - y_j||^2 in the reference's op order (utils/distance.py:21)."""
         dev = self.backend.device
-        xf = x.reshape(x.shape[0], -1).to(device=dev, dtype=torch.float32).contiguous()
+        xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
         m = xf.shape[0]
         precision = self.precision()
         out = torch.empty(m, self.ds.n, dtype=torch.float32, device=dev)

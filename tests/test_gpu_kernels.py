@@ -401,3 +401,71 @@ def test_fused_noise_engine_matches_unfused(backend):
     for k in ("log_l", "mean_e", "entropy"):
         err = (sf[k].double() - su[k].double()).abs().cpu()
         assert (err <= torch.maximum(1e-4 * su[k].double().abs().cpu() + 2e-5, floor)).all(), k
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: ties, tiny / ragged shapes, empty inputs, extreme temperatures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["exact", "f16x3"])
+def test_argmin_ties_take_the_first_index(backend, precision):
+    """Duplicated training points: torch.min / argmin return the first index on ties -- across column
+    tiles, splits and record merges."""
+    g = syn.gen(41)
+    base = torch.rand(40, 320, generator=g) * 2 - 1
+    data = torch.cat([base, torch.rand(700, 320, generator=g) * 2 - 1, base, base[:7]])     # copies 740.. and 780..
+    x = base[:25] + 1e-3 * torch.randn(25, 320, generator=g)
+    t_rows = torch.full((25,), 1e-2)
+    for splits in (0, 1, 3):
+        out, argmin = run_stats(backend, x, data, t_rows, precision, n_splits=splits)
+        assert torch.equal(argmin, torch.arange(25)), f"{precision} S={splits}"
+        ref = oracle_rows(x, data, t_rows)
+        assert torch.equal(ref["f32"]["argmin"], torch.arange(25))
+        check_stats(out, argmin, ref, what=f"ties {precision} S={splits}")
+
+
+def test_tiny_and_ragged_shapes(backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = syn.gen(42)
+    for (n, d, m, prec) in ((1, 7, 3, "exact"), (5, 1, 9, "exact"), (3, 257, 2, "f16x3"), (130, 264, 1, "f16x3"),
+                            (257, 1000, 129, "f16x3")):
+        data = torch.randn(n, d, generator=g)
+        x = data[torch.randint(0, n, (m,), generator=g)] + 0.3 * torch.randn(m, d, generator=g)
+        t_rows = torch.logspace(-2, 2, m)
+        eng = PosteriorEngine(EmpiricalDataset(data, backend=backend), EngineConfig(precision=prec))
+        st = eng.stats(x, t_rows)
+        ref = oracle_rows(x, data, t_rows)
+        arbitrated_close(st["entropy"], ref["f32"]["entropy"], ref["f64"]["entropy"], atol=2e-5, floor=2 * ref["floor_e"],
+                         what=f"entropy ({n},{d},{m}) {prec}")
+        agree = ref["f32"]["argmin"] == ref["f64"]["argmin"]
+        assert torch.equal(st["argmin"].cpu()[agree], ref["f64"]["argmin"][agree])
+        got = eng.posterior_mean(x, t_rows).cpu()
+        e64 = 0.5 * orc.pairwise_sqdist(x.double(), data.double())
+        p64 = torch.softmax(-(e64 - e64.min(1, keepdim=True).values) / t_rows.double()[:, None], dim=1)
+        e32 = 0.5 * orc.pairwise_sqdist(x, data)
+        p32 = torch.softmax(-(e32 - e32.min(1, keepdim=True).values) / t_rows[:, None], dim=1)
+        arbitrated_close(got, p32 @ data, p64 @ data.double(), atol=2e-5, what=f"mean ({n},{d},{m}) {prec}")
+
+
+def test_empty_queries_and_extreme_temperatures(backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = syn.gen(43)
+    data = torch.rand(300, 512, generator=g) * 2 - 1
+    for prec in ("exact", "f16x3"):
+        eng = PosteriorEngine(EmpiricalDataset(data, backend=backend), EngineConfig(precision=prec))
+        st = eng.stats(data[:0], torch.ones(0))
+        assert st["entropy"].shape == (0,) and st["argmin"].shape == (0,)
+        assert eng.posterior_mean(data[:0], torch.ones(0)).shape == (0, 512)
+        assert eng.noised_stats(data[:0], torch.tensor([0.1, 1.0]))["entropy"].shape == (2, 0)
+        x = data[:6] + 0.05 * torch.randn(6, 512, generator=g)
+        t_rows = torch.tensor([1e-30, 1e-12, 1e-6, 1e6, 1e12, 1e30])
+        st = eng.stats(x, t_rows)
+        for k in ("log_l", "mean_e", "var_e", "entropy", "e_min"):
+            assert torch.isfinite(st[k]).all(), f"{prec} {k} not finite at extreme T: {st[k]}"
+        assert torch.equal(st["argmin"].cpu(), torch.arange(6))
+        # T -> 0: a delta on the nearest point; T -> inf: uniform weights
+        assert st["log_l"][:3].abs().max().item() < 1e-6 and st["mean_e"][:3].abs().max().item() < 1e-6
+        assert abs(st["entropy"][-1].item()) < 1e-5 and abs(st["log_l"][-1].item() - math.log(300)) < 1e-5
+        mean = eng.posterior_mean(x, t_rows).cpu()
+        assert torch.isfinite(mean).all()
+        torch.testing.assert_close(mean[:3], data[:3], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(mean[-1], data.mean(0), rtol=1e-4, atol=1e-5)
