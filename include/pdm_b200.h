@@ -233,6 +233,16 @@ int pdm_weighted_mean_exact_f32(const float* p, int64_t ldp, int64_t M, int64_t 
                                 float* out, int64_t ldo, int32_t accumulate, pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * k-NN selection on a dense distance tile (pdm_posterior_stats with energy_out, mult 2): the k smallest
+ * entries of every row, ascending, ties by lower column index; vals (rows, k), idx (rows, k) int64 (-1 / +inf
+ * when a row has fewer than k finite entries).  Replaces sklearn's NearestNeighbors.kneighbors on the CPU in
+ * utils/stats.py:50-60, 137-146 (sigma_reg^2 = d_k^2 * scale / D, self included as neighbour 0) and the
+ * min / scatter / min flow of scripts/analyze_cifar_nn.py:37-47.
+ * ------------------------------------------------------------------------------------------- */
+int pdm_topk_smallest_f32(const float* x, int64_t ldx, int64_t rows, int64_t n, int32_t k,
+                          float* vals, int64_t* idx, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Backward pass of K8 (autograd through Scheduler.true_posterior_mean_x0, which
  * scripts/optimize_schedule.py:57-91,151 differentiates with respect to the noise schedule).
  * With x0_hat = sum_j p_j y_j, upstream gradient g, s_j = y_j.g and a = sum_j p_j s_j:

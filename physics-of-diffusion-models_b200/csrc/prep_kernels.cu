@@ -402,6 +402,52 @@ __global__ void __launch_bounds__(256) denoiser_backward_weights_kernel(
     if (threadIdx.x == 0) { sums[2 * row] = af; sums[2 * row + 1] = (float)b; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k smallest entries of every row of a dense (rows, n) matrix, ascending, ties by lower column index.
+// One block per row, k selection rounds over the (L2-resident) row: round r takes the lexicographic minimum of
+// (value, column) strictly above the pair selected in round r-1.  Replaces the CPU k-NN search of
+// utils/stats.py:50-60, 138-146 on the distance tiles of pdm_posterior_stats(energy_out).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_smallest_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int k,
+                                                            float* __restrict__ vals, int64_t* __restrict__ idx) {
+    __shared__ float sv[8];
+    __shared__ long long si[8];
+    __shared__ float last_v_s;
+    __shared__ long long last_i_s;
+    const int64_t row = blockIdx.x;
+    const float* xr = x + row * ldx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float last_v = -INFINITY;
+    long long last_i = -1;
+    for (int r = 0; r < k; ++r) {
+        float bv = INFINITY;
+        long long bi = 0x7fffffffffffffffLL;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const float v = __ldg(xr + j);
+            const bool above = v > last_v || (v == last_v && j > last_i);
+            if (above && (v < bv || (v == bv && j < bi))) { bv = v; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (sv[w] < bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+            const bool found = bi != 0x7fffffffffffffffLL;
+            vals[row * k + r] = found ? bv : INFINITY;
+            idx[row * k + r] = found ? bi : -1;
+            last_v_s = bv; last_i_s = bi;
+        }
+        __syncthreads();
+        last_v = last_v_s; last_i = last_i_s;
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace pdm
@@ -525,6 +571,17 @@ extern "C" int pdm_denoiser_backward_weights(const float* energy, int64_t lde, c
     PDM_REQUIRE(M < (1ll << 31), "pdm_denoiser_backward_weights: M too large for one launch");
     denoiser_backward_weights_kernel<<<(unsigned)M, 256, 0, as_stream(stream)>>>(energy, lde, sdot, lds, N, e_min, l, inv_temp,
                                                                                 s_scale, w, ldw, sums);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_topk_smallest_f32(const float* x, int64_t ldx, int64_t rows, int64_t n, int32_t k,
+                                     float* vals, int64_t* idx, pdm_stream_t stream) {
+    PDM_REQUIRE(x && vals && idx && rows >= 0 && n > 0 && ldx >= n && k >= 1 && k <= 1024,
+                "pdm_topk_smallest_f32: bad arguments (1 <= k <= 1024)");
+    if (rows == 0) return PDM_OK;
+    PDM_REQUIRE(rows < (1ll << 31), "pdm_topk_smallest_f32: too many rows for one launch");
+    topk_smallest_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, ldx, n, (int)k, vals, idx);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

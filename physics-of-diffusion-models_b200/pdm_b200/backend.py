@@ -326,3 +326,14 @@ class CudaBackend:
                                                      self._stream()), "pdm_denoiser_backward_weights")
         self.launches += 1
         return w, sums
+
+    def topk_smallest(self, x: Tensor, k: int):
+        """k smallest entries per row of a dense (rows, n) matrix: (values (rows, k) ascending, indices int64)."""
+        x = self._f32(x)
+        rows, n = x.shape
+        vals = torch.empty(rows, k, dtype=torch.float32, device=self.device)
+        idx = torch.empty(rows, k, dtype=torch.int64, device=self.device)
+        check(self.lib.pdm_topk_smallest_f32(x.data_ptr(), _ld(x), rows, n, int(k), vals.data_ptr(), idx.data_ptr(),
+                                             self._stream()), "pdm_topk_smallest_f32")
+        self.launches += 1
+        return vals, idx

@@ -94,7 +94,10 @@ def _knn_sigma_reg_sq(eng: PosteriorEngine, knn_k: int, sigma_reg_scale: float) 
     step = max(1, min(ds.n, (1 << 30) // (4 * ds.n)))
     for r0 in range(0, ds.n, step):
         d2 = eng.pairwise_sqdist(ds.y[r0:r0 + step])
-        kth = torch.topk(d2, knn_k + 1, dim=1, largest=False).values[:, -1]
+        if hasattr(eng.backend, "topk_smallest"):
+            kth = eng.backend.topk_smallest(d2, min(knn_k + 1, ds.n))[0][:, -1]
+        else:                                       # CPU test double
+            kth = torch.topk(d2, min(knn_k + 1, ds.n), dim=1, largest=False).values[:, -1]
         out[r0:r0 + step] = kth.clamp_(min=0)
     return out * sigma_reg_scale / float(ds.d)
 

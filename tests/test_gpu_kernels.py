@@ -469,3 +469,20 @@ def test_empty_queries_and_extreme_temperatures(backend):
         assert torch.isfinite(mean).all()
         torch.testing.assert_close(mean[:3], data[:3], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(mean[-1], data.mean(0), rtol=1e-4, atol=1e-5)
+
+
+def test_topk_smallest(backend):
+    """pdm_topk_smallest_f32 against a stable sort (ties by lower index), incl. k > number of finite entries."""
+    g = syn.gen(51)
+    dev = backend.device
+    for rows, n, k in ((37, 1000, 6), (5, 50_000, 6), (3, 9, 9), (4, 300, 1)):
+        x = torch.randn(rows, n, generator=g)
+        x[:, n // 3] = x[:, n // 2]                                  # an exact tie in every row
+        x[0, :] = x[0, 0]                                            # a constant row: indices 0..k-1
+        vals, idx = backend.topk_smallest(x.to(dev), k)
+        order = torch.sort(x, dim=1, stable=True)
+        assert torch.equal(vals.cpu(), order.values[:, :k]) and torch.equal(idx.cpu(), order.indices[:, :k])
+    x = torch.full((2, 5), float("inf"))
+    x[0, 3] = 1.0
+    vals, idx = backend.topk_smallest(x.to(dev), 3)
+    assert idx.cpu()[0].tolist() == [3, 0, 1] and vals.cpu()[0, 0] == 1.0      # +inf entries are still entries (index order)
