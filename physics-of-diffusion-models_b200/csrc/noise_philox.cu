@@ -46,14 +46,17 @@ __global__ void __launch_bounds__(256) noised_row_scales_kernel(const float* __r
 }
 
 // 32-bit index arithmetic throughout (one draw stays below 2^31 elements); (row, column) of the four elements a
-// curand_normal4 call fills are advanced incrementally instead of divided out.
+// curand_normal4 call fills are advanced incrementally instead of divided out.  kX / kSplit select the outputs at
+// compile time; ldh == d on the split path, so operand offsets are row * d + k = t * numel + li.
+template <bool kX, bool kSplit>
 __global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;                   // < draw_threads by construction
     const unsigned t = blockIdx.y;
     const unsigned numel = (unsigned)(p.b * p.d), G = (unsigned)p.draw_threads, d = (unsigned)p.d;
     const unsigned gq = G / d, gr = G - gq * d;                                   // G = gq * d + gr
     const float sig = p.sigma[t];
-    const long long row0 = (long long)t * p.b;
+    const size_t draw0 = (size_t)t * numel;                                       // first element of this draw
+    const float* __restrict__ inv_scale = kSplit ? p.inv_scale + (size_t)t * p.b : nullptr;
     curandStatePhilox4_32_10_t st;
     curand_init(p.seed, (unsigned long long)idx, p.offset + (unsigned long long)t * p.offset_step, &st);
     unsigned li = idx, b = idx / d, k = idx - (idx / d) * d;
@@ -63,14 +66,15 @@ __global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p)
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
             if (li < numel) {
-                const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(p.x0 + (long long)b * p.ld_x0 + k));
-                const long long row = row0 + b;
-                if (p.x_out) p.x_out[row * p.ldx + k] = v;
-                if (p.hi) {
-                    const float vs = v * __frcp_rn(__ldg(p.inv_scale + row));     // exact: inv_scale is a power of two
+                const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(p.x0 + (size_t)b * p.ld_x0 + k));
+                if (kX) p.x_out[((size_t)t * p.b + b) * p.ldx + k] = v;
+                if (kSplit) {
+                    // 1 / inv_scale for a power of two: mirror the exponent field (254 - e), exact
+                    const float scale = __uint_as_float(0x7f000000u - __float_as_uint(__ldg(inv_scale + b)));
+                    const float vs = v * scale;
                     const __half h = __float2half_rn(vs);
-                    p.hi[row * p.ldh + k] = h;
-                    p.lo[row * p.ldh + k] = __float2half_rn(vs - __half2float(h));
+                    p.hi[draw0 + li] = h;
+                    p.lo[draw0 + li] = __float2half_rn(vs - __half2float(h));
                 }
             }
             li += G; b += gq; k += gr;                  // next element of this call: G further on
@@ -142,7 +146,9 @@ extern "C" int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t o
         PDM_CUDA_CHECK(cudaGetLastError());
     }
     dim3 grid((unsigned)(draw_threads / 256), (unsigned)n_draws);
-    noised_rows_philox_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+    if (x_out && hi)  noised_rows_philox_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(p);
+    else if (hi)      noised_rows_philox_kernel<false, true><<<grid, 256, 0, as_stream(stream)>>>(p);
+    else              noised_rows_philox_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(p);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

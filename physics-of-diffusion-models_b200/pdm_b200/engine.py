@@ -171,7 +171,8 @@ class EngineConfig:
     cta_group: int = 0                 # 0 = library default (2)
     m_group: int = 0
     n_splits: int = 0
-    max_query_bytes: int = 2 << 30     # scratch budget for one block of query rows (noise + split)
+    max_query_bytes: int = 6 << 30     # scratch budget for one block of query rows (noise + split): fewer, larger
+                                       # launches (and fewer cross-GPU merges) per schedule; 180 GB of HBM3e to spare
     max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
     sync_noise: bool = True            # sharded runs: make every rank draw rank 0's noise stream (set False when
                                        # every rank seeds its generator identically)
