@@ -217,7 +217,7 @@ def test_denoiser_backward_matches_reference_autograd(cuda_device, case):
                    * 0.5 * ab.item() ** -1.5 * dab)
         _grad_close(t.grad, g[f"{case}_gtau_{i}"], t64.grad, 1e-3 + 4 * floor_e, f"{case} grad tau tau#{i}", floor=floor_t)
     eng = sched._engine_for_data(data)
-    assert eng.precision() == ("f16x3" if case == "wide" else "exact")
+    assert eng.precision() == ("exact" if case == "gmm1d" else "f16x3")
 
 
 def test_denoiser_backward_lattice_and_sampler_chain(cuda_device):
