@@ -177,6 +177,8 @@ class EngineConfig:
     max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
     sync_noise: bool = True            # sharded runs: make every rank draw rank 0's noise stream (set False when
                                        # every rank seeds its generator identically)
+    delta_shortcut: bool = True        # posterior mean: rows whose posterior is a delta to fp32 resolution take their
+                                       # nearest training point directly (skips weights + second contraction for them)
     fused_noise: bool = True           # regenerate torch.randn's Philox stream inside the operand kernel (bit-identical,
                                        # verified once per device) instead of torch.randn + pdm_prepare_rows
     slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows and the
@@ -518,8 +520,28 @@ class PosteriorEngine:
             with ph("fused+energy"):
                 parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)
             with ph("merge"):
-                st, _ = self._merge(parts, inv_temp)
+                st, amin = self._merge(parts, inv_temp)
             e_min, l = st[_cabi.OUT_E_MIN], st[_cabi.OUT_L]
+            out_blk, sel = out[r0:r1], None
+            if self.cfg.delta_shortcut:
+                # Rows whose posterior is a delta to fp32 resolution (every other weight sums to <= 2^-23): the mean IS
+                # the nearest training point -- a gather (on the shard that owns it) instead of weights + contraction.
+                with ph("delta rows"):
+                    delta = (l - 1.0) <= 2.0 ** -23
+                    n_delta = int(delta.sum().item())
+                    if n_delta > 0:
+                        src = ds.y if values is None else values
+                        local = amin - ds.index_offset
+                        own = delta & (local >= 0) & (local < ds.n)
+                        picked = src.index_select(0, local.clamp(0, ds.n - 1)) * own[:, None].to(src.dtype)
+                        if n_delta == rows:
+                            out_blk.copy_(picked)
+                            continue
+                        sel = (~delta).nonzero().flatten()
+                        out_blk.copy_(picked * delta[:, None].to(src.dtype))
+                        energy, e_min, l, inv_temp = (energy.index_select(0, sel), e_min.index_select(0, sel).contiguous(),
+                                                      l.index_select(0, sel).contiguous(), inv_temp.index_select(0, sel).contiguous())
+            target = out_blk if sel is None else torch.empty(sel.shape[0], out.shape[1], dtype=torch.float32, device=dev)
             if tensor:
                 with ph("weights"):
                     p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
@@ -527,13 +549,15 @@ class PosteriorEngine:
                     yt_hi, yt_lo, yscale = vt if vt is not None else (ds.transposed_split() + (ds.scale,))
                     if vt is None and precision == "f16x2":
                         yt_lo = None                      # lattice dataset: weights_hi.Y + weights_lo.Y is all there is
-                    self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=out[r0:r1],
+                    self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=target,
                                             cta_group=self.cfg.cta_group)
             else:
                 with ph("weights"):
                     p = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=False)
                 with ph("gemm2"):
-                    self.backend.weighted_mean_exact(p, ds.y if values is None else values, out=out[r0:r1])
+                    self.backend.weighted_mean_exact(p, ds.y if values is None else values, out=target)
+            if sel is not None:
+                out_blk.index_copy_(0, sel, target)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out, group=self.group)

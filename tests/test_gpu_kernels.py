@@ -486,3 +486,28 @@ def test_topk_smallest(backend):
     x[0, 3] = 1.0
     vals, idx = backend.topk_smallest(x.to(dev), 3)
     assert idx.cpu()[0].tolist() == [3, 0, 1] and vals.cpu()[0, 0] == 1.0      # +inf entries are still entries (index order)
+
+
+@pytest.mark.parametrize("precision", ["exact", "f16x3"])
+def test_posterior_mean_delta_rows_shortcut(backend, precision):
+    """Rows whose posterior is a delta to fp32 resolution are gathered instead of contracted: same result as the full
+    weights + contraction path, for all-delta, no-delta and mixed batches."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = syn.gen(61)
+    n, d, m = 900, 384, 150
+    data = torch.rand(n, d, generator=g) * 2 - 1
+    ds = EmpiricalDataset(data, backend=backend)
+    x = data[torch.randint(0, n, (m,), generator=g)] + 0.05 * torch.randn(m, d, generator=g)
+    for name, temps in (("all delta", torch.full((m,), 1e-3)), ("none", torch.full((m,), 50.0)),
+                        ("mixed", torch.logspace(-3, 2.5, m))):
+        res = {}
+        for on in (True, False):
+            cfg = EngineConfig(precision=precision)
+            cfg.delta_shortcut = on
+            res[on] = PosteriorEngine(ds, cfg).posterior_mean(x, temps).cpu()
+        assert (res[True] - res[False]).abs().max().item() <= 3e-7 * data.abs().max().item() + 1e-7, name
+        e64 = 0.5 * orc.pairwise_sqdist(x.double(), data.double())
+        p64 = torch.softmax(-(e64 - e64.min(1, keepdim=True).values) / temps.double()[:, None], dim=1)
+        e32 = 0.5 * orc.pairwise_sqdist(x, data)
+        p32 = torch.softmax(-(e32 - e32.min(1, keepdim=True).values) / temps[:, None], dim=1)
+        arbitrated_close(res[True], p32 @ data, p64 @ data.double(), atol=2e-5, what=f"delta shortcut {name} {precision}")
