@@ -377,11 +377,13 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate)" if precision != "exact" else "f32",
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "C2: N=50000 d=3072 B=1024 x 1000-step linear-beta DDPM temperatures "
                                    "(compute_stats_batch)", "N": n, "d": d, "B": b, "n_T": n_t,
                        "precision": precision, "sharding": f"dataset rows / {world}",
+                       "arithmetic": ("fp32-equivalent: fp16 hi/lo split operands (22 significant bits), exact products, "
+                                      "fp32 accumulation on tcgen05 tensor cores" if precision != "exact" else "fp32 FMA on CUDA cores"),
                        "l2": "inputs (dataset 614 MB + queries) exceed the 126 MB L2; no flush needed",
                        "plan_splits_group_cta": plan},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
