@@ -84,21 +84,42 @@ def _dataset_summary(eng: PosteriorEngine) -> tuple[float, float, float]:
     return cached
 
 
+def _k_smallest(eng: PosteriorEngine, mat: Tensor, k: int) -> Tensor:
+    """(rows, k) smallest entries per row, ascending."""
+    if hasattr(eng.backend, "topk_smallest"):
+        return eng.backend.topk_smallest(mat, k)[0]
+    return torch.topk(mat, k, dim=1, largest=False).values          # CPU test double
+
+
 def _knn_sigma_reg_sq(eng: PosteriorEngine, knn_k: int, sigma_reg_scale: float) -> Tensor:
     """d_k^2 * scale / D with d_k the distance to the k-th neighbour, self excluded
-    (utils/stats.py:137-146, where sklearn's kneighbors(k+1) runs on the CPU)."""
+    (utils/stats.py:137-146, where sklearn's kneighbors(k+1) runs on the CPU).  With a row-sharded dataset every
+    rank searches its own shard for all N points and the per-shard candidates are merged (all-gather of k+1
+    distances per point and shard)."""
     ds = eng.ds
+    queries = ds.y
     if eng.world > 1:
-        raise NotImplementedError("adaptive k-NN regularisation is not available with a sharded dataset yet")
-    out = torch.empty(ds.n, dtype=torch.float32, device=ds.y.device)
-    step = max(1, min(ds.n, (1 << 30) // (4 * ds.n)))
-    for r0 in range(0, ds.n, step):
-        d2 = eng.pairwise_sqdist(ds.y[r0:r0 + step])
-        if hasattr(eng.backend, "topk_smallest"):
-            kth = eng.backend.topk_smallest(d2, min(knn_k + 1, ds.n))[0][:, -1]
-        else:                                       # CPU test double
-            kth = torch.topk(d2, min(knn_k + 1, ds.n), dim=1, largest=False).values[:, -1]
-        out[r0:r0 + step] = kth.clamp_(min=0)
+        src = getattr(ds, "full_moments_source", None)
+        if src is None:
+            raise NotImplementedError("adaptive k-NN regularisation with a sharded dataset needs the full dataset as queries")
+        queries = src.reshape(src.shape[0], -1).to(device=ds.y.device, dtype=torch.float32)
+    n_q = queries.shape[0]
+    kk = min(knn_k + 1, ds.n_total)
+    k_local = min(kk, ds.n)
+    out = torch.empty(n_q, dtype=torch.float32, device=ds.y.device)
+    step = max(1, min(n_q, (1 << 30) // (4 * ds.n)))
+    for r0 in range(0, n_q, step):
+        d2 = eng.pairwise_sqdist(queries[r0:r0 + step])
+        cand = _k_smallest(eng, d2, k_local)
+        if eng.world > 1:
+            import torch.distributed as dist
+            if k_local < kk:
+                cand = torch.cat([cand, torch.full((cand.shape[0], kk - k_local), float("inf"), device=cand.device)], dim=1)
+            allc = torch.empty(eng.world * cand.shape[0], kk, dtype=cand.dtype, device=cand.device)   # rank-major
+            dist.all_gather_into_tensor(allc, cand.contiguous(), group=eng.group)
+            allc = allc.view(eng.world, cand.shape[0], kk).permute(1, 0, 2).reshape(cand.shape[0], -1).contiguous()
+            cand = _k_smallest(eng, allc, kk)
+        out[r0:r0 + step] = cand[:, -1].clamp_(min=0)
     return out * sigma_reg_scale / float(ds.d)
 
 
