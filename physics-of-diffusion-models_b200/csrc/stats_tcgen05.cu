@@ -55,6 +55,26 @@ constexpr int kRegsEpilogue = 232;
 
 enum { EPI_STATS = 0, EPI_STORE = 1 };
 
+// Soft rendezvous of the TMA producers at the start of every round.  CTA groups that share a column split stream the
+// same dataset tiles; they start a round together and drift apart by a tile or two over its ~50 column tiles, which
+// L2 absorbs -- but nothing re-aligns them between rounds, and over a long launch the drift grows until every group
+// fetches its own copy of the dataset from HBM (measured: 0.48 MB of HBM reads per query row at 57k rows, 0.73 MB at
+// 172k).  Re-aligning once per round costs microseconds.  The wait is bounded (50 us): a group that is not resident
+// yet only costs the others that much, never a deadlock.  One counter per round, zeroed by the host before the launch.
+constexpr int kMaxSyncRounds = 16384;
+__device__ unsigned g_round_sync[kMaxSyncRounds];
+
+__device__ __forceinline__ void round_rendezvous(unsigned* counter, unsigned expected) {
+    atomicAdd(counter, 1u);
+    const uint64_t t0 = global_timer_ns();
+    while (true) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= expected || global_timer_ns() - t0 > 50000ull) break;
+        __nanosleep(256);
+    }
+}
+
 // Dev instrumentation (-DPDM_STALL_STATS): nanoseconds each role of every CTA spent blocked on its
 // barriers: [0] producer on smem-empty, [1] MMA on smem-full, [2] MMA on TMEM-empty, [3] epilogue warp 4
 // on TMEM-full, [4] kernel wall time.  Read + reset with pdm_debug_read_stalls.
@@ -74,6 +94,9 @@ struct GemmParams {
     int32_t flush_kb;     // k blocks accumulated inside the tensor core before a flush to registers
     uint32_t wait_hint_ns; // suspend-time hint of mbarrier.try_wait
     uint64_t hint_a, hint_b;   // L2 eviction-priority hints of the A (query) and B (dataset) tile loads
+    unsigned* round_sync;      // soft rendezvous of the TMA producers (nullptr = off), one counter per rendezvous
+    int32_t sync_points;       // counters available
+    int32_t sync_tiles;        // column tiles between two rendezvous
     int32_t m_tiles;      // row super-tiles of 128*CG rows
     int32_t n_tiles;      // column tiles of kBlockN
     int32_t m_group, n_splits;
@@ -176,7 +199,17 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #endif
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
                 const int32_t a_row = (mt * CG + (int)rank) * kRowsPerCta;
-                for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
+                const int round = mt / p.m_group;
+                const int row_groups = min(p.m_group, p.m_tiles - round * p.m_group);     // row tiles at work this round
+                const int per_round = (ceil_div(p.n_tiles, p.n_splits) + p.sync_tiles - 1) / max(1, p.sync_tiles);
+                int j = 0;
+                for (int nt = sp; nt < p.n_tiles; nt += p.n_splits, ++j) {
+                    if (p.round_sync && j % p.sync_tiles == 0 && (round > 0 || j > 0)) {
+                        const int point = round * per_round + j / p.sync_tiles;
+                        // column splits that still have a tile at step j: s + j*S < n_tiles
+                        const int col_groups = min(p.n_splits, p.n_tiles - j * p.n_splits);
+                        if (point < p.sync_points) round_rendezvous(p.round_sync + point, (unsigned)(row_groups * col_groups * CG));
+                    }
                     const int32_t b_row = nt * kBlockN + (int)rank * kRowsPerCta;
                     for (int kb = 0; kb < p.num_kb; ++kb) {
                         { PDM_STALL_BEGIN(); mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns); PDM_STALL_END(st_empty); }
@@ -589,7 +622,7 @@ static int require_sm100(DeviceInfo* info) {
 // few idle SMs cost nothing and HBM traffic does (B200, C2 block: (S,G) = (4,16) reads 23 GB per launch,
 // (9,8) 57 GB, same run time).  If nothing fits, the shortest schedule is taken.
 void plan_schedule(int pairs, int64_t m_tiles, int64_t n_tiles, int64_t a_tile_bytes, int* m_group, int* n_splits) {
-    const int64_t budget = 52ll << 20;
+    const int64_t budget = 50ll << 20;               // 16 live A tiles at d = 3072; 17 falls off an L2 cliff (+45 % HBM reads)
     const int64_t g_cap = std::max<int64_t>(1, budget / std::max<int64_t>(1, a_tile_bytes));
     int64_t min_steps = -1;
     for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
@@ -644,6 +677,21 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.wait_hint_ns = wait_hint_setting();
     p.hint_a = evict_hint_setting("PDM_HINT_A", kEvictNormal);
     p.hint_b = evict_hint_setting("PDM_HINT_B", kEvictNormal);
+    {
+        static const bool round_sync_on = !(getenv("PDM_ROUND_SYNC") && atoi(getenv("PDM_ROUND_SYNC")) == 0);
+        const int64_t rounds = ceil_div(ceil_div(a.M, (int64_t)kRowsPerCta * cg), (int64_t)a.m_group);
+        static const int sync_tiles = getenv("PDM_SYNC_TILES") ? std::max(1, atoi(getenv("PDM_SYNC_TILES"))) : 8;
+        const int64_t cols_per_round = ceil_div(ceil_div(a.N, (int64_t)(cg == 2 ? 256 : 128)), (int64_t)a.n_splits);
+        const int64_t points = rounds * ceil_div(cols_per_round, (int64_t)sync_tiles);
+        if (round_sync_on && points > 1) {
+            void* sym = nullptr;
+            PDM_CUDA_CHECK(cudaGetSymbolAddress(&sym, g_round_sync));
+            p.sync_points = (int32_t)std::min<int64_t>(points, kMaxSyncRounds);
+            p.sync_tiles = sync_tiles;
+            PDM_CUDA_CHECK(cudaMemsetAsync(sym, 0, sizeof(unsigned) * p.sync_points, stream));
+            p.round_sync = static_cast<unsigned*>(sym);
+        }
+    }
     p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
     p.m_group = a.m_group; p.n_splits = a.n_splits;
