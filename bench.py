@@ -391,9 +391,10 @@ def run_ours(args):
                            "after the first call"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["tflops"], "traffic": profiled_traffic() if (world == 1 and n_t * b >= 57344) else None,
-                         "traffic_note": "HBM bytes per launch (57344 query rows x full dataset) from profiles/r1_fused_gemm_ncu_full_bench_block.csv; "
-                                         "algorithmic minimum 1.3e9 (operands once)",
+                         "frac": ach / peaks["tflops"], "traffic": profiled_traffic() if (world == 1 and n_t * b >= 172032) else None,
+                         "traffic_note": "HBM bytes (read + write) of ONE launch = one 6 GiB block of the step, 172032 query rows x the "
+                                         "full dataset, from the ncu --set full capture summarised in profiles/"
+                                         "r1_fused_gemm_ncu_full_bench_block.csv; algorithmic minimum 2.7e9 (operands once)",
                          "kernel": "pdm::tc::fused_gemm_kernel",
                          "executed_tflops": terms * ach, "kernel_ms_per_step": k_ms / max(1, args.steps),
                          "peak_source": peaks["source"], "flops_per_pair": 2 * d},

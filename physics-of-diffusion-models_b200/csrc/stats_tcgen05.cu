@@ -615,35 +615,25 @@ static int require_sm100(DeviceInfo* info) {
     return PDM_OK;
 }
 
-// Pick (m_group, n_splits) = (G, S).  Every CTA group walks ceil(m_tiles/G) * ceil(n_tiles/S) tiles: that product
-// is the schedule's length (tile quantisation).  The dataset is streamed from HBM once per ROUND (= ceil(m_tiles/G)
-// of them) as long as the G live A tiles stay in L2, so among the schedules within 12 % of the shortest one whose A
-// tiles fit a 52 MB L2 budget the one with the fewest rounds wins: the kernel runs at the chip's power cap, where a
-// few idle SMs cost nothing and HBM traffic does (B200, C2 block: (S,G) = (4,16) reads 23 GB per launch,
-// (9,8) 57 GB, same run time).  If nothing fits, the shortest schedule is taken.
+// Pick (m_group, n_splits) = (G, S).  Every CTA group walks ceil(m_tiles/G) * ceil(n_tiles/S) tiles: that product is
+// the schedule's length (tile quantisation).  The shortest schedule whose G live A tiles fit a 50 MB L2 budget wins
+// (ties: the larger G = fewer passes over the dataset); if nothing fits, the shortest overall.  With the producers
+// re-aligned every few column tiles (round_rendezvous) the dataset tiles of a split are shared out of L2 for any G, so
+// keeping all 74 groups busy beats minimising HBM passes: measured on the 172 032 x 50 000 block, (S,G) = (6,12)
+// 119.9 ms, (9,8) 120.8, (5,14) 121.9, (4,16) 125.1 (gpurun_out/exp11.log).
 void plan_schedule(int pairs, int64_t m_tiles, int64_t n_tiles, int64_t a_tile_bytes, int* m_group, int* n_splits) {
-    const int64_t budget = 50ll << 20;               // 16 live A tiles at d = 3072; 17 falls off an L2 cliff (+45 % HBM reads)
+    const int64_t budget = 50ll << 20;
     const int64_t g_cap = std::max<int64_t>(1, budget / std::max<int64_t>(1, a_tile_bytes));
-    int64_t min_steps = -1;
-    for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
-        const int64_t g = std::min<int64_t>(pairs / s, m_tiles);
-        const int64_t steps = ceil_div(m_tiles, g) * ceil_div(n_tiles, (int64_t)s);
-        if (min_steps < 0 || steps < min_steps) min_steps = steps;
-    }
     int best_g = 0, best_s = 0;
-    int64_t best_rounds = 0, best_steps = 0;
+    int64_t best_steps = 0;
     for (int pass = 0; pass < 2 && best_g == 0; ++pass) {         // pass 0: inside the L2 budget; pass 1: anything
         for (int s = 1; s <= pairs && s <= n_tiles; ++s) {
             for (int64_t g = std::min<int64_t>(pairs / s, m_tiles); g >= 1; --g) {
                 if (pass == 0 && g > g_cap) continue;
                 const int64_t steps = ceil_div(m_tiles, g) * ceil_div(n_tiles, (int64_t)s);
-                if (pass == 0 && steps * 100 > min_steps * 112) continue;
-                const int64_t rounds = ceil_div(m_tiles, g);
-                const bool better = best_g == 0 ||
-                    (pass == 0 ? (rounds < best_rounds || (rounds == best_rounds && steps < best_steps) ||
-                                  (rounds == best_rounds && steps == best_steps && g < best_g))
-                               : (steps < best_steps || (steps == best_steps && g > best_g)));
-                if (better) { best_g = (int)g; best_s = s; best_rounds = rounds; best_steps = steps; }
+                if (best_g == 0 || steps < best_steps || (steps == best_steps && g > best_g)) {
+                    best_g = (int)g; best_s = s; best_steps = steps;
+                }
             }
         }
     }
@@ -676,7 +666,7 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.flush_kb = flush_kb_setting(terms);
     p.wait_hint_ns = wait_hint_setting();
     p.hint_a = evict_hint_setting("PDM_HINT_A", kEvictNormal);
-    p.hint_b = evict_hint_setting("PDM_HINT_B", kEvictNormal);
+    p.hint_b = evict_hint_setting("PDM_HINT_B", kEvictFirst);      // dataset tiles are dead once their split has passed
     {
         static const bool round_sync_on = !(getenv("PDM_ROUND_SYNC") && atoi(getenv("PDM_ROUND_SYNC")) == 0);
         const int64_t rounds = ceil_div(ceil_div(a.M, (int64_t)kRowsPerCta * cg), (int64_t)a.m_group);
