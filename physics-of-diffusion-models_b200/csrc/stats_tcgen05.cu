@@ -1,22 +1,26 @@
 // tcgen05 / TMEM / TMA fused pass for sm_100a.
 //
 // One warp-specialised persistent kernel computes S = A.B^T on the 5th-generation tensor cores with the
-// fp16 hi/lo operand split (three kind::f16 MMAs per k-step: hi.hi + lo.hi + hi.lo, fp32 accumulation in
-// TMEM) and consumes each accumulator tile straight from TMEM in one of two epilogues:
+// fp16 hi/lo operand split (TERMS kind::f16 MMAs per k-step: hi.hi + lo.hi [+ hi.lo], exact products, fp32
+// accumulation in TMEM; TERMS = 2 when the dataset is an fp16-exact lattice and its lo part is empty) and consumes
+// each accumulator tile straight from TMEM in one of two epilogues:
 //   EPI_STATS  energies E = 0.5*((|x|^2 - 2 x.y) + |y|^2) -> online min / log-sum-exp / energy moments
 //              per query row (online_stats.cuh); the M x N distance matrix never reaches HBM.
 //              Replaces utils/distance.py:13-21 + utils/stats.py:71-101, 271-289 + scheduler.py:64-68.
 //   EPI_STORE  out = scale * S, the posterior-mean contraction p @ data (scheduler.py:69).
 //
 // Per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only with cta_group::2), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (thread <-> TMEM lane <-> query row).  Pipelines: smem full/empty
-// (TMA <-> MMA, kStages deep) and TMEM full/empty (MMA <-> epilogue, 2 accumulator stages), all mbarriers.
-// With cta_group::2 a CTA pair owns a 256-row x 256-column tile: each CTA loads its 128 A rows and half of
-// the B rows, the leader issues M=256 MMAs, each CTA's epilogue drains its own TMEM half.
+// allocator, warps 4-11 = epilogue (two warps per TMEM lane quarter; thread <-> TMEM lane <-> query row).
+// Pipelines: smem full/empty (TMA <-> MMA, kStages deep) and TMEM full/empty (MMA <-> epilogue, 2 accumulator
+// stages), all mbarriers.  The accumulator is flushed into fp32 registers (round-to-nearest adds) every flush_kb
+// k-blocks: the tensor core's own accumulation truncates.  With cta_group::2 a CTA pair owns a 256-row x
+// 256-column tile: each CTA loads its 128 A rows and half of the B rows, the leader issues M=256 MMAs, each CTA's
+// epilogue drains its own TMEM half.
 //
 // Schedule: pair p -> (i = p % m_group, s = p / m_group).  Round r handles row super-tile r*m_group + i;
 // within it the pair walks column tiles s, s + n_splits, ...  Pairs that share i re-use the same A tiles
-// out of L2 while pairs that share s stream the same B tiles; partial records per (row, s) are merged by
+// out of L2 while pairs that share s stream the same B tiles (the producers re-align every few column tiles,
+// round_rendezvous, so that this sharing survives a long launch); partial records per (row, s) are merged by
 // pdm_merge_partials (the same rule that merges dataset shards across GPUs).
 #include "pdm_common.cuh"
 #include "online_stats.cuh"
