@@ -255,9 +255,13 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            step(args.warmup + i)
+            last = step(args.warmup + i)
         e1.record()
         barrier()
+        # the timed steps produced real statistics: S = logZ' + <e> - log N lies in [-log N, 0] at every temperature
+        lo_s, hi_s = float(last.min().item()), float(last.max().item())
+        if not (math.isfinite(lo_s) and math.isfinite(hi_s) and lo_s >= -math.log(n) - 1e-3 and hi_s <= 1e-3):
+            raise RuntimeError(f"bench: entropy out of range [{lo_s}, {hi_s}] -- the timed path did not compute the statistics")
         clk = clock_sampler.stop() if clock_sampler is not None else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
