@@ -181,15 +181,20 @@ class EngineConfig:
                                        # nearest training point directly (skips weights + second contraction for them)
     fused_noise: bool = True           # regenerate torch.randn's Philox stream inside the operand kernel (bit-identical,
                                        # verified once per device) instead of torch.randn + pdm_prepare_rows
-    slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows and the
-                                       # prepared operands are all-gathered.  Off by default: regenerating all rows
-                                       # in-kernel costs ~0.9 ms per 0.7 GB block on B200, less than all-gathering them.
+    slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows on a side
+                                       # stream, one block ahead, and the operands are all-gathered.  Off: measured on
+                                       # 8 B200s the exchange does not hide under the persistent tensor kernel (no free
+                                       # SMs for NCCL) -- 114.8 ms per step against 109.5 ms with every rank regenerating
+                                       # all rows in-kernel (17 ms per step).  PDM_SLICE_NOISE=1 turns it on.
 
     @staticmethod
     def from_env() -> "EngineConfig":
-        return EngineConfig(precision=os.environ.get("PDM_PRECISION", "auto"),
-                            cta_group=_env_int("PDM_CTA_GROUP"), m_group=_env_int("PDM_M_GROUP"),
-                            n_splits=_env_int("PDM_N_SPLITS"))
+        cfg = EngineConfig(precision=os.environ.get("PDM_PRECISION", "auto"),
+                           cta_group=_env_int("PDM_CTA_GROUP"), m_group=_env_int("PDM_M_GROUP"),
+                           n_splits=_env_int("PDM_N_SPLITS"))
+        if os.environ.get("PDM_SLICE_NOISE", "") in ("0", "1"):
+            cfg.slice_noise = os.environ["PDM_SLICE_NOISE"] == "1"
+        return cfg
 
 
 class PosteriorEngine:
@@ -330,8 +335,37 @@ class PosteriorEngine:
             self._sync_generator(dev)            # every rank regenerates rank 0's stream: 16 bytes instead of the noise
         x0_absmax = self.backend.row_absmax(x0f) if fused and self.precision() != "exact" else None
         if sliced:
+            # Each rank draws + prepares 1/world of a block's rows on a side stream and the operands are all-gathered
+            # there, one block ahead of the fused pass on the main stream: the replicated Philox work (ALU-bound,
+            # ~2 % of a single-GPU step but world times that share of a sharded one) shrinks by `world`, and the
+            # NVLink all-gather hides under the tensor-core kernel.
             t_per_block = max(self.world, t_per_block // self.world * self.world)
             self._sync_generator(dev)
+            blocks = [(t0, min(n_t, t0 + t_per_block)) for t0 in range(0, n_t, t_per_block)]
+            main = torch.cuda.current_stream(dev)
+            side = self._side_stream(dev)
+
+            def launch(t0, t1):
+                side.wait_stream(main)                     # inputs (and the buffers of earlier blocks) are ready
+                with torch.cuda.stream(side):
+                    return self._sliced_prepare(x0, x0f, temp[t0:t1], dev, fused, x0_absmax)
+
+            nxt = launch(*blocks[0])
+            for k, (t0, t1) in enumerate(blocks):
+                prep = nxt
+                main.wait_stream(side)
+                for t in prep.values():
+                    if t is not None:
+                        t.record_stream(main)
+                if k + 1 < len(blocks):
+                    nxt = launch(*blocks[k + 1])           # enqueued before this block's fused pass: runs beside it
+                o, i = self.stats_block(x0f, (t1 - t0) * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep)
+                outs.append(o)
+                idxs.append(i)
+            out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
+            res = {k: out[j].view(n_t, b) for j, k in enumerate(STAT_KEYS)}
+            res["argmin"] = (torch.cat(idxs) if len(idxs) > 1 else idxs[0]).view(n_t, b)
+            return res
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
@@ -339,14 +373,6 @@ class PosteriorEngine:
             if ph is None:
                 import contextlib
                 ph = lambda _n: contextlib.nullcontext()  # noqa: E731
-            if sliced:
-                t_rows = temp[t0:t1].repeat_interleave(b)
-                with ph("noise+prepare+gather"):
-                    prep = self._sliced_prepare(x0, x0f, temp[t0:t1], dev, fused, x0_absmax)
-                o, i = self.stats_block(x0f, nb * b, t_rows, aux=aux, prep=prep)
-                outs.append(o)
-                idxs.append(i)
-                continue
             if fused:
                 with ph("noise+prepare"):
                     gen = self._cuda_generator(dev)
@@ -396,6 +422,15 @@ class PosteriorEngine:
             step = g.get_offset() - o0
             PosteriorEngine._RANDN_OFFSETS[key] = step
         return step
+
+    _SIDE_STREAMS: dict = {}
+
+    @staticmethod
+    def _side_stream(dev: torch.device):
+        key = str(dev)
+        if key not in PosteriorEngine._SIDE_STREAMS:
+            PosteriorEngine._SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+        return PosteriorEngine._SIDE_STREAMS[key]
 
     def _sync_generator(self, dev: torch.device) -> None:
         """Give every rank rank 0's CUDA generator state (seed and offset), so that each can draw its slice of the
