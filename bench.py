@@ -167,7 +167,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     w = workload()
-    b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 2)
+    b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 8)
     orc, data, x0, temps = cpu_sample(w, b_cpu, nt_cpu, 0)
     cores = torch.get_num_threads()
     for _ in range(args.warmup):
@@ -412,7 +412,7 @@ def run_ours(args):
             lattice_line["roofline_frac"] = lattice_line["kernel_algorithmic_tflops"] / peak
             line["lattice_8bit"] = lattice_line
         if world == 1:
-            b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 4)
+            b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 96)
             orc, cdata, cx0, ctemps = cpu_sample(w, b_cpu, nt_cpu, 0)
             cpu_step(orc, cdata[:2000], cx0, ctemps[:1])           # warm the BLAS threads
             t0 = time.perf_counter()
