@@ -109,7 +109,8 @@ int pdm_prepare_rows(const float* src, int64_t src_rows, int64_t ld_src,
  * with eps bit-identical to what torch.randn would have written (same thread <-> element map, same cuRAND
  * device functions; `draw_threads` = 256 * grid of that torch launch).  Outputs: x_out fp32 (optional) and/or the
  * fp16 hi/lo split with inv_scale, scaled by the per-row power of two given by the bound max|x0_r| + 6.8 sigma[t]
- * (ldh == d, d % 8 == 0).  Row norms of the split operands: pdm_split_row_norms.  Replaces the torch.randn launch +
+ * (x0 and the outputs contiguous: ld_x0 == ldx == ldh == d; d % 8 == 0 for the split).  Row norms of the split
+ * operands: pdm_split_row_norms.  Replaces the torch.randn launch +
  * pdm_prepare_rows pair (12 B/element less HBM traffic); the host checks bit-identity against torch.randn once. */
 int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t offset_step, int64_t draw_threads,
                            const float* x0, int64_t b, int64_t d, int64_t ld_x0,

@@ -55,7 +55,12 @@ __global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p)
     const unsigned numel = (unsigned)(p.b * p.d), G = (unsigned)p.draw_threads, d = (unsigned)p.d;
     const unsigned gq = G / d, gr = G - gq * d;                                   // G = gq * d + gr
     const float sig = p.sigma[t];
-    const size_t draw0 = (size_t)t * numel;                                       // first element of this draw
+    // x0 is contiguous (ld_x0 == d) and so are the outputs (ldx == ldh == d): element li of draw t sits at offset li
+    // of the draw's slab, 32-bit offsets from per-draw base pointers
+    const float* __restrict__ x0 = p.x0;
+    float* __restrict__ xo = kX ? p.x_out + (size_t)t * numel : nullptr;
+    __half* __restrict__ hi = kSplit ? p.hi + (size_t)t * numel : nullptr;
+    __half* __restrict__ lo = kSplit ? p.lo + (size_t)t * numel : nullptr;
     const float* __restrict__ inv_scale = kSplit ? p.inv_scale + (size_t)t * p.b : nullptr;
     curandStatePhilox4_32_10_t st;
     curand_init(p.seed, (unsigned long long)idx, p.offset + (unsigned long long)t * p.offset_step, &st);
@@ -66,19 +71,19 @@ __global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p)
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
             if (li < numel) {
-                const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(p.x0 + (size_t)b * p.ld_x0 + k));
-                if (kX) p.x_out[((size_t)t * p.b + b) * p.ldx + k] = v;
+                const float v = __fadd_rn(__fmul_rn(rv[ii], sig), __ldg(x0 + li));
+                if (kX) xo[li] = v;
                 if (kSplit) {
                     // 1 / inv_scale for a power of two: mirror the exponent field (254 - e), exact
                     const float scale = __uint_as_float(0x7f000000u - __float_as_uint(__ldg(inv_scale + b)));
                     const float vs = v * scale;
                     const __half h = __float2half_rn(vs);
-                    p.hi[draw0 + li] = h;
-                    p.lo[draw0 + li] = __float2half_rn(vs - __half2float(h));
+                    hi[li] = h;
+                    lo[li] = __float2half_rn(vs - __half2float(h));
                 }
             }
-            li += G; b += gq; k += gr;                  // next element of this call: G further on
-            if (k >= d) { k -= d; ++b; }
+            li += G;                                    // next element of this call: G further on
+            if (kSplit) { b += gq; k += gr; if (k >= d) { k -= d; ++b; } }
         }
     }
 }
@@ -127,12 +132,13 @@ extern "C" int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t o
                                       const float* sigma, int64_t n_draws, const float* x0_absmax,
                                       float* x_out, int64_t ldx,
                                       uint16_t* hi, uint16_t* lo, int64_t ldh, float* inv_scale, pdm_stream_t stream) {
-    PDM_REQUIRE(x0 && sigma && b > 0 && d > 0 && ld_x0 >= d && n_draws >= 0, "pdm_noised_rows_philox: bad arguments");
+    PDM_REQUIRE(x0 && sigma && b > 0 && d > 0 && ld_x0 == d && n_draws >= 0,
+                "pdm_noised_rows_philox: bad arguments (x0 must be contiguous: ld_x0 == d)");
     PDM_REQUIRE(draw_threads > 0 && draw_threads % 256 == 0 && draw_threads / 256 <= 0x7fffffffll,
                 "pdm_noised_rows_philox: draw_threads must be a positive multiple of 256");
     PDM_REQUIRE(b * d < (1ll << 31), "pdm_noised_rows_philox: one draw must stay below 2^31 elements (torch splits larger ones)");
     PDM_REQUIRE(x_out || hi, "pdm_noised_rows_philox: no output requested");
-    PDM_REQUIRE(!x_out || ldx >= d, "pdm_noised_rows_philox: ldx < d");
+    PDM_REQUIRE(!x_out || ldx == d, "pdm_noised_rows_philox: x_out must be contiguous (ldx == d)");
     PDM_REQUIRE((hi == nullptr) == (lo == nullptr), "pdm_noised_rows_philox: hi and lo go together");
     PDM_REQUIRE(!hi || (x0_absmax && inv_scale && ldh == d && d % 8 == 0),
                 "pdm_noised_rows_philox: the split needs x0_absmax, inv_scale and ldh == d with d %% 8 == 0");
