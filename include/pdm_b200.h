@@ -254,10 +254,12 @@ int pdm_topk_smallest_f32(const float* x, int64_t ldx, int64_t rows, int64_t n, 
  *     w[r,j] = p_rj (s_rj - a_r)   and   sums[r] = (a_r, sum_j w_rj e_rj);
  * the caller contracts w with the dataset like the forward weights.  (Centring first: the uncentred form
  * sum p s y - a x0_hat cancels to zero at low T and its round-off would be amplified by 1/T.)
+ * Row-sharded datasets: a first call (a_in = NULL) yields the local a_r; the caller sums them over the shards
+ * and calls again with a_in = the global a_r (e_min, l are the merged, global ones in both calls).
  * ------------------------------------------------------------------------------------------- */
 int pdm_denoiser_backward_weights(const float* energy, int64_t lde, const float* sdot, int64_t lds,
                                   int64_t M, int64_t N, const float* e_min, const float* l,
-                                  const float* inv_temp, const float* s_scale,
+                                  const float* inv_temp, const float* s_scale, const float* a_in,
                                   float* w, int64_t ldw, float* sums, pdm_stream_t stream);
 
 #ifdef __cplusplus

@@ -378,19 +378,25 @@ __global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) denoiser_backward_weights_kernel(
     const float* __restrict__ energy, int64_t lde, const float* __restrict__ sdot, int64_t lds, int64_t N,
     const float* __restrict__ e_min, const float* __restrict__ l, const float* __restrict__ inv_temp,
-    const float* __restrict__ s_scale, float* __restrict__ w, int64_t ldw, float* __restrict__ sums) {
+    const float* __restrict__ s_scale, const float* __restrict__ a_in, float* __restrict__ w, int64_t ldw,
+    float* __restrict__ sums) {
     __shared__ double red_d[32];
     const int64_t row = blockIdx.x;
     const float m = e_min[row], it = inv_temp[row], inv_l = 1.f / l[row], sc = s_scale ? s_scale[row] : 1.f;
     const float* er = energy + row * lde;
     const float* sr = sdot + row * lds;
     float* wr = w + row * ldw;
-    double a = 0.0;
-    for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
-        const float e = fminf((__ldg(er + j) - m) * it, kMaxE);
-        a += (double)(fast_exp2(-e * kLog2e) * inv_l) * (double)(sc * __ldg(sr + j));
+    float af;
+    if (a_in) {
+        af = a_in[row];                      // a summed over every shard of the dataset by the caller
+    } else {
+        double a = 0.0;
+        for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
+            const float e = fminf((__ldg(er + j) - m) * it, kMaxE);
+            a += (double)(fast_exp2(-e * kLog2e) * inv_l) * (double)(sc * __ldg(sr + j));
+        }
+        af = (float)block_reduce(a, OpAddD(), 0.0, red_d);
     }
-    const float af = (float)block_reduce(a, OpAddD(), 0.0, red_d);
     double b = 0.0;
     for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
         const float e = fminf((__ldg(er + j) - m) * it, kMaxE);
@@ -563,14 +569,14 @@ extern "C" int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t
 
 extern "C" int pdm_denoiser_backward_weights(const float* energy, int64_t lde, const float* sdot, int64_t lds,
                                              int64_t M, int64_t N, const float* e_min, const float* l,
-                                             const float* inv_temp, const float* s_scale,
+                                             const float* inv_temp, const float* s_scale, const float* a_in,
                                              float* w, int64_t ldw, float* sums, pdm_stream_t stream) {
     PDM_REQUIRE(energy && sdot && e_min && l && inv_temp && w && sums && M >= 0 && N > 0 && lde >= N && lds >= N && ldw >= N,
                 "pdm_denoiser_backward_weights: bad arguments");
     if (M == 0) return PDM_OK;
     PDM_REQUIRE(M < (1ll << 31), "pdm_denoiser_backward_weights: M too large for one launch");
     denoiser_backward_weights_kernel<<<(unsigned)M, 256, 0, as_stream(stream)>>>(energy, lde, sdot, lds, N, e_min, l, inv_temp,
-                                                                                s_scale, w, ldw, sums);
+                                                                                s_scale, a_in, w, ldw, sums);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

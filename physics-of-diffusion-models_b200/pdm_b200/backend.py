@@ -315,14 +315,14 @@ class CudaBackend:
         return out
 
     def denoiser_backward_weights(self, energy: Tensor, sdot: Tensor, e_min: Tensor, l: Tensor, inv_temp: Tensor,
-                                  s_scale: Optional[Tensor] = None):
+                                  s_scale: Optional[Tensor] = None, a_in: Optional[Tensor] = None):
         """Centred weights w = p * (s - a) (M, N), s = s_scale * sdot, a = sum_j p_j s_j, and sums (M, 2) = (a, sum w e)."""
         m, n = energy.shape
         w = torch.empty(m, n, dtype=torch.float32, device=self.device)
         sums = torch.empty(m, 2, dtype=torch.float32, device=self.device)
         check(self.lib.pdm_denoiser_backward_weights(energy.data_ptr(), _ld(energy), sdot.data_ptr(), _ld(sdot),
                                                      m, n, e_min.data_ptr(), l.data_ptr(), inv_temp.data_ptr(),
-                                                     _ptr(s_scale), w.data_ptr(), _ld(w), sums.data_ptr(),
+                                                     _ptr(s_scale), _ptr(a_in), w.data_ptr(), _ld(w), sums.data_ptr(),
                                                      self._stream()), "pdm_denoiser_backward_weights")
         self.launches += 1
         return w, sums

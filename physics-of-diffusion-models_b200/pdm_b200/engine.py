@@ -604,8 +604,6 @@ class PosteriorEngine:
         temperature.  The energies are recomputed (nothing of size M x N is kept between forward and backward):
             s_j = y_j . g,  a = sum_j p_j s_j,   g_q = sum_j p_j (s_j - a) y_j / T = Cov_p(s, y) / T,
             g_T = sum_j p_j (s_j - a) e_j / T = Cov_p(s, e) / T        with e_j = (E_j - E_min) / T."""
-        if self.world > 1:
-            raise PdmError("posterior_mean_backward is not available with a sharded dataset yet")
         dev = self.backend.device
         ds = self.ds
         xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
@@ -633,7 +631,7 @@ class PosteriorEngine:
                 gp = self.backend.prepare_rows(g[r0:r1], rows, want_norms=False)
                 sdot = self.backend.split_gemm(gp["hi"], gp["lo"], y_hi, None if precision == "f16x2" else y_lo, ds.d,
                                                1.0 / ds.scale, cta_group=self.cfg.cta_group)      # (rows, n) * 2^k_row
-                w, sums = self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp, gp["inv_scale"])
+                w, sums = self._centred_weights(energy, sdot, e_min, l, inv_temp, gp["inv_scale"])
                 wp = self.backend.prepare_rows(w, rows, want_norms=False)
                 yt_hi, yt_lo = ds.transposed_split()
                 acc = self.backend.split_gemm(wp["hi"], wp["lo"], yt_hi, None if precision == "f16x2" else yt_lo, ds.n,
@@ -641,11 +639,26 @@ class PosteriorEngine:
                 acc = acc * wp["inv_scale"][:, None]
             else:
                 sdot = self.backend.weighted_mean_exact(g[r0:r1], ds.transposed())
-                w, sums = self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp)
+                w, sums = self._centred_weights(energy, sdot, e_min, l, inv_temp, None)
                 acc = self.backend.weighted_mean_exact(w, ds.y)
             g_q[r0:r1] = acc * inv_temp[:, None]
             g_t[r0:r1] = sums[:, 1] * inv_temp
+        if self.world > 1:                      # Cov_p(s, y) and Cov_p(s, e) are sums over the shards' dataset rows
+            import torch.distributed as dist
+            dist.all_reduce(g_q, group=self.group)
+            dist.all_reduce(g_t, group=self.group)
         return g_q, g_t
+
+    def _centred_weights(self, energy, sdot, e_min, l, inv_temp, s_scale):
+        """w = p (s - a) and (a, sum w e).  With a row-sharded dataset a = sum_j p_j s_j runs over every shard: local
+        sums first, all-reduce, then the centring with the global a."""
+        if self.world == 1:
+            return self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp, s_scale)
+        import torch.distributed as dist
+        _, sums = self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp, s_scale)
+        a = sums[:, 0].contiguous()
+        dist.all_reduce(a, group=self.group)
+        return self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp, s_scale, a_in=a)
 
     # -- dense distances (callers of compute_pw_dist_sqr index / min / scatter the matrix) -----------
     def pairwise_sqdist(self, x: Tensor) -> Tensor:

@@ -153,10 +153,10 @@ class FakeBackend:
             out.copy_(r)
         return out
 
-    def denoiser_backward_weights(self, energy, sdot, e_min, l, inv_temp, s_scale=None):
+    def denoiser_backward_weights(self, energy, sdot, e_min, l, inv_temp, s_scale=None, a_in=None):
         e = (energy - e_min[:, None]) * inv_temp[:, None]
         p = torch.exp(-e) / l[:, None]
         s = sdot if s_scale is None else sdot * s_scale[:, None]
-        a = (p * s).sum(1)
+        a = (p * s).sum(1) if a_in is None else a_in
         w = p * (s - a[:, None])
         return w, torch.stack([a, (w * e).sum(1)], dim=1)

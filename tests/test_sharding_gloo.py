@@ -43,11 +43,14 @@ def _worker(rank, world, port, out_dir):
     st = eng.noised_stats(x0, temp)
     xq = x0 + 0.3 * torch.randn(b, d, generator=torch.Generator().manual_seed(5))
     mean = eng.posterior_mean(xq, torch.full((b,), 0.5))
+    up = torch.randn(b, d, generator=torch.Generator().manual_seed(6))
+    gq, gt = eng.posterior_mean_backward(xq, torch.full((b,), 0.5), None, up)
     # adaptive k-NN regulariser on the sharded dataset: every rank searches its shard, candidates are merged
     import utils.stats as ustats
     ds.full_moments_source = data
     sig = ustats._knn_sigma_reg_sq(eng, 5, 1.0)
     torch.save({"entropy": st["entropy"], "argmin": st["argmin"], "var_e": st["var_e"], "mean": mean, "sigma_reg_sq": sig,
+                "gq": gq, "gt": gt,
                 "calls": be.calls}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -59,7 +62,7 @@ def test_two_rank_sharded_equals_unsharded(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
-    for k in ("entropy", "argmin", "var_e", "mean", "sigma_reg_sq"):
+    for k in ("entropy", "argmin", "var_e", "mean", "sigma_reg_sq", "gq", "gt"):
         assert torch.equal(r0[k], r1[k]), k                  # both ranks end with the same merged result
     assert "reduce" in r0["calls"]
 
@@ -79,6 +82,10 @@ def test_two_rank_sharded_equals_unsharded(tmp_path):
     torch.testing.assert_close(st["var_e"], r0["var_e"], rtol=1e-4, atol=1e-5)
     xq = x0 + 0.3 * torch.randn(b, d, generator=torch.Generator().manual_seed(5))
     torch.testing.assert_close(eng.posterior_mean(xq, torch.full((b,), 0.5)), r0["mean"], rtol=1e-5, atol=1e-6)
+    up = torch.randn(b, d, generator=torch.Generator().manual_seed(6))
+    gq, gt = eng.posterior_mean_backward(xq, torch.full((b,), 0.5), None, up)     # backward pass: shards sum to the whole
+    torch.testing.assert_close(r0["gq"], gq, rtol=1e-3, atol=1e-4 * gq.abs().max().item())     # fp32 sums, other order
+    torch.testing.assert_close(r0["gt"], gt, rtol=1e-3, atol=1e-4 * gt.abs().max().item())
     from oracle import posterior as orc
     import utils.stats as ustats
     torch.testing.assert_close(r0["sigma_reg_sq"], ustats._knn_sigma_reg_sq(eng, 5, 1.0), rtol=1e-5, atol=1e-7)
