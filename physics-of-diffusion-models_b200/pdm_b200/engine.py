@@ -335,10 +335,10 @@ class PosteriorEngine:
             self._sync_generator(dev)            # every rank regenerates rank 0's stream: 16 bytes instead of the noise
         x0_absmax = self.backend.row_absmax(x0f) if fused and self.precision() != "exact" else None
         if sliced:
-            # Each rank draws + prepares 1/world of a block's rows on a side stream and the operands are all-gathered
-            # there, one block ahead of the fused pass on the main stream: the replicated Philox work (ALU-bound,
-            # ~2 % of a single-GPU step but world times that share of a sharded one) shrinks by `world`, and the
-            # NVLink all-gather hides under the tensor-core kernel.
+            # Opt-in (EngineConfig.slice_noise): each rank draws + prepares 1/world of a block's rows on a side stream
+            # and the operands are all-gathered there, one block ahead of the fused pass on the main stream.  The
+            # replicated Philox work shrinks by `world`; whether the exchange hides depends on SMs being free beside
+            # the persistent tensor kernel (on 8 B200s it did not: see the note on the config field).
             t_per_block = max(self.world, t_per_block // self.world * self.world)
             self._sync_generator(dev)
             blocks = [(t0, min(n_t, t0 + t_per_block)) for t0 in range(0, n_t, t_per_block)]
