@@ -480,6 +480,15 @@ class PosteriorEngine:
         return self.backend.noised_rows_philox(seed, offset, step, x0f, temps.sqrt().contiguous(), x0_absmax=x0_absmax,
                                                want_x=not tensor, want_split=tensor)
 
+    def _prefetch_group(self):
+        """A communicator of its own for the operand exchange of the sliced path: on the engine's group it would queue
+        in front of the (tiny, latency-critical) merge all-gather of the block being computed."""
+        if getattr(self, "_pf_group", None) is None:
+            import torch.distributed as dist
+            ranks = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+            self._pf_group = dist.new_group(ranks=ranks)
+        return self._pf_group
+
     def _sliced_prepare(self, x0: Tensor, x0f: Tensor, temps: Tensor, dev: torch.device, fused: bool = False,
                         x0_absmax=None) -> dict:
         """Operands of the rows (t, b), t in ``temps``: this rank draws the noise of its ceil(nb/world) temperatures
@@ -513,7 +522,7 @@ class PosteriorEngine:
                 out[key] = None
                 continue
             full = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            dist.all_gather_into_tensor(full, t.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(full, t.contiguous(), group=self._prefetch_group())
             out[key] = full[:nb * b]
         return out
 
