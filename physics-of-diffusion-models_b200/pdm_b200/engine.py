@@ -183,9 +183,9 @@ class EngineConfig:
                                        # verified once per device) instead of torch.randn + pdm_prepare_rows
     slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows on a side
                                        # stream, one block ahead, and the operands are all-gathered.  Off: measured on
-                                       # 8 B200s the exchange does not hide under the persistent tensor kernel (no free
-                                       # SMs for NCCL) -- 114.8 ms per step against 109.5 ms with every rank regenerating
-                                       # all rows in-kernel (17 ms per step).  PDM_SLICE_NOISE=1 turns it on.
+                                       # 8 B200s the exchange does not hide under the persistent tensor kernel --
+                                       # 113.6 ms per step against 109.5 ms with every rank regenerating all rows
+                                       # in-kernel (17 ms per step).  PDM_SLICE_NOISE=1 turns it on.
 
     @staticmethod
     def from_env() -> "EngineConfig":
