@@ -511,3 +511,36 @@ def test_posterior_mean_delta_rows_shortcut(backend, precision):
         e32 = 0.5 * orc.pairwise_sqdist(x, data)
         p32 = torch.softmax(-(e32 - e32.min(1, keepdim=True).values) / temps[:, None], dim=1)
         arbitrated_close(res[True], p32 @ data, p64 @ data.double(), atol=2e-5, what=f"delta shortcut {name} {precision}")
+
+
+def test_random_shapes_against_oracle(backend):
+    """Seeded sweep over ragged shapes (every tile boundary: rows vs 128/256, columns vs 128/256, d vs 8/64), continuous
+    and 8-bit data, statistics + posterior mean against the fp64 oracle."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = syn.gen(71)
+    for case in range(16):
+        n = int(torch.randint(1, 900, (1,), generator=g))
+        d = int(torch.randint(64, 700, (1,), generator=g))
+        m = int(torch.randint(1, 400, (1,), generator=g))
+        pixels = case % 3 == 0
+        data = pixel_images(n, d, g) if pixels else torch.randn(n, d, generator=g) * 0.7
+        x = data[torch.randint(0, n, (m,), generator=g)] + 0.4 * torch.randn(m, d, generator=g)
+        t_rows = 10 ** (torch.rand(m, generator=g) * 5 - 2.5)
+        eng = PosteriorEngine(EmpiricalDataset(data, backend=backend), EngineConfig())
+        assert eng.precision() == ("f16x2" if pixels else "f16x3")
+        st = eng.stats(x, t_rows)
+        ref = oracle_rows(x, data, t_rows)
+        what = f"case {case} (n={n}, d={d}, m={m}, {'pixels' if pixels else 'continuous'})"
+        arbitrated_close(st["entropy"], ref["f32"]["entropy"], ref["f64"]["entropy"], atol=2e-5, floor=2 * ref["floor_e"],
+                         what=what + " entropy")
+        arbitrated_close(st["e_min"], ref["f32"]["e_min"], ref["f64"]["e_min"], atol=1e-5, floor=ref["floor_E"], what=what + " e_min")
+        fe2 = ref["floor_e"] * (1 + 2 * ref["f64"]["mean_e"].double())
+        arbitrated_close(st["var_e"], ref["f32"]["var_e"], ref["f64"]["var_e"], atol=2e-5, floor=fe2, what=what + " var_e")
+        agree = ref["f32"]["argmin"] == ref["f64"]["argmin"]
+        assert torch.equal(st["argmin"].cpu()[agree], ref["f64"]["argmin"][agree]), what
+        got = eng.posterior_mean(x, t_rows).cpu()
+        e64 = 0.5 * orc.pairwise_sqdist(x.double(), data.double())
+        p64 = torch.softmax(-(e64 - e64.min(1, keepdim=True).values) / t_rows.double()[:, None], dim=1)
+        e32 = 0.5 * orc.pairwise_sqdist(x, data)
+        p32 = torch.softmax(-(e32 - e32.min(1, keepdim=True).values) / t_rows[:, None], dim=1)
+        arbitrated_close(got, p32 @ data, p64 @ data.double(), atol=2e-5, what=what + " posterior mean")
