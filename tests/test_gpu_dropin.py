@@ -276,3 +276,22 @@ def test_sharded_sliced_noise_two_gpus(cuda_device):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_sharded_gpu.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_c_abi_without_python(cuda_device, tmp_path):
+    """The boundary is the C ABI, not Python: a stand-alone C++ host (tests/c/abi_smoke.cu: cudaMalloc'd buffers, plan,
+    fused pass on both precisions, merge, error codes) built with nvcc against include/pdm_b200.h + libpdm_b200.so."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available on this box")
+    libdir = os.path.join(root, "physics-of-diffusion-models_b200", "lib")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "abi_smoke.cu"), "-o", exe, "-L", libdir, "-lpdm_b200",
+                    "-Xlinker", "-rpath", "-Xlinker", libdir], check=True, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ABI SMOKE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
