@@ -234,6 +234,18 @@ int pdm_weighted_mean_exact_f32(const float* p, int64_t ldp, int64_t M, int64_t 
                                 float* out, int64_t ldo, int32_t accumulate, pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * One reverse-diffusion update of the ideal-denoiser sampler (diffusion/ddpm_sampling.py:94-110 with the
+ * DDPMPredictions algebra of diffusion/ddpm/ddpm.py:17-20 folded in):
+ *     out = c_x0 * x0_hat + c_xt * xt + c_noise * noise        (noise may be NULL: DDIM, or the last DDPM step)
+ * DDPM: c_x0 = sqrt(ab') beta / (1 - ab), c_xt = sqrt(alpha) (1 - ab') / (1 - ab), c_noise = sqrt((1 - ab')/(1 - ab) beta),
+ *       alpha = ab / ab', beta = 1 - alpha;
+ * DDIM: c_x0 = sqrt(ab') - sqrt(1 - ab') sqrt(ab) / sqrt(1 - ab),  c_xt = sqrt(1 - ab') / sqrt(1 - ab).
+ * out may alias xt.
+ * ------------------------------------------------------------------------------------------- */
+int pdm_sampler_step_f32(const float* x0_hat, const float* xt, const float* noise, float c_x0, float c_xt,
+                         float c_noise, float* out, int64_t n, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * k-NN selection on a dense distance tile (pdm_posterior_stats with energy_out, mult 2): the k smallest
  * entries of every row, ascending, ties by lower column index; vals (rows, k), idx (rows, k) int64 (-1 / +inf
  * when a row has fewer than k finite entries).  Replaces sklearn's NearestNeighbors.kneighbors on the CPU in

@@ -454,6 +454,37 @@ __global__ void __launch_bounds__(256) topk_smallest_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// one reverse-diffusion update: out = c_x0 * x0_hat + c_xt * xt (+ c_noise * noise), the DDPM / DDIM step of
+// diffusion/ddpm_sampling.py:94-110 with the x0 / eps algebra of diffusion/ddpm/ddpm.py:17-20 folded into three
+// host-computed coefficients.  HBM-bound: 12-16 B per element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sampler_step_kernel(const float* __restrict__ x0_hat, const float* __restrict__ xt,
+                                                           const float* __restrict__ noise, float c_x0, float c_xt, float c_noise,
+                                                           float* __restrict__ out, int64_t n, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        for (; i < n4; i += stride) {
+            const float4 a = ldg_f4(x0_hat + 4 * i), b = ldg_f4(xt + 4 * i);
+            float4 r = make_float4(fmaf(c_xt, b.x, c_x0 * a.x), fmaf(c_xt, b.y, c_x0 * a.y), fmaf(c_xt, b.z, c_x0 * a.z),
+                                   fmaf(c_xt, b.w, c_x0 * a.w));
+            if (noise) {
+                const float4 e = ldg_f4(noise + 4 * i);
+                r.x = fmaf(c_noise, e.x, r.x); r.y = fmaf(c_noise, e.y, r.y); r.z = fmaf(c_noise, e.z, r.z); r.w = fmaf(c_noise, e.w, r.w);
+            }
+            *reinterpret_cast<float4*>(out + 4 * i) = r;
+        }
+        i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // scalar tail
+    }
+    for (; i < n; i += stride) {
+        float r = fmaf(c_xt, __ldg(xt + i), c_x0 * __ldg(x0_hat + i));
+        if (noise) r = fmaf(c_noise, __ldg(noise + i), r);
+        out[i] = r;
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace pdm
@@ -588,6 +619,17 @@ extern "C" int pdm_topk_smallest_f32(const float* x, int64_t ldx, int64_t rows, 
     if (rows == 0) return PDM_OK;
     PDM_REQUIRE(rows < (1ll << 31), "pdm_topk_smallest_f32: too many rows for one launch");
     topk_smallest_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, ldx, n, (int)k, vals, idx);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_sampler_step_f32(const float* x0_hat, const float* xt, const float* noise, float c_x0, float c_xt,
+                                    float c_noise, float* out, int64_t n, pdm_stream_t stream) {
+    PDM_REQUIRE(x0_hat && xt && out && n >= 0, "pdm_sampler_step_f32: bad arguments");
+    if (n == 0) return PDM_OK;
+    const bool vec = aligned16(x0_hat) && aligned16(xt) && aligned16(out) && (!noise || aligned16(noise));
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 16);
+    sampler_step_kernel<<<grid, 256, 0, as_stream(stream)>>>(x0_hat, xt, noise, c_x0, c_xt, c_noise, out, n, vec ? 1 : 0);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

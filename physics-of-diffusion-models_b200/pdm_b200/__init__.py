@@ -5,6 +5,7 @@ to this package (``utils/``, ``diffusion/``); they call into ``PosteriorEngine``
 """
 from ._cabi import PdmError, LIB_PATH  # noqa: F401
 from .engine import EmpiricalDataset, PosteriorEngine, EngineConfig, STAT_KEYS, pow2_scale_for  # noqa: F401
+from .sampling import IdealSampler, step_coefficients  # noqa: F401
 
 __all__ = ["PdmError", "LIB_PATH", "EmpiricalDataset", "PosteriorEngine", "EngineConfig", "STAT_KEYS",
-           "pow2_scale_for"]
+           "pow2_scale_for", "IdealSampler", "step_coefficients"]

@@ -337,3 +337,16 @@ class CudaBackend:
                                              self._stream()), "pdm_topk_smallest_f32")
         self.launches += 1
         return vals, idx
+
+    def sampler_step(self, x0_hat: Tensor, xt: Tensor, noise: Optional[Tensor], c_x0: float, c_xt: float, c_noise: float,
+                     out: Optional[Tensor] = None) -> Tensor:
+        """out = c_x0 * x0_hat + c_xt * xt (+ c_noise * noise); ``out`` may be ``xt``."""
+        if out is None:
+            out = torch.empty_like(xt)
+        for t in (x0_hat, xt, out) + ((noise,) if noise is not None else ()):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise PdmError("sampler_step needs contiguous float32 tensors on the engine's device")
+        check(self.lib.pdm_sampler_step_f32(x0_hat.data_ptr(), xt.data_ptr(), _ptr(noise), float(c_x0), float(c_xt),
+                                            float(c_noise), out.data_ptr(), xt.numel(), self._stream()), "pdm_sampler_step_f32")
+        self.launches += 1
+        return out

@@ -1,0 +1,97 @@
+"""Reverse-diffusion sampling with the closed-form (ideal) denoiser, entirely on the engine.
+
+The reference samples with ``DDPMSampler`` (diffusion/ddpm_sampling.py:14-139) around ``DDPMTrue``: per step
+``get_predictions`` (diffusion/ddpm/ddpm.py:33-36), the x0 / eps algebra of ``DDPMPredictions`` (:17-20) and the DDPM
+or DDIM update (:94-110) -- a dozen elementwise torch kernels and one host sync (``prev_log_temp > -inf``) per step.
+That loop keeps working unchanged on top of the drop-in ``DDPMTrue``; this module is the fused form of the same
+recurrence: the schedule is read once on the host, every step is
+``PosteriorEngine.posterior_mean`` (VP query x_t / sqrt(ab) at temperature (1 - ab)/ab) followed by ONE kernel
+``pdm_sampler_step_f32`` whose three coefficients carry the whole update, and nothing of the loop depends on a device
+value.  The RNG stream is the reference's: ``torch.randn`` for the initial state and, for DDPM steps, one
+``torch.randn_like`` per step except the last.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, Optional
+
+import torch
+from torch import Tensor
+
+from .engine import EmpiricalDataset, PosteriorEngine, EngineConfig, default_backend
+
+
+def step_coefficients(alpha_bar: float, prev_alpha_bar: float, step_type: str) -> tuple[float, float, float]:
+    """(c_x0, c_xt, c_noise) of  x_prev = c_x0 x0_hat + c_xt x_t + c_noise eps'  for one step ab -> ab'.
+
+    DDPM (ddpm_sampling.py:99-107): alpha = ab/ab', beta = 1 - alpha,
+        c_x0 = sqrt(ab') beta / (1 - ab),  c_xt = sqrt(alpha)(1 - ab')/(1 - ab),  c_noise = sqrt((1 - ab')/(1 - ab) beta).
+    DDIM (:109-110) with eps = (x_t - sqrt(ab) x0_hat)/sqrt(1 - ab) (ddpm.py:19):
+        c_x0 = sqrt(ab') - sqrt(1 - ab') sqrt(ab)/sqrt(1 - ab),  c_xt = sqrt(1 - ab')/sqrt(1 - ab),  c_noise = 0."""
+    ab, abp = float(alpha_bar), float(prev_alpha_bar)
+    if step_type == "ddpm":
+        alpha = ab / abp
+        beta = 1.0 - alpha
+        return (math.sqrt(abp) * beta / (1.0 - ab), math.sqrt(alpha) * (1.0 - abp) / (1.0 - ab),
+                math.sqrt(max((1.0 - abp) / (1.0 - ab) * beta, 0.0)))
+    if step_type == "ddim":
+        r = math.sqrt(max(1.0 - abp, 0.0)) / math.sqrt(1.0 - ab)
+        return (math.sqrt(abp) - r * math.sqrt(ab), r, 0.0)
+    raise ValueError(f"unknown step type: {step_type}")
+
+
+class IdealSampler:
+    """Sampler for the empirical (ideal) denoiser of a training set resident on the GPU.
+
+    ``log_temp``: ascending log-temperatures of the schedule (what ``DDPMSampler.log_temp`` holds); sampling walks it
+    from the last entry down and finishes at the clean state (log_temp = -inf, alpha_bar = 1)."""
+
+    def __init__(self, train_data: Tensor, log_temp: Tensor | Iterable[float], step_type: str = "ddim",
+                 engine: Optional[PosteriorEngine] = None, config: Optional[EngineConfig] = None):
+        if step_type not in ("ddpm", "ddim"):
+            raise ValueError(f"unknown step type: {step_type}")
+        self.engine = engine if engine is not None else PosteriorEngine(
+            EmpiricalDataset(train_data, backend=default_backend()), config)
+        self.backend = self.engine.backend
+        self.step_type = step_type
+        lt = torch.as_tensor(log_temp, dtype=torch.float64).reshape(-1).cpu()
+        self.log_temp = lt.tolist()                                   # read once: the loop never syncs on a device value
+        self.alpha_bar = torch.sigmoid(-lt).tolist()                  # alpha_bar_from_log_temp, scheduler.py:24-25
+        self.obj_size = tuple(train_data.shape[1:])
+
+    @torch.no_grad()
+    def batch_sample(self, batch_size: int, track_states: bool = False) -> dict[str, Tensor]:
+        dev = self.backend.device
+        d = self.engine.ds.d
+        xt = torch.randn(batch_size, *self.obj_size, device=dev)      # ddpm_sampling.py:114
+        states = [] if track_states else None
+        flat = xt.view(batch_size, d)
+        ones = torch.ones(batch_size, dtype=torch.float32, device=dev)
+        for idx in range(len(self.alpha_bar) - 1, -1, -1):
+            ab = self.alpha_bar[idx]
+            abp = self.alpha_bar[idx - 1] if idx > 0 else 1.0         # clean_log_temp = -inf -> alpha_bar = 1
+            last = idx == 0
+            x0_hat = self.engine.posterior_mean(flat, ones * ((1.0 - ab) / ab), post=ones * (1.0 / math.sqrt(ab)))
+            c_x0, c_xt, c_noise = step_coefficients(ab, abp, self.step_type)
+            noise = None
+            if self.step_type == "ddpm" and not last:                 # no draw on the last step (:107)
+                noise = torch.randn_like(xt).view(batch_size, d)
+            self.backend.sampler_step(x0_hat, flat, noise, c_x0, c_xt, c_noise if noise is not None else 0.0, out=flat)
+            if states is not None:
+                states.append(xt.clone())
+        res = {"x": xt}
+        if states is not None:
+            res["states"] = torch.stack(states[::-1])
+        return res
+
+    @torch.no_grad()
+    def sample(self, n_samples: int, batch_size: int, track_states: bool = False) -> dict[str, Tensor]:
+        """``n_samples`` samples in batches of ``batch_size`` (ddpm_sampling.py:131-139); results stay on the device."""
+        parts: dict[str, list[Tensor]] = {}
+        done = 0
+        while done < n_samples:
+            b = min(batch_size, n_samples - done)
+            for k, v in self.batch_sample(b, track_states).items():
+                parts.setdefault(k, []).append(v)
+            done += b
+        return {k: torch.cat(v, dim=1 if k == "states" else 0) for k, v in parts.items()}

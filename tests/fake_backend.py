@@ -160,3 +160,12 @@ class FakeBackend:
         a = (p * s).sum(1) if a_in is None else a_in
         w = p * (s - a[:, None])
         return w, torch.stack([a, (w * e).sum(1)], dim=1)
+
+    def sampler_step(self, x0_hat, xt, noise, c_x0, c_xt, c_noise, out=None):
+        r = c_x0 * x0_hat + c_xt * xt
+        if noise is not None:
+            r = r + c_noise * noise
+        if out is None:
+            return r
+        out.copy_(r)
+        return out

@@ -295,3 +295,34 @@ def test_c_abi_without_python(cuda_device, tmp_path):
                     "-Xlinker", "-rpath", "-Xlinker", libdir], check=True, capture_output=True, text=True, timeout=300)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ABI SMOKE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("step_type", ["ddim", "ddpm"])
+def test_ideal_sampler_on_gpu(cuda_device, step_type):
+    """pdm_b200.IdealSampler (posterior mean + one fused update kernel per step, no host syncs on device values) against
+    the reference's DDPMSampler recurrence run through the drop-in DDPMTrue, same CUDA RNG stream."""
+    import diffusion.scheduler.scheduler as sched
+    from diffusion import DDPMTrue
+    from diffusion.scheduler import LinearBetaScheduler
+    from pdm_b200 import IdealSampler
+    from test_host_logic_cpu import _reference_style_sampling
+    sched._DENOISER_ENGINES.clear()
+    gen = torch.Generator().manual_seed(3)
+    px = torch.randint(0, 256, (800, 3, 16, 16), generator=gen, dtype=torch.uint8)
+    data = ((px.float() / 255 - 0.5) / 0.5).to(cuda_device)           # 8-bit images: the two-product path
+    sch = LinearBetaScheduler(1e-4, 2.478e4)
+    log_temp = sch.log_temp_from_tau(torch.linspace(0, 1, 26, device=cuda_device)[1:])
+    sampler = IdealSampler(data, log_temp, step_type=step_type)
+    assert sampler.engine.precision() == "f16x2"
+    torch.manual_seed(21)
+    got = sampler.batch_sample(64)["x"]
+    model = DDPMTrue(sch, "x0", data)
+    torch.manual_seed(21)
+    with torch.no_grad():
+        want = _reference_style_sampling(model, sch, log_temp, 64, (3, 16, 16), step_type, torch.float32, device=cuda_device)
+    assert got.shape == want.shape and got.device == want.device
+    err = (got - want).abs().max().item()
+    assert err <= 2e-3, err
+    # the trajectories end on training images (the posterior is a delta at the lowest noise level)
+    d2 = torch.cdist(got.reshape(64, -1), data.reshape(800, -1)).min(1).values
+    assert d2.max().item() < 0.5

@@ -249,3 +249,59 @@ def test_lattice_candidates_and_detection():
     assert detect_lattice_scale(p, y, absmax=1.0) == 510.0 and p.asked[-3:] == [2040.0, 1020.0, 510.0]
     assert detect_lattice_scale(Probe(set()), y, absmax=1.0) == 0.0
     assert LATTICE_RATIO_MAX == 2.0 ** -44
+
+
+def _reference_style_sampling(model, sch, log_temp, batch, obj_size, step_type, dtype, device="cpu"):
+    """The reference's DDPMSampler.batch_sample / step recurrence (diffusion/ddpm_sampling.py:92-126) written out with
+    torch ops, around any DDPM-like ``model`` -- the yardstick for the fused sampler."""
+    from diffusion import DDPMPredictions
+    from diffusion.scheduler import cast_log_temp, alpha_bar_from_log_temp
+    xt = torch.randn(batch, *obj_size, device=device).to(dtype)
+    clean = torch.full((1,), -torch.inf, device=device)
+    for idx in range(len(log_temp) - 1, -1, -1):
+        lt = log_temp[idx].view(1)
+        prev = log_temp[idx - 1].view(1) if idx > 0 else clean
+        tau = sch.tau_from_log_temp(lt).clip(0, 1)
+        ab_pred = cast_log_temp(sch.alpha_bar_from_tau(tau), xt)
+        pred = DDPMPredictions(model(xt, tau).to(dtype), xt, ab_pred.to(dtype), "x0")
+        ab = cast_log_temp(alpha_bar_from_log_temp(lt), xt).to(dtype)
+        abp = cast_log_temp(alpha_bar_from_log_temp(prev), xt).to(dtype)
+        if step_type == "ddpm":
+            alpha = ab / abp
+            beta = 1 - alpha
+            noise = torch.randn_like(xt.float()).to(dtype) if idx > 0 else 0
+            xt = pred.x0 * (abp.sqrt() * beta) / (1 - ab) + xt * (alpha.sqrt() * (1 - abp)) / (1 - ab) \
+                + noise * ((1 - abp) / (1 - ab) * beta).sqrt()
+        else:
+            xt = abp.sqrt() * pred.x0 + (1 - abp).sqrt() * pred.eps
+    return xt
+
+
+@pytest.mark.parametrize("step_type", ["ddim", "ddpm"])
+def test_ideal_sampler_matches_reference_recurrence(fake, step_type):
+    """Fused sampler (three coefficients per step, one update kernel) against the reference's step algebra in fp64
+    on the same RNG draws."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig, IdealSampler, step_coefficients
+    from diffusion.scheduler import LinearBetaScheduler
+    g = load_golden("denoiser.npz")
+    data = g["data"][:96]
+    sch = LinearBetaScheduler(float(g["min_temp"]), float(g["max_temp"]))
+    log_temp = sch.log_temp_from_tau(torch.linspace(0, 1, 13, dtype=torch.float64)[1:]).float()
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=fake), EngineConfig(precision="exact"))
+    sampler = IdealSampler(data, log_temp, step_type=step_type, engine=eng)
+    torch.manual_seed(11)
+    got = sampler.batch_sample(7)["x"]
+
+    class Oracle64(torch.nn.Module):
+        def forward(self, xt, tau):
+            return orc.posterior_mean_x0(xt, sch.alpha_bar_from_tau(tau.double()), data, dtype=torch.float64)
+
+    torch.manual_seed(11)
+    want = _reference_style_sampling(Oracle64(), sch, log_temp.double(), 7, tuple(data.shape[1:]), step_type, torch.float64)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got.double(), want, rtol=2e-3, atol=2e-3)
+    # the last step lands on the posterior mean at the lowest noise level; coefficients at the clean end
+    c = step_coefficients(0.3, 1.0, "ddpm")
+    assert abs(c[0] - 1.0) < 1e-12 and c[1] == 0.0 and c[2] == 0.0
+    out = sampler.sample(10, 4, track_states=True)
+    assert out["x"].shape == (10, *data.shape[1:]) and out["states"].shape == (12, 10, *data.shape[1:])
