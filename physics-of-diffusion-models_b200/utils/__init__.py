@@ -29,6 +29,7 @@ from .stats import (  # noqa: F401
     compute_metric_stats as compute_metric_stats,
     compute_metric_stats_batch as compute_metric_stats_batch,
     compute_model_metric_stats as compute_model_metric_stats,
+    compute_thermo_stats as compute_thermo_stats,       # extension: legacy notebook schema (log_Z, U, full_U, var_H)
 )
 from .metric_utils import (  # noqa: F401
     compute_metric_scalar as compute_metric_scalar,

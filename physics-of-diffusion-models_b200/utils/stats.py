@@ -262,6 +262,34 @@ def compute_stats(dataloader: DataLoader, data_generator, temp: Tensor, n_sample
     return stats
 
 
+def compute_thermo_stats(dataloader: DataLoader, data_generator, temp: Tensor, n_samples: int) -> dict[str, Tensor]:
+    """Extension (not in the reference's current API): every thermodynamic curve of the same fused pass, averaged over
+    the queries, in the LEGACY schema the reference's notebooks still read (analyze_stats.ipynb:73-80,
+    compare_datasets.ipynb:72-73: ``temp, log_Z, U, full_U, var_H`` with F = -T log_Z, S = log_Z + U/T,
+    C = var_H / T^2) next to the current ``entropy`` key:
+        log_Z  = log (1/N) sum_j exp(-(E_j - E_min)/T)     (min-shifted, formulas.md:62-66)
+        U      = <E - E_min>,   full_U = <E>,   var_H = Var(E),   heat_capacity = var_H / T^2,
+        free_energy = -T log_Z + E_min (unshifted),   entropy = log_Z + U/T."""
+    eng = _engine_for(dataloader)
+    dev = eng.backend.device
+    t = temp.to(device=dev, dtype=torch.float32).reshape(-1, 1)
+    acc: dict[str, list[Tensor]] = defaultdict(list)
+    remaining = n_samples
+    while remaining > 0:
+        x0_traj = next(data_generator)[0]
+        st = eng.noised_stats(x0_traj, temp)
+        log_z = st["log_l"] - math.log(eng.ds.n_total)
+        u = st["mean_e"] * t
+        cur = {"entropy": st["entropy"], "log_Z": log_z, "U": u, "full_U": u + st["e_min"], "var_H": st["var_e"] * t * t,
+               "heat_capacity": st["var_e"], "free_energy": -t * log_z + st["e_min"]}
+        for k, v in cur.items():
+            acc[k].append(v)
+        remaining -= len(x0_traj)
+    out = {k: torch.cat(v, dim=1).mean(dim=1).cpu() for k, v in acc.items()}
+    out["temp"] = temp
+    return out
+
+
 def extrapolate_entropy(temp: Tensor, entropy: Tensor, min_temp: float) -> tuple[Tensor, Tensor]:
     """Log-linear continuation of the entropy curve below its steepest segment (utils/stats.py:314-322).
     Tiny CPU post-processing on (n_T,) vectors."""

@@ -305,3 +305,30 @@ def test_ideal_sampler_matches_reference_recurrence(fake, step_type):
     assert abs(c[0] - 1.0) < 1e-12 and c[1] == 0.0 and c[2] == 0.0
     out = sampler.sample(10, 4, track_states=True)
     assert out["x"].shape == (10, *data.shape[1:]) and out["states"].shape == (12, 10, *data.shape[1:])
+
+
+def test_thermo_stats_legacy_schema(fake):
+    """compute_thermo_stats: the legacy notebook schema (analyze_stats.ipynb:73-80) out of the same pass --
+    S = log_Z + U/T reproduces the entropy of compute_stats, C = var_H/T^2, F = -T log_Z + E_min."""
+    import utils
+    from torch.utils.data import DataLoader, TensorDataset
+    g = load_golden("stats_gmm.npz")
+    loader = DataLoader(TensorDataset(g["data"]), batch_size=int(g["dl_bs"]), shuffle=False)
+
+    def batches():
+        while True:
+            yield (g["x0"],)
+
+    import utils.stats as ustats
+    ustats._engine_for(loader)                      # upload once (creating the loader's iterator consumes the global RNG)
+    torch.manual_seed(3)
+    th = utils.compute_thermo_stats(loader, batches(), g["temp"], n_samples=len(g["x0"]))
+    torch.manual_seed(3)
+    ent = utils.compute_stats(loader, batches(), g["temp"], n_samples=len(g["x0"]))["entropy"]
+    assert set(th) >= {"temp", "entropy", "log_Z", "U", "full_U", "var_H", "heat_capacity", "free_energy"}
+    torch.testing.assert_close(th["entropy"], ent, rtol=1e-5, atol=1e-6)
+    # the identities hold per query; after averaging over queries they hold for the averages of the same quantities
+    torch.testing.assert_close(th["log_Z"] + th["U"] / g["temp"], th["entropy"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(th["var_H"] / g["temp"] ** 2, th["heat_capacity"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(th["free_energy"], -g["temp"] * th["log_Z"] + (th["full_U"] - th["U"]), rtol=1e-4, atol=1e-4)
+    assert (th["var_H"] >= 0).all() and (th["full_U"] >= th["U"] - 1e-6).all()
