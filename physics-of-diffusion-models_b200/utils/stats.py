@@ -23,7 +23,6 @@ import weakref
 from collections import defaultdict
 from typing import Generator, Optional
 
-import numpy as np
 import torch
 from torch import Tensor
 from torch.utils.data import DataLoader

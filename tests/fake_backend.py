@@ -8,7 +8,6 @@ with torch on the CPU.  The product never imports it.
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 from torch import Tensor

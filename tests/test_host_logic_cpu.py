@@ -1,6 +1,5 @@
 """Host logic of the engine and of the reference-facing drop-in modules, on the CPU with the test double of the
 backend (tests/fake_backend.py): schedule blocking, RNG order, dataset caching, record merge, posterior mean."""
-import math
 
 import pytest
 import torch

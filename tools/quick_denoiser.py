@@ -1,5 +1,5 @@
 """Device-time probe of the posterior-mean (ideal denoiser) path at CIFAR-10 shape (dev tool)."""
-import os, sys, time
+import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "physics-of-diffusion-models_b200"))
