@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PDM_ABI_VERSION 1
+#define PDM_ABI_VERSION 2
 
 #define PDM_OK               0
 #define PDM_ERR_INVALID_ARG (-1)
@@ -178,7 +178,8 @@ typedef struct pdm_stats_args {
     const float* inv_temp;      /* (M) 1/T                                                         */
     const float* y_aux;         /* (N) per-point scalar s_j (utils/stats.py:101) or NULL           */
     /* outputs */
-    float*   partials;          /* (M, records_per_row, PDM_PART_STRIDE)                           */
+    float*   partials;          /* (records_per_row, M, PDM_PART_STRIDE): record-major, so that both the
+                                   kernel's stores and the merge's loads are coalesced over rows   */
     float*   energy_out;        /* optional (M, lde): energy_mult * E  (2.0 gives the squared
                                    distance of utils/distance.py:21, 1.0 the energy)               */
     int64_t  lde;
@@ -192,21 +193,22 @@ int pdm_posterior_stats(const pdm_stats_args* args, pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Merge of partial records (the only exchange step of the sharded path).
- * parts is indexed [outer][row][inner][PDM_PART_STRIDE] with strides outer_stride / row_stride /
- * PDM_PART_STRIDE floats: `inner` = the N splits of one launch, `outer` = dataset shards (GPUs)
- * after an all-gather.  Writes out[PDM_OUT_ROWS][M] and argmin[M] (int64 global dataset index,
- * first index on ties like torch.min).  n_total = total dataset size N for the entropy's log N.
+ * Record (outer o, row r, inner i) sits at parts + o*outer_stride + i*inner_stride + r*row_stride floats:
+ * `inner` = the records one launch emits per row (pdm_posterior_stats writes them record-major:
+ * inner_stride = M*PDM_PART_STRIDE, row_stride = PDM_PART_STRIDE), `outer` = dataset shards (GPUs) after an
+ * all-gather.  Writes out[PDM_OUT_ROWS][M] and argmin[M] (int64 global dataset index, first index on ties
+ * like torch.min).  n_total = total dataset size N for the entropy's log N.
  * ------------------------------------------------------------------------------------------- */
 int pdm_merge_partials(const float* parts, int64_t M, int64_t n_outer, int64_t outer_stride,
-                       int64_t n_inner, int64_t row_stride, const float* inv_temp, int64_t n_total,
-                       float* out, int64_t* argmin, pdm_stream_t stream);
+                       int64_t n_inner, int64_t inner_stride, int64_t row_stride, const float* inv_temp,
+                       int64_t n_total, float* out, int64_t* argmin, pdm_stream_t stream);
 
 /* Same combination without the finalisation: out_records (M, PDM_PART_STRIDE) holds ONE merged record
  * per row.  A rank reduces its own splits with this before the all-gather, so that 32 bytes per query
  * row cross NVLink instead of 32 bytes per (row, split). */
 int pdm_reduce_partials(const float* parts, int64_t M, int64_t n_outer, int64_t outer_stride,
-                        int64_t n_inner, int64_t row_stride, const float* inv_temp, float* out_records,
-                        pdm_stream_t stream);
+                        int64_t n_inner, int64_t inner_stride, int64_t row_stride, const float* inv_temp,
+                        float* out_records, pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K8 posterior mean  x0_hat_b = sum_j p_bj y_j,  p_bj = exp(-(E_bj - m_b)/T_b)/l_b.

@@ -180,9 +180,19 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
     __shared__ float red_f[32];
     float amax = 0.f;
     const int64_t total = rows * d;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / d, c = i - r * d;
-        amax = fmaxf(amax, fabsf(__ldg(x + r * ld + c)));
+    if (ld == d && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {          // contiguous: one flat, 128-bit vectorised sweep
+        const int64_t n4 = total >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+            const float4 v = ldg_f4(x + 4 * i);
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+        for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+            amax = fmaxf(amax, fabsf(__ldg(x + i)));
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / d, c = i - r * d;
+            amax = fmaxf(amax, fabsf(__ldg(x + r * ld + c)));
+        }
     }
     amax = block_reduce(amax, OpMaxF(), 0.f, red_f);
     if (threadIdx.x == 0) atomicMax(out_bits, __float_as_uint(amax));

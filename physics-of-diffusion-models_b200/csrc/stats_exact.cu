@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256, 2) exact_stats_kernel(ExactParams p) {
         o.idx = __shfl_xor_sync(0xffffffffu, st.idx, 1);
         if (par == 0 && grow < p.M) {
             state_merge(st, o, inv_t);
-            state_store(st, p.partials + (grow * p.n_splits + split) * PDM_PART_STRIDE);
+            state_store(st, p.partials + ((int64_t)split * p.M + grow) * PDM_PART_STRIDE);   // record-major
         }
     }
 }

@@ -478,7 +478,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 }
                 // one partial record per (row, split, column half)
                 if (EPI == EPI_STATS && p.partials && row_ok)
-                    packed_store(st, p.partials + (grow * (2 * p.n_splits) + 2 * sp + half) * PDM_PART_STRIDE);
+                    packed_store(st, p.partials + ((int64_t)(2 * sp + half) * p.M + grow) * PDM_PART_STRIDE);   // record-major
             }
 #ifdef PDM_STALL_STATS
             if (warp == kEpiWarp0 && lane == 0) { g_stall[blockIdx.x][3] = st_tfull; g_stall[blockIdx.x][5] = st_stats; }

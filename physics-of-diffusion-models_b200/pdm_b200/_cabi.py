@@ -57,8 +57,8 @@ SIGNATURES = {
     "pdm_column_moments_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P]),
     "pdm_posterior_stats_plan": (C.c_int, [C.POINTER(StatsArgs), C.c_int, C.POINTER(C.c_int64)]),
     "pdm_posterior_stats": (C.c_int, [C.POINTER(StatsArgs), _P]),
-    "pdm_merge_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
-    "pdm_reduce_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "pdm_merge_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
+    "pdm_reduce_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "pdm_weights_from_energy": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "pdm_split_gemm_f16x3": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P]),
     "pdm_sampler_step_f32": (C.c_int, [_P, _P, _P, _F, _F, _F, _P, _I64, _P]),
@@ -84,7 +84,7 @@ def load() -> C.CDLL:
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
-            if lib.pdm_abi_version() != 1:
+            if lib.pdm_abi_version() != 2:
                 raise PdmError("libpdm_b200.so ABI version mismatch; rebuild the library")
             _lib = lib
     return _lib

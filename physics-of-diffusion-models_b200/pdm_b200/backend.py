@@ -232,7 +232,7 @@ class CudaBackend:
               "pdm_posterior_stats_plan")
         partials = None
         if want_partials:
-            partials = torch.empty(M, a.records_per_row, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
+            partials = torch.empty(a.records_per_row, M, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
             a.partials = partials.data_ptr()
         if energy_out is not None:
             a.energy_out, a.lde, a.energy_mult = energy_out.data_ptr(), _ld(energy_out), float(energy_mult)
@@ -249,26 +249,29 @@ class CudaBackend:
         return partials
 
     def merge(self, parts: Tensor, inv_temp: Tensor, n_total: int):
-        """parts: (M, S, 8) or (G, M, S, 8) contiguous."""
-        if parts.dim() == 3:
-            parts = parts.unsqueeze(0)
+        """parts: (S, M, 8) record-major, as posterior_stats emits them, or (G, M, S, 8): G all-gathered shards of
+        row-major records (the (M, 1, 8) outputs of ``reduce``)."""
         parts = parts.contiguous()
-        g, m, s, _ = parts.shape
+        if parts.dim() == 3:
+            s, m, _ = parts.shape
+            g, outer, inner, row = 1, 0, parts.stride(0), parts.stride(1)
+        else:
+            g, m, s, _ = parts.shape
+            outer, inner, row = parts.stride(0), parts.stride(2), parts.stride(1)
         out = torch.empty(_cabi.OUT_ROWS, m, dtype=torch.float32, device=self.device)
         argmin = torch.empty(m, dtype=torch.int64, device=self.device)
-        check(self.lib.pdm_merge_partials(parts.data_ptr(), m, g, _ld(parts), s, parts.stride(1),
-                                          inv_temp.data_ptr(), n_total, out.data_ptr(), argmin.data_ptr(),
-                                          self._stream()), "pdm_merge_partials")
+        check(self.lib.pdm_merge_partials(parts.data_ptr(), m, g, outer, s, inner, row, inv_temp.data_ptr(), n_total,
+                                          out.data_ptr(), argmin.data_ptr(), self._stream()), "pdm_merge_partials")
         self.launches += 1
         return out, argmin
 
     def reduce(self, parts: Tensor, inv_temp: Tensor) -> Tensor:
-        """(M, S, 8) -> (M, 1, 8): one merged, not yet finalised, record per row."""
+        """(S, M, 8) record-major -> (M, 1, 8): one merged, not yet finalised, record per row."""
         parts = parts.contiguous()
-        m, s, _ = parts.shape
+        s, m, _ = parts.shape
         out = torch.empty(m, 1, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_reduce_partials(parts.data_ptr(), m, 1, 0, s, _ld(parts), inv_temp.data_ptr(),
-                                           out.data_ptr(), self._stream()), "pdm_reduce_partials")
+        check(self.lib.pdm_reduce_partials(parts.data_ptr(), m, 1, 0, s, parts.stride(0), parts.stride(1),
+                                           inv_temp.data_ptr(), out.data_ptr(), self._stream()), "pdm_reduce_partials")
         self.launches += 1
         return out
 

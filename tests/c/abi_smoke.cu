@@ -89,7 +89,7 @@ int main() {
         CK(cudaMalloc(&dparts, nfloats * 4));
         a.partials = dparts;
         PK(pdm_posterior_stats(&a, st));
-        PK(pdm_merge_partials(dparts, M, 1, 0, a.records_per_row, (int64_t)a.records_per_row * PDM_PART_STRIDE, dit, N, dout, dargmin, st));
+        PK(pdm_merge_partials(dparts, M, 1, 0, a.records_per_row, M * PDM_PART_STRIDE, PDM_PART_STRIDE, dit, N, dout, dargmin, st));
         std::vector<float> out(PDM_OUT_ROWS * M);
         std::vector<int64_t> arg(M);
         CK(cudaMemcpyAsync(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost, st));
