@@ -6,32 +6,50 @@
 
 namespace pdm {
 
+// Records are stored record-major, so the threads of a warp read consecutive 32-byte records.  A thread's loads do
+// not depend on its exp-heavy merge chain: kChunk records are fetched at a time and the next chunk is already in
+// flight while the current one is merged (same merge order as a plain loop -> same bits).
+constexpr int kChunk = 4;
+
+struct RecordCursor {          // walks (outer, inner) without a 64-bit division per record
+    const float* base;
+    int64_t outer_stride, inner_stride, n_inner, i;
+    __device__ __forceinline__ const float4* next() {
+        const float4* p = reinterpret_cast<const float4*>(base + i * inner_stride);
+        if (++i == n_inner) { i = 0; base += outer_stride; }
+        return p;
+    }
+};
+
 __device__ __forceinline__ void gather_row(const float* __restrict__ parts, int64_t row, int64_t n_outer, int64_t outer_stride,
                                            int64_t n_inner, int64_t row_stride, int64_t inner_stride, float it, RowState& acc) {
     state_init(acc);
-    // the record after the one being merged is already in flight (a thread's loads do not depend on its exp-heavy
-    // merge chain); records are stored record-major, so the threads of a warp read consecutive 32-byte records
     const int64_t total = n_outer * n_inner;
-    if (total == 0) return;
-    float4 n0 = __ldg(reinterpret_cast<const float4*>(parts + row * row_stride));
-    float4 n1 = __ldg(reinterpret_cast<const float4*>(parts + row * row_stride) + 1);
-    for (int64_t t = 0; t < total; ++t) {
-        const float4 c0 = n0, c1 = n1;
-        if (t + 1 < total) {
-            const int64_t o = (t + 1) / n_inner, i = (t + 1) - o * n_inner;
-            const float4* nx = reinterpret_cast<const float4*>(parts + o * outer_stride + row * row_stride + i * inner_stride);
-            n0 = __ldg(nx);
-            n1 = __ldg(nx + 1);
+    RecordCursor cur{parts + row * row_stride, outer_stride, inner_stride, n_inner, 0};
+    float4 nx0[kChunk], nx1[kChunk];
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+        if (k < total) { const float4* p = cur.next(); nx0[k] = __ldg(p); nx1[k] = __ldg(p + 1); }
+    for (int64_t t0 = 0; t0 < total; t0 += kChunk) {
+        float4 c0[kChunk], c1[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) { c0[k] = nx0[k]; c1[k] = nx1[k]; }
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+            if (t0 + kChunk + k < total) { const float4* p = cur.next(); nx0[k] = __ldg(p); nx1[k] = __ldg(p + 1); }
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) {
+            if (t0 + k >= total) break;
+            RowState s;
+            s.m = c0[k].x; s.l = c0[k].y; s.a1 = c0[k].z; s.a2 = c0[k].w; s.aux = c1[k].x;
+            s.idx = ((long long)__float_as_int(c1[k].z) << 32) | (long long)(unsigned)__float_as_int(c1[k].y);
+            state_merge(acc, s, it);
         }
-        RowState s;
-        s.m = c0.x; s.l = c0.y; s.a1 = c0.z; s.a2 = c0.w; s.aux = c1.x;
-        s.idx = ((long long)__float_as_int(c1.z) << 32) | (long long)(unsigned)__float_as_int(c1.y);
-        state_merge(acc, s, it);
     }
 }
 
 // Combine records without finalising: one record per row (what a rank sends to its peers).
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ parts, int64_t M, int64_t n_outer,
+__global__ void __launch_bounds__(256, 3) reduce_partials_kernel(const float* __restrict__ parts, int64_t M, int64_t n_outer,
                                                               int64_t outer_stride, int64_t n_inner, int64_t row_stride,
                                                               int64_t inner_stride, const float* __restrict__ inv_temp,
                                                               float* __restrict__ out) {
@@ -42,7 +60,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     state_store(acc, out + row * PDM_PART_STRIDE);
 }
 
-__global__ void __launch_bounds__(256) merge_partials_kernel(const float* __restrict__ parts, int64_t M, int64_t n_outer,
+__global__ void __launch_bounds__(256, 3) merge_partials_kernel(const float* __restrict__ parts, int64_t M, int64_t n_outer,
                                                              int64_t outer_stride, int64_t n_inner, int64_t row_stride,
                                                              int64_t inner_stride, const float* __restrict__ inv_temp, float log_n,
                                                              float* __restrict__ out, int64_t* __restrict__ argmin) {
