@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PDM_ABI_VERSION 2
+#define PDM_ABI_VERSION 3
 
 #define PDM_OK               0
 #define PDM_ERR_INVALID_ARG (-1)
@@ -184,6 +184,11 @@ typedef struct pdm_stats_args {
                                    distance of utils/distance.py:21, 1.0 the energy)               */
     int64_t  lde;
     float    energy_mult;
+    /* screened launches (tensor path only): process only the listed row tiles of 128*cta_group rows
+       (tile t = rows [t*128*cta_group, (t+1)*128*cta_group)); records of other rows are left untouched.
+       NULL = every row.  pdm_posterior_stats_plan sizes the schedule for n_row_tiles tiles. */
+    const int32_t* row_tiles;   /* (n_row_tiles) device, or NULL                                   */
+    int64_t  n_row_tiles;
 } pdm_stats_args;
 
 /* Fills args->n_splits / m_group / cta_group when they are 0, sets args->records_per_row and reports the
@@ -209,6 +214,42 @@ int pdm_merge_partials(const float* parts, int64_t M, int64_t n_outer, int64_t o
 int pdm_reduce_partials(const float* parts, int64_t M, int64_t n_outer, int64_t outer_stride,
                         int64_t n_inner, int64_t inner_stride, int64_t row_stride, const float* inv_temp,
                         float* out_records, pdm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Certified delta posteriors (adaptive precision; an optimisation the reference has no counterpart of:
+ * it evaluates utils/stats.py:80-90, 282-289 for every pair at every temperature).
+ * In the low-noise part of a schedule the posterior of a query is a delta on its nearest training point to
+ * fp32 resolution.  One tensor-core product (PDM_PREC_F16X1) with a rigorous error bound is enough to PROVE
+ * that for a row; proven rows take the closed form (E_min exact, l = 1, <e> = <e^2> = 0, entropy = -log N)
+ * and only the row tiles holding an unproven row go through the full-precision pass (row_tiles above).
+ *
+ * Step 1, pdm_screen_temperatures: the screening pass runs at a fictitious temperature T' per row,
+ *     1/T' = e_star / (g*T + 2*delta),   delta = kappa * 2^-10 * ||x|| * max_j ||y_j||
+ * (delta bounds |E1 - E| of the one-product energies: each operand is rounded to 11 significant bits).
+ * Step 2, pdm_screen_certify on the merged output of that pass: a row is certified when
+ *     l' < 1.25   and   <e>' l' < 0.9 * e_star * exp(-e_star).
+ * Every other point j then has (E1_j - E1_min)/T' > e_star  (e exp(-e) decreases for e > 1, and a point with
+ * e < 1 would push l' above 1.36), i.e. a true gap E_j - E_min > g*T: its weight is below exp(-g), all of them
+ * together below N exp(-g).  With g = 17 + log N that is under half an fp32 ulp of l = 1.  flags[r] = 1 for
+ * certified rows; tile_list / n_tiles_out[0] = the ascending list of row tiles (rows_per_tile rows each)
+ * that hold at least one uncertified row.
+ * Step 3, pdm_screen_finalize, after the full pass over those tiles has been merged into out / argmin:
+ * certified rows are overwritten with the closed form; E_min is recomputed for the arg-min of the
+ * screening pass from the split operands (fp64 accumulation, then the fused pass's fp32 formula).
+ * Row-sharded datasets: the screening records are merged across shards like any others, so every shard holds
+ * the same flags; the shard that owns a certified row's arg-min writes E_min and the aux value, the others
+ * write +inf / -inf, and the caller combines the E_min rows with MIN and the aux rows with MAX.
+ * ------------------------------------------------------------------------------------------- */
+int pdm_screen_temperatures(const float* q_norm, const float* inv_temp, int64_t M, const float* y_norm_max,
+                            float g, float e_star, float kappa, float* inv_temp_screen, pdm_stream_t stream);
+int pdm_screen_certify(const float* screen_out, int64_t M, float e_star, int32_t rows_per_tile,
+                       uint8_t* flags, int32_t* tile_list, int32_t* n_tiles_out, pdm_stream_t stream);
+int pdm_screen_finalize(const uint8_t* flags, const int64_t* screen_argmin, int64_t M, int64_t d,
+                        const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldqh, const float* q_inv_scale,
+                        const float* q_norm,
+                        const uint16_t* y_hi, const uint16_t* y_lo, int64_t ldyh, float y_inv_scale,
+                        const float* y_norm, const float* y_aux, int64_t index_offset, int64_t n_local,
+                        int64_t n_total, float* out, int64_t* argmin, pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K8 posterior mean  x0_hat_b = sum_j p_bj y_j,  p_bj = exp(-(E_bj - m_b)/T_b)/l_b.

@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libpdm_b200.so")
 
-SOURCES = ["cabi.cu", "prep_kernels.cu", "noise_philox.cu", "merge.cu", "stats_exact.cu", "stats_tcgen05.cu"]
+SOURCES = ["cabi.cu", "prep_kernels.cu", "noise_philox.cu", "merge.cu", "screen.cu", "stats_exact.cu", "stats_tcgen05.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
               "-DPDM_BUILD"] + ARCH

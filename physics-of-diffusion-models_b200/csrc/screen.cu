@@ -1,0 +1,195 @@
+// Certified delta posteriors (adaptive precision of the statistics pass); contract in include/pdm_b200.h.
+//
+// The reference evaluates every (query, point) pair at every temperature (utils/stats.py:80-90, 282-289).  In the
+// low-noise part of a schedule the posterior of a row is a delta on its nearest training point to fp32 resolution;
+// a ONE-product tensor-core pass (operands rounded to 11 significant bits, |E1 - E| <= delta rigorously) run at a
+// fictitious temperature proves it, and the proven rows skip the full-precision pass.
+//   screen_temperatures_kernel  1/T' per row                                   (HBM: 8 B read, 4 B written per row)
+//   certify_rows_kernel         flags from the merged screening statistics    (8 B read per row)
+//   tile_list_kernel            ascending list of row tiles with an unproven row (one block, ballot scan)
+//   finalize_rows_kernel        closed form for proven rows; E_min from the split operands in fp64
+//                               (one warp per proven row: 8*d B read)
+#include "pdm_common.cuh"
+
+namespace pdm {
+
+__global__ void __launch_bounds__(256) screen_temperatures_kernel(const float* __restrict__ q_norm,
+                                                                  const float* __restrict__ inv_temp, int64_t M,
+                                                                  const float* __restrict__ y_norm_max, float g,
+                                                                  float e_star, float kappa, float* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const float delta = kappa * 0.0009765625f * sqrtf(q_norm[r]) * sqrtf(__ldg(y_norm_max));
+    const float t = 1.f / inv_temp[r];
+    out[r] = e_star / fmaf(g, t, 2.f * delta);
+}
+
+__global__ void __launch_bounds__(256) certify_rows_kernel(const float* __restrict__ screen_out, int64_t M, float a1_max,
+                                                           uint8_t* __restrict__ flags) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const float l = screen_out[PDM_OUT_L * M + r];
+    const float a1 = screen_out[PDM_OUT_MEAN_E * M + r] * l;
+    // NaN / inf fail both comparisons: such rows stay on the full-precision path
+    flags[r] = (l > 0.99f && l < 1.25f && a1 >= 0.f && a1 < a1_max) ? 1 : 0;
+}
+
+// One block walks the tiles in order; a tile is listed unless every one of its rows is certified.
+__global__ void __launch_bounds__(1024) tile_list_kernel(const uint8_t* __restrict__ flags, int64_t M, int32_t rows_per_tile,
+                                                         int32_t* __restrict__ tile_list, int32_t* __restrict__ n_out) {
+    __shared__ int warp_count[32];
+    __shared__ int base;
+    const int64_t tiles = ceil_div(M, (int64_t)rows_per_tile);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < tiles; t0 += blockDim.x) {
+        const int64_t t = t0 + threadIdx.x;
+        bool listed = false;
+        if (t < tiles) {
+            const int64_t r0 = t * rows_per_tile, r1 = min(M, r0 + rows_per_tile);
+            for (int64_t r = r0; r < r1 && !listed; ++r) listed = flags[r] == 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, listed);
+        if (lane == 0) warp_count[warp] = __popc(bal);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += warp_count[w];
+        if (listed) tile_list[before + __popc(bal & ((1u << lane) - 1u))] = (int32_t)t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_count[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = base;
+}
+
+struct FinalizeParams {
+    const uint8_t* flags; const int64_t* screen_argmin; int64_t M, d;
+    const uint16_t* q_hi; const uint16_t* q_lo; int64_t ldqh; const float* q_inv_scale; const float* q_norm;
+    const uint16_t* y_hi; const uint16_t* y_lo; int64_t ldyh; float y_inv_scale;
+    const float* y_norm; const float* y_aux; int64_t index_offset, n_local; float neg_log_n;
+    float* out; int64_t* argmin;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 p = __half22float2(h[i]);
+        f[2 * i] = p.x; f[2 * i + 1] = p.y;
+    }
+}
+
+__global__ void __launch_bounds__(256) finalize_rows_kernel(const FinalizeParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= p.M || !p.flags[r]) return;                       // warp-uniform
+    const int64_t k = p.screen_argmin[r];
+    const int64_t j = k - p.index_offset;
+    const int64_t M = p.M;
+    if (lane == 0) {
+        p.out[PDM_OUT_LOG_L * M + r] = 0.f;
+        p.out[PDM_OUT_MEAN_E * M + r] = 0.f;
+        p.out[PDM_OUT_MEAN_E2 * M + r] = 0.f;
+        p.out[PDM_OUT_VAR_E * M + r] = 0.f;
+        p.out[PDM_OUT_ENTROPY * M + r] = p.neg_log_n;
+        p.out[PDM_OUT_L * M + r] = 1.f;
+        if (p.argmin) p.argmin[r] = k;
+    }
+    if (j < 0 || j >= p.n_local) {
+        // the arg-min lives on another shard: its owner writes E_min and the aux value; the caller combines the
+        // shards' rows with MIN (E_min: +inf here) and MAX (aux: -inf here) -- both leave the rows of uncertified
+        // queries, which are identical on every shard, as they are
+        if (lane == 0) { p.out[PDM_OUT_E_MIN * M + r] = INFINITY; p.out[PDM_OUT_AUX_MEAN * M + r] = -INFINITY; }
+        return;
+    }
+    const uint4* qh = reinterpret_cast<const uint4*>(p.q_hi + r * p.ldqh);
+    const uint4* ql = p.q_lo ? reinterpret_cast<const uint4*>(p.q_lo + r * p.ldqh) : nullptr;
+    const uint4* yh = reinterpret_cast<const uint4*>(p.y_hi + j * p.ldyh);
+    const uint4* yl = p.y_lo ? reinterpret_cast<const uint4*>(p.y_lo + j * p.ldyh) : nullptr;
+    const int64_t chunks = ceil_div(p.d, 8);                   // columns d..ld-1 of the split operands are zero
+    double acc = 0.0;
+    for (int64_t c = lane; c < chunks; c += 32) {
+        float a[8], al[8], b[8], bl[8];
+        unpack8(__ldg(qh + c), a);
+        unpack8(__ldg(yh + c), b);
+        if (ql) unpack8(__ldg(ql + c), al);
+        if (yl) unpack8(__ldg(yl + c), bl);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const double x = (double)a[i] + (ql ? (double)al[i] : 0.0);
+            const double y = (double)b[i] + (yl ? (double)bl[i] : 0.0);
+            acc = fma(x, y, acc);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        // the fused pass's formula (stats_tcgen05.cu epilogue) on the exactly rounded dot product
+        const float neg2inv = -2.f * p.q_inv_scale[r] * p.y_inv_scale;
+        const float u = __fadd_rn(fmaf((float)acc, neg2inv, p.q_norm[r]), p.y_norm[j]);
+        p.out[PDM_OUT_E_MIN * M + r] = 0.5f * u;
+        p.out[PDM_OUT_AUX_MEAN * M + r] = p.y_aux ? p.y_aux[j] : 0.f;
+    }
+}
+
+}  // namespace pdm
+
+using namespace pdm;
+
+extern "C" int pdm_screen_temperatures(const float* q_norm, const float* inv_temp, int64_t M, const float* y_norm_max,
+                                       float g, float e_star, float kappa, float* inv_temp_screen, pdm_stream_t stream) {
+    PDM_REQUIRE(q_norm && inv_temp && y_norm_max && inv_temp_screen && M >= 0, "pdm_screen_temperatures: bad arguments");
+    PDM_REQUIRE(g > 0.f && e_star >= 2.f && e_star <= 80.f && kappa >= 1.f,
+                "pdm_screen_temperatures: need g > 0, 2 <= e_star <= 80 (e exp(-e) must stay a normal fp32), kappa >= 1");
+    if (M == 0) return PDM_OK;
+    screen_temperatures_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(q_norm, inv_temp, M, y_norm_max, g,
+                                                                                         e_star, kappa, inv_temp_screen);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_screen_certify(const float* screen_out, int64_t M, float e_star, int32_t rows_per_tile,
+                                  uint8_t* flags, int32_t* tile_list, int32_t* n_tiles_out, pdm_stream_t stream) {
+    PDM_REQUIRE(screen_out && flags && tile_list && n_tiles_out && M >= 0 && rows_per_tile >= 1,
+                "pdm_screen_certify: bad arguments");
+    PDM_REQUIRE(e_star >= 2.f && e_star <= 80.f, "pdm_screen_certify: 2 <= e_star <= 80");
+    PDM_REQUIRE(ceil_div(M, (int64_t)rows_per_tile) < (1ll << 31), "pdm_screen_certify: too many row tiles");
+    const float a1_max = 0.9f * e_star * expf(-e_star);
+    if (M > 0) {
+        certify_rows_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(screen_out, M, a1_max, flags);
+        PDM_CUDA_CHECK(cudaGetLastError());
+    }
+    tile_list_kernel<<<1, 1024, 0, as_stream(stream)>>>(flags, M, rows_per_tile, tile_list, n_tiles_out);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_screen_finalize(const uint8_t* flags, const int64_t* screen_argmin, int64_t M, int64_t d,
+                                   const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldqh, const float* q_inv_scale,
+                                   const float* q_norm,
+                                   const uint16_t* y_hi, const uint16_t* y_lo, int64_t ldyh, float y_inv_scale,
+                                   const float* y_norm, const float* y_aux, int64_t index_offset, int64_t n_local,
+                                   int64_t n_total, float* out, int64_t* argmin, pdm_stream_t stream) {
+    PDM_REQUIRE(flags && screen_argmin && q_hi && q_inv_scale && q_norm && y_hi && y_norm && out && M >= 0 && d > 0 &&
+                n_local > 0 && n_total >= n_local, "pdm_screen_finalize: bad arguments");
+    PDM_REQUIRE(ldqh % 8 == 0 && ldyh % 8 == 0 && ldqh >= d && ldyh >= d &&
+                (reinterpret_cast<uintptr_t>(q_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_hi) & 15) == 0 &&
+                (!q_lo || (reinterpret_cast<uintptr_t>(q_lo) & 15) == 0) && (!y_lo || (reinterpret_cast<uintptr_t>(y_lo) & 15) == 0),
+                "pdm_screen_finalize: split operands must be 16-byte aligned with leading dimensions that are multiples of 8");
+    if (M == 0) return PDM_OK;
+    FinalizeParams p;
+    p.flags = flags; p.screen_argmin = screen_argmin; p.M = M; p.d = d;
+    p.q_hi = q_hi; p.q_lo = q_lo; p.ldqh = ldqh; p.q_inv_scale = q_inv_scale; p.q_norm = q_norm;
+    p.y_hi = y_hi; p.y_lo = y_lo; p.ldyh = ldyh; p.y_inv_scale = y_inv_scale;
+    p.y_norm = y_norm; p.y_aux = y_aux; p.index_offset = index_offset; p.n_local = n_local;
+    p.neg_log_n = -logf((float)n_total);
+    p.out = out; p.argmin = argmin;
+    finalize_rows_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, as_stream(stream)>>>(p);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}

@@ -101,7 +101,8 @@ struct GemmParams {
     unsigned* round_sync;      // soft rendezvous of the TMA producers (nullptr = off), one counter per rendezvous
     int32_t sync_points;       // counters available
     int32_t sync_tiles;        // column tiles between two rendezvous
-    int32_t m_tiles;      // row super-tiles of 128*CG rows
+    int32_t m_tiles;      // row super-tiles of 128*CG rows at work (all of them, or the length of tile_list)
+    const int32_t* tile_list;  // optional: the row super-tiles to process (screened launches); nullptr = 0..m_tiles-1
     int32_t n_tiles;      // column tiles of kBlockN
     int32_t m_group, n_splits;
     // EPI_STATS
@@ -202,7 +203,8 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const uint64_t t_begin = global_timer_ns();
 #endif
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
-                const int32_t a_row = (mt * CG + (int)rank) * kRowsPerCta;
+                const int tile = p.tile_list ? __ldg(p.tile_list + mt) : mt;
+                const int32_t a_row = (tile * CG + (int)rank) * kRowsPerCta;
                 const int round = mt / p.m_group;
                 const int row_groups = min(p.m_group, p.m_tiles - round * p.m_group);     // row tiles at work this round
                 const int per_round = (ceil_div(p.n_tiles, p.n_splits) + p.sync_tiles - 1) / max(1, p.sync_tiles);
@@ -315,7 +317,8 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const float yn_bound = (float)(p.num_kb * kBlockK) * (4096.f * p.y_inv_scale) * (4096.f * p.y_inv_scale);
             const float half_mult = 0.5f * p.energy_mult;
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
-                const int64_t grow = (int64_t)(mt * CG + (int)rank) * kRowsPerCta + row_in_cta;
+                const int tile = p.tile_list ? __ldg(p.tile_list + mt) : mt;
+                const int64_t grow = (int64_t)(tile * CG + (int)rank) * kRowsPerCta + row_in_cta;
                 const bool row_ok = grow < p.M;
                 float xn = 0.f, neg2inv = 0.f, c2 = -0.5f * kLog2e;
                 bool safe = true;          // (u - 2m) * c2 cannot overflow for this row: no per-element clamp
@@ -673,7 +676,7 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.hint_b = evict_hint_setting("PDM_HINT_B", kEvictFirst);      // dataset tiles are dead once their split has passed
     {
         static const bool round_sync_on = !(getenv("PDM_ROUND_SYNC") && atoi(getenv("PDM_ROUND_SYNC")) == 0);
-        const int64_t rounds = ceil_div(ceil_div(a.M, (int64_t)kRowsPerCta * cg), (int64_t)a.m_group);
+        const int64_t rounds = ceil_div(a.row_tiles ? a.n_row_tiles : ceil_div(a.M, (int64_t)kRowsPerCta * cg), (int64_t)a.m_group);
         static const int sync_tiles = getenv("PDM_SYNC_TILES") ? std::max(1, atoi(getenv("PDM_SYNC_TILES"))) : 8;
         const int64_t cols_per_round = ceil_div(ceil_div(a.N, (int64_t)(cg == 2 ? 256 : 128)), (int64_t)a.n_splits);
         const int64_t points = rounds * ceil_div(cols_per_round, (int64_t)sync_tiles);
@@ -687,6 +690,11 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
         }
     }
     p.m_tiles = (int32_t)ceil_div(a.M, (int64_t)kRowsPerCta * cg);
+    if (a.row_tiles) {
+        PDM_REQUIRE(a.n_row_tiles >= 1 && a.n_row_tiles <= p.m_tiles, "n_row_tiles must be between 1 and the number of row tiles");
+        p.m_tiles = (int32_t)a.n_row_tiles;
+        p.tile_list = a.row_tiles;
+    }
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
     p.m_group = a.m_group; p.n_splits = a.n_splits;
     PDM_REQUIRE(p.m_group >= 1 && p.n_splits >= 1 && (int64_t)p.m_group * p.n_splits <= info.sm_count / cg,
@@ -722,7 +730,8 @@ extern "C" int pdm_posterior_stats_plan(pdm_stats_args* a, int device, int64_t* 
         const int cg = a->cta_group;
         PDM_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
         const int pairs = sm / cg;
-        const int64_t m_tiles = std::max<int64_t>(1, ceil_div(a->M, 128 * cg)), n_tiles = ceil_div(a->N, cg == 2 ? 256 : 128);
+        const int64_t m_tiles = a->row_tiles ? std::max<int64_t>(1, a->n_row_tiles) : std::max<int64_t>(1, ceil_div(a->M, 128 * cg));
+        const int64_t n_tiles = ceil_div(a->N, cg == 2 ? 256 : 128);
         const int64_t k_pad = round_up(a->d, 64);
         const int64_t a_tile_bytes = 128ll * cg * k_pad * 2 * (a->precision == PDM_PREC_F16X1 ? 1 : 2);
         int g = a->m_group, s = a->n_splits;
@@ -745,7 +754,8 @@ extern "C" int pdm_posterior_stats(const pdm_stats_args* a, pdm_stream_t stream)
     PDM_REQUIRE(!a->partials || a->inv_temp, "pdm_posterior_stats: inv_temp missing");
     PDM_REQUIRE(!a->energy_out || a->lde >= a->N, "pdm_posterior_stats: lde < N");
     PDM_REQUIRE(a->n_splits >= 1, "pdm_posterior_stats: n_splits must be planned (>= 1)");
-    if (a->M == 0) return PDM_OK;
+    PDM_REQUIRE(!a->row_tiles || a->precision != PDM_PREC_EXACT_F32, "pdm_posterior_stats: row_tiles needs the tensor path");
+    if (a->M == 0 || (a->row_tiles && a->n_row_tiles == 0)) return PDM_OK;
     switch (a->precision) {
         case PDM_PREC_EXACT_F32: return launch_exact_stats(*a, as_stream(stream));
         case PDM_PREC_F16X3:

@@ -35,6 +35,7 @@ class StatsArgs(C.Structure):
         ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldyh", C.c_int64), ("y_inv_scale", C.c_float),
         ("q_norm", C.c_void_p), ("y_norm", C.c_void_p), ("inv_temp", C.c_void_p), ("y_aux", C.c_void_p),
         ("partials", C.c_void_p), ("energy_out", C.c_void_p), ("lde", C.c_int64), ("energy_mult", C.c_float),
+        ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int64),
     ]
 
 
@@ -59,6 +60,10 @@ SIGNATURES = {
     "pdm_posterior_stats": (C.c_int, [C.POINTER(StatsArgs), _P]),
     "pdm_merge_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
     "pdm_reduce_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "pdm_screen_temperatures": (C.c_int, [_P, _P, _I64, _P, _F, _F, _F, _P, _P]),
+    "pdm_screen_certify": (C.c_int, [_P, _I64, _F, _I32, _P, _P, _P, _P]),
+    "pdm_screen_finalize": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _I64, _F, _P, _P, _I64, _I64, _I64,
+                                      _P, _P, _P]),
     "pdm_weights_from_energy": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "pdm_split_gemm_f16x3": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P]),
     "pdm_sampler_step_f32": (C.c_int, [_P, _P, _P, _F, _F, _F, _P, _I64, _P]),
@@ -84,7 +89,7 @@ def load() -> C.CDLL:
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
-            if lib.pdm_abi_version() != 2:
+            if lib.pdm_abi_version() != 3:
                 raise PdmError("libpdm_b200.so ABI version mismatch; rebuild the library")
             _lib = lib
     return _lib

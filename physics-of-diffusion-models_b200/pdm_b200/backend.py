@@ -212,7 +212,10 @@ class CudaBackend:
                         q_split=None, y_split=None, y_inv_scale: float = 1.0, y_aux: Optional[Tensor] = None,
                         index_offset: int = 0, n_splits: int = 0, m_group: int = 0, cta_group: int = 0,
                         want_partials: bool = True, energy_out: Optional[Tensor] = None,
-                        energy_mult: float = 1.0) -> Optional[Tensor]:
+                        energy_mult: float = 1.0, row_tiles: Optional[Tensor] = None,
+                        n_row_tiles: int = 0) -> Optional[Tensor]:
+        """``row_tiles`` (int32, device) / ``n_row_tiles``: screened launch over the listed row tiles of
+        128*cta_group rows only; records of the other rows are left as allocated (uninitialised)."""
         a = StatsArgs()
         a.precision = PRECISIONS[precision]
         a.n_splits, a.m_group, a.cta_group = n_splits, m_group, cta_group
@@ -227,6 +230,10 @@ class CudaBackend:
             a.q_hi, a.q_lo, a.ldqh, a.q_inv_scale = q_hi.data_ptr(), _ptr(q_lo), _ld(q_hi), q_inv.data_ptr()
             a.y_hi, a.y_lo, a.ldyh, a.y_inv_scale = y_hi.data_ptr(), _ptr(y_lo), _ld(y_hi), float(y_inv_scale)
         a.q_norm, a.y_norm, a.inv_temp, a.y_aux = q_norm.data_ptr(), y_norm.data_ptr(), _ptr(inv_temp), _ptr(y_aux)
+        if row_tiles is not None:
+            assert row_tiles.dtype == torch.int32 and row_tiles.is_contiguous() and n_row_tiles <= row_tiles.numel()
+            a.row_tiles, a.n_row_tiles = row_tiles.data_ptr(), int(n_row_tiles)
+            keep.append(row_tiles)
         nfloats = C.c_int64()
         check(self.lib.pdm_posterior_stats_plan(C.byref(a), self.device.index or 0, C.byref(nfloats)),
               "pdm_posterior_stats_plan")
@@ -242,7 +249,8 @@ class CudaBackend:
         check(self.lib.pdm_posterior_stats(C.byref(a), self._stream()), "pdm_posterior_stats")
         if self.kernel_events is not None:
             ev1.record()
-            self.kernel_events.append((ev0, ev1, M * N))
+            rows_done = M if row_tiles is None else min(M, int(n_row_tiles) * 128 * a.cta_group)
+            self.kernel_events.append((ev0, ev1, rows_done * N))
         self.launches += 1
         self.last_plan = (a.n_splits, a.m_group, a.cta_group)
         del keep
@@ -264,6 +272,40 @@ class CudaBackend:
                                           out.data_ptr(), argmin.data_ptr(), self._stream()), "pdm_merge_partials")
         self.launches += 1
         return out, argmin
+
+    # ---- certified delta posteriors (adaptive precision) -------------------------------------------
+    def screen_temperatures(self, q_norm: Tensor, inv_temp: Tensor, y_norm_max: Tensor, g: float, e_star: float,
+                            kappa: float) -> Tensor:
+        out = torch.empty_like(inv_temp)
+        check(self.lib.pdm_screen_temperatures(q_norm.data_ptr(), inv_temp.data_ptr(), inv_temp.numel(), y_norm_max.data_ptr(),
+                                               float(g), float(e_star), float(kappa), out.data_ptr(), self._stream()),
+              "pdm_screen_temperatures")
+        self.launches += 1
+        return out
+
+    def screen_certify(self, screen_out: Tensor, e_star: float, rows_per_tile: int):
+        """-> flags (M,) uint8, tile_list (tiles,) int32, n_listed (1,) int32 -- all on the device."""
+        m = screen_out.shape[1]
+        tiles = (m + rows_per_tile - 1) // rows_per_tile
+        flags = torch.empty(m, dtype=torch.uint8, device=self.device)
+        tile_list = torch.empty(max(1, tiles), dtype=torch.int32, device=self.device)
+        n_listed = torch.empty(1, dtype=torch.int32, device=self.device)
+        check(self.lib.pdm_screen_certify(screen_out.data_ptr(), m, float(e_star), int(rows_per_tile), flags.data_ptr(),
+                                          tile_list.data_ptr(), n_listed.data_ptr(), self._stream()), "pdm_screen_certify")
+        self.launches += 2
+        return flags, tile_list, n_listed
+
+    def screen_finalize(self, flags: Tensor, screen_argmin: Tensor, d: int, q_split, q_norm: Tensor, y_split,
+                        y_inv_scale: float, y_norm: Tensor, y_aux: Optional[Tensor], index_offset: int, n_local: int,
+                        n_total: int, out: Tensor, argmin: Tensor) -> None:
+        q_hi, q_lo, q_inv = q_split
+        y_hi, y_lo = y_split
+        check(self.lib.pdm_screen_finalize(flags.data_ptr(), screen_argmin.data_ptr(), flags.numel(), d,
+                                           q_hi.data_ptr(), _ptr(q_lo), _ld(q_hi), q_inv.data_ptr(), q_norm.data_ptr(),
+                                           y_hi.data_ptr(), _ptr(y_lo), _ld(y_hi), float(y_inv_scale), y_norm.data_ptr(),
+                                           _ptr(y_aux), index_offset, n_local, n_total, out.data_ptr(), argmin.data_ptr(),
+                                           self._stream()), "pdm_screen_finalize")
+        self.launches += 1
 
     def reduce(self, parts: Tensor, inv_temp: Tensor) -> Tensor:
         """(S, M, 8) record-major -> (M, 1, 8): one merged, not yet finalised, record per row."""

@@ -107,6 +107,14 @@ class EmpiricalDataset:
         self._yt = None
         self._moments = None
         self._scale = None
+        self._y_norm_max = None
+
+    @property
+    def y_norm_max(self) -> Tensor:
+        """max_j ||y_j||^2 as a one-element device tensor (error bound of the screening pass)."""
+        if self._y_norm_max is None:
+            self._y_norm_max = self.y_norm.max().reshape(1).contiguous()
+        return self._y_norm_max
 
     # -- lazily built device-side views ----------------------------------------------------------
     def _absmax(self) -> float:
@@ -181,6 +189,12 @@ class EngineConfig:
                                        # nearest training point directly (skips weights + second contraction for them)
     fused_noise: bool = True           # regenerate torch.randn's Philox stream inside the operand kernel (bit-identical,
                                        # verified once per device) instead of torch.randn + pdm_prepare_rows
+    screen: bool = False               # noised_stats: certified delta posteriors.  A one-product tensor pass with a rigorous
+                                       # error bound proves, row by row, that every other training point's weight is below
+                                       # exp(-screen_g) of the nearest one's; proven rows take the closed form and only the
+                                       # row tiles with an unproven row run the full-precision pass (include/pdm_b200.h,
+                                       # pdm_screen_*).  PDM_SCREEN=1 turns it on.
+    screen_g: float = 0.0              # weight cut-off exponent; 0 = 17 + log N (everything dropped sums to < 2^-24)
     slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows on a side
                                        # stream, one block ahead, and the operands are all-gathered.  Off: measured on
                                        # 8 B200s the exchange does not hide under the persistent tensor kernel --
@@ -192,6 +206,8 @@ class EngineConfig:
         cfg = EngineConfig(precision=os.environ.get("PDM_PRECISION", "auto"),
                            cta_group=_env_int("PDM_CTA_GROUP"), m_group=_env_int("PDM_M_GROUP"),
                            n_splits=_env_int("PDM_N_SPLITS"))
+        if os.environ.get("PDM_SCREEN", "") in ("0", "1"):
+            cfg.screen = os.environ["PDM_SCREEN"] == "1"
         if os.environ.get("PDM_SLICE_NOISE", "") in ("0", "1"):
             cfg.slice_noise = os.environ["PDM_SLICE_NOISE"] == "1"
         return cfg
@@ -213,6 +229,11 @@ class PosteriorEngine:
         self.cfg = config if config is not None else EngineConfig.from_env()
         self.group = group
         self.world = 1
+        # screening bookkeeping: rows / row tiles seen by the screening pass and what it left for the full pass
+        self.screen_report = {"rows_screened": 0, "rows_certified": 0, "tiles_screened": 0, "tiles_full_pass": 0,
+                              "rows_unscreened": 0}
+        self._screen_t_fail = math.inf
+        self._y_norm_max = None
         if group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(group)
@@ -244,12 +265,15 @@ class PosteriorEngine:
                                          want_x=(want_x or not tensor), want_norms=True, want_split=tensor)
 
     def _local_partials(self, prep: dict, rows: int, inv_temp: Tensor, aux: Optional[Tensor], precision: str,
-                        energy_out: Optional[Tensor] = None, energy_mult: float = 1.0, want_partials: bool = True):
+                        energy_out: Optional[Tensor] = None, energy_mult: float = 1.0, want_partials: bool = True,
+                        row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0):
         ds = self.ds
         kw = dict(precision=precision, M=rows, N=ds.n, d=ds.d, q_norm=prep["norms"], y_norm=ds.y_norm,
                   inv_temp=inv_temp, y_aux=aux, index_offset=ds.index_offset, n_splits=self.cfg.n_splits,
                   m_group=self.cfg.m_group, cta_group=self.cfg.cta_group, want_partials=want_partials,
                   energy_out=energy_out, energy_mult=energy_mult)
+        if row_tiles is not None:
+            kw.update(row_tiles=row_tiles, n_row_tiles=n_row_tiles)
         if precision == "exact":
             return self.backend.posterior_stats(q=prep["x"], y=ds.y, **kw)
         y_hi, y_lo = ds.split()
@@ -267,9 +291,68 @@ class PosteriorEngine:
             parts = gathered.view((self.world,) + tuple(local.shape))
         return self.backend.merge(parts, inv_temp, self.ds.n_total)
 
+    # -- certified delta posteriors ----------------------------------------------------------------
+    SCREEN_E_STAR = 50.0       # the screening pass certifies (E1_j - E1_min)/T' > e_star for every other point
+    SCREEN_KAPPA = 1.25        # safety factor on the first-order bound 2^-10 ||x|| ||y|| of |x.y - x_hi.y_hi|
+
+    def screening_usable(self) -> bool:
+        return (self.cfg.screen and self.precision() in ("f16x3", "f16x2") and hasattr(self.backend, "screen_certify"))
+
+    def _global_y_norm_max(self) -> Tensor:
+        if self._y_norm_max is None:
+            v = self.ds.y_norm_max.clone()
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(v, op=dist.ReduceOp.MAX, group=self.group)
+            self._y_norm_max = v
+        return self._y_norm_max
+
+    def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
+                        precision: str):
+        """One-product pass at the fictitious temperature -> certificate per row -> full-precision pass over the row
+        tiles that hold an unproven row -> closed form for the proven rows.  One host read (two scalars) per block."""
+        be, ds = self.backend, self.ds
+        g = self.cfg.screen_g if self.cfg.screen_g > 0 else 17.0 + math.log(max(2, ds.n_total))
+        inv_t1 = be.screen_temperatures(prep["norms"], inv_temp, self._global_y_norm_max(), g, self.SCREEN_E_STAR,
+                                        self.SCREEN_KAPPA)
+        parts1 = self._local_partials(prep, rows, inv_t1, None, "f16x1")
+        out1, arg1 = self._merge(parts1, inv_t1)             # across shards too: every rank sees the same certificate
+        rows_per_tile = 128 * (self.cfg.cta_group or 2)
+        flags, tile_list, n_listed = be.screen_certify(out1, self.SCREEN_E_STAR, rows_per_tile)
+        open_rows = flags == 0
+        t_open = torch.where(open_rows, temp_rows, torch.full_like(temp_rows, math.inf)).min()
+        n_open_rows = open_rows.sum()
+        n_tiles, t_open, n_open_rows = (float(v) for v in torch.stack(
+            [n_listed[0].to(torch.float64), t_open.to(torch.float64), n_open_rows.to(torch.float64)]).cpu())
+        n_tiles = int(n_tiles)
+        rep = self.screen_report
+        rep["rows_screened"] += rows
+        rep["rows_certified"] += rows - int(n_open_rows)
+        rep["tiles_screened"] += (rows + rows_per_tile - 1) // rows_per_tile
+        rep["tiles_full_pass"] += n_tiles
+        self._screen_t_fail = min(self._screen_t_fail, t_open)
+        if n_tiles > 0:
+            parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=n_tiles)
+            out, argmin = self._merge(parts, inv_temp)
+        else:
+            out = torch.empty(len(STAT_KEYS), rows, dtype=torch.float32, device=be.device)
+            argmin = torch.empty(rows, dtype=torch.int64, device=be.device)
+        y_hi, y_lo = ds.split()
+        be.screen_finalize(flags, arg1, ds.d, (prep["hi"], prep["lo"], prep["inv_scale"]), prep["norms"],
+                           (y_hi, None if precision == "f16x2" else y_lo), 1.0 / ds.scale, ds.y_norm, aux,
+                           ds.index_offset, ds.n, ds.n_total, out, argmin)
+        if self.world > 1:
+            # the owner of a certified row's nearest point holds its E_min / aux value (others: +inf / -inf)
+            import torch.distributed as dist
+            both = torch.stack([out[_cabi.OUT_E_MIN], -out[_cabi.OUT_AUX_MEAN]])
+            dist.all_reduce(both, op=dist.ReduceOp.MIN, group=self.group)
+            out[_cabi.OUT_E_MIN].copy_(both[0])
+            out[_cabi.OUT_AUX_MEAN].copy_(-both[1])
+        return out, argmin
+
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
                     sigma: Optional[Tensor] = None, post: Optional[Tensor] = None, aux: Optional[Tensor] = None,
-                    prep: Optional[dict] = None):
+                    prep: Optional[dict] = None, screen: bool = False):
         """Statistics for ``rows`` query rows; returns (out (8, rows), argmin (rows,)) device tensors.
         Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional); ``prep`` passes
         already prepared operands (rank-sliced preparation of a sharded run) instead."""
@@ -282,6 +365,10 @@ class PosteriorEngine:
         if prep is None:
             with ph("prepare"):
                 prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
+        if screen and self.screening_usable():
+            with ph("fused"):
+                return self._screened_block(prep, rows, temp_rows.to(torch.float32), inv_temp, aux, precision)
+        self.screen_report["rows_unscreened"] += rows
         with ph("fused"):
             parts = self._local_partials(prep, rows, inv_temp, aux, precision)
         with ph("merge"):
@@ -334,6 +421,12 @@ class PosteriorEngine:
         if self.world > 1 and fused and not sliced:
             self._sync_generator(dev)            # every rank regenerates rank 0's stream: 16 bytes instead of the noise
         x0_absmax = self.backend.row_absmax(x0f) if fused and self.precision() != "exact" else None
+        # Screening policy: a block is screened while its lowest temperature is below the lowest temperature at which a
+        # row has failed the certificate so far in this call (schedules run from low to high noise; a block above that
+        # mark would pay the one-product pass for nothing).
+        screen_on = self.screening_usable()
+        temp_host = temp.detach().cpu() if screen_on else None
+        self._screen_t_fail = math.inf
         if sliced:
             # Opt-in (EngineConfig.slice_noise): each rank draws + prepares 1/world of a block's rows on a side stream
             # and the operands are all-gathered there, one block ahead of the fused pass on the main stream.  The
@@ -369,6 +462,7 @@ class PosteriorEngine:
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
+            screen = screen_on and float(temp_host[t0:t1].min()) < self._screen_t_fail
             ph = getattr(self.backend, "phase", None)
             if ph is None:
                 import contextlib
@@ -380,7 +474,7 @@ class PosteriorEngine:
                     base = gen.get_offset()
                     prep = self._fused_prepare(gen.initial_seed(), base, step_off, x0f, temp[t0:t1], x0_absmax)
                     gen.set_offset(base + nb * step_off)
-                o, i = self.stats_block(x0f, nb * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep)
+                o, i = self.stats_block(x0f, nb * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep, screen=screen)
                 outs.append(o)
                 idxs.append(i)
                 continue
@@ -397,7 +491,8 @@ class PosteriorEngine:
                 dist.broadcast(noise, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                                group=self.group)
             t_rows = temp[t0:t1].repeat_interleave(b)
-            o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux)
+            o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux,
+                                    screen=screen)
             outs.append(o)
             idxs.append(i)
         out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]

@@ -43,11 +43,21 @@ def main():
 
     ref, off_ref = run(full, 123)
     other = 123 if rank == 0 else 999 + rank                  # with sync_noise every rank must end up on rank 0's stream
-    for slice_noise, sync, seed in ((True, False, 123), (False, False, 123), (True, True, other), (False, True, other)):
+    # last entry: certified delta posteriors (EngineConfig.screen) on the sharded dataset
+    for slice_noise, sync, seed, screen in ((True, False, 123, False), (False, False, 123, False), (True, True, other, False),
+                                            (False, True, other, False), (False, True, other, True)):
         cfg = EngineConfig(max_query_bytes=96 << 20)          # several blocks of temperatures
-        cfg.slice_noise, cfg.sync_noise = slice_noise, sync
+        cfg.slice_noise, cfg.sync_noise, cfg.screen = slice_noise, sync, screen
         shard = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=n, global_absmax=amax, lattice_scale=lat)
-        st, off = run(PosteriorEngine(shard, cfg, group=dist.group.WORLD), seed)
+        eng = PosteriorEngine(shard, cfg, group=dist.group.WORLD)
+        st, off = run(eng, seed)
+        if screen:
+            rep = eng.screen_report
+            if rank == 0:
+                print("screened sharded run:", rep)
+            if rep["rows_certified"] < 10 * b or rep["rows_unscreened"] == 0:
+                ok = False
+                print(f"rank {rank}: screening did not engage as expected: {rep}")
         xn = (x0.reshape(b, -1).double() ** 2).sum(1)[None, :] + d * temps.double()[:, None]
         floor = 8 * 2.0 ** -24 * (xn + (data.double() ** 2).sum(1).max()) / temps.double()[:, None]
         for k in ("log_l", "mean_e", "entropy"):
@@ -59,7 +69,13 @@ def main():
         if not torch.equal(st["argmin"], ref["argmin"]):
             ok = False
             print(f"rank {rank} slice={slice_noise} sync={sync}: argmin mismatch")
-        if not torch.equal(st["e_min"], ref["e_min"]):
+        if screen:
+            # certified rows recompute E_min in fp64 from the operands: within the fp32 round-off floor of the full pass
+            err = (st["e_min"].double() - ref["e_min"].double()).abs()
+            if (err > floor * temps.double()[:, None]).any():
+                ok = False
+                print(f"rank {rank} screened: e_min off by {err.max().item():.3e}")
+        elif not torch.equal(st["e_min"], ref["e_min"]):
             ok = False
             print(f"rank {rank} slice={slice_noise} sync={sync}: e_min not bit-identical")
         if not (sync and rank != 0) and off != off_ref:
