@@ -233,6 +233,7 @@ class PosteriorEngine:
         self.screen_report = {"rows_screened": 0, "rows_certified": 0, "tiles_screened": 0, "tiles_full_pass": 0,
                               "rows_unscreened": 0}
         self._screen_t_fail = math.inf
+        self._screen_t_retry = math.inf    # after a screened block that certified nothing: next attempt at T <= this
         self._y_norm_max = None
         if group is not None:
             import torch.distributed as dist
@@ -317,7 +318,7 @@ class PosteriorEngine:
                                         self.SCREEN_KAPPA)
         parts1 = self._local_partials(prep, rows, inv_t1, None, "f16x1")
         out1, arg1 = self._merge(parts1, inv_t1)             # across shards too: every rank sees the same certificate
-        rows_per_tile = 128 * (self.cfg.cta_group or 2)
+        rows_per_tile = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)     # the fused kernel's row tile
         flags, tile_list, n_listed = be.screen_certify(out1, self.SCREEN_E_STAR, rows_per_tile)
         open_rows = flags == 0
         t_open = torch.where(open_rows, temp_rows, torch.full_like(temp_rows, math.inf)).min()
@@ -331,6 +332,8 @@ class PosteriorEngine:
         rep["tiles_screened"] += (rows + rows_per_tile - 1) // rows_per_tile
         rep["tiles_full_pass"] += n_tiles
         self._screen_t_fail = min(self._screen_t_fail, t_open)
+        if int(n_open_rows) == rows:
+            self._screen_t_retry = 0.25 * t_open
         if n_tiles > 0:
             parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=n_tiles)
             out, argmin = self._merge(parts, inv_temp)
@@ -423,10 +426,13 @@ class PosteriorEngine:
         x0_absmax = self.backend.row_absmax(x0f) if fused and self.precision() != "exact" else None
         # Screening policy: a block is screened while its lowest temperature is below the lowest temperature at which a
         # row has failed the certificate so far in this call (schedules run from low to high noise; a block above that
-        # mark would pay the one-product pass for nothing).
+        # mark would pay the one-product pass for nothing).  After a screened block that certifies nothing the
+        # next attempt waits for a block that reaches a quarter of its lowest temperature (schedules that start at the
+        # high-noise end pay a logarithmic number of failed attempts).
         screen_on = self.screening_usable()
         temp_host = temp.detach().cpu() if screen_on else None
         self._screen_t_fail = math.inf
+        self._screen_t_retry = math.inf
         if sliced:
             # Opt-in (EngineConfig.slice_noise): each rank draws + prepares 1/world of a block's rows on a side stream
             # and the operands are all-gathered there, one block ahead of the fused pass on the main stream.  The
@@ -462,7 +468,7 @@ class PosteriorEngine:
         for t0 in range(0, n_t, t_per_block):
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
-            screen = screen_on and float(temp_host[t0:t1].min()) < self._screen_t_fail
+            screen = screen_on and float(temp_host[t0:t1].min()) < min(self._screen_t_fail, self._screen_t_retry)
             ph = getattr(self.backend, "phase", None)
             if ph is None:
                 import contextlib

@@ -159,3 +159,16 @@ def test_screened_cifar_shape_block(backend):
         assert (err <= tol).all(), (k, err.max().item())
     err_m = (o_s[cabi.OUT_E_MIN].double() - o_u[cabi.OUT_E_MIN].double()).abs()
     assert (err_m <= 8 * 2.0 ** -24 * (xn + float(d))).all()
+
+
+def test_screened_descending_schedule(backend):
+    """A schedule that starts at the high-noise end: failed attempts back off, the low-noise end is still certified."""
+    n, d, b = 2000, 256, 256
+    data = torch.rand(n, d, generator=syn.gen(7)) * 2 - 1
+    x0 = data[500:500 + b].clone()
+    temp = torch.tensor([1e4, 1e3, 300.0, 100.0, 30.0, 10.0, 0.3, 1e-2, 1e-4])
+    scr, (o_s, a_s), (o_u, a_u), ref = run_both(backend, data, x0, temp, block_temps=1)
+    check_stats(o_s, a_s, ref, what="screened, descending")
+    rep = scr.screen_report
+    assert rep["rows_certified"] >= 2 * b and rep["rows_unscreened"] >= 2 * b, rep
+    assert torch.equal(a_s, a_u)

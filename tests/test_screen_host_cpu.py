@@ -1,0 +1,171 @@
+"""CPU tests of the certified-delta-posterior host logic (pdm_b200.engine: EngineConfig.screen) on a torch test double
+that restates the pdm_screen_* contract of include/pdm_b200.h: the screening policy over a schedule, the row-tile list,
+the closed form, and -- independently of any kernel -- the SOUNDNESS of the certificate: every row it certifies is
+checked in fp64 to have all other weights below exp(-g)."""
+import math
+
+import torch
+
+from fake_backend import FakeBackend, PART, _pack_idx
+from oracle import posterior as orc
+from oracle import synthetic as syn
+from pdm_b200 import EmpiricalDataset, EngineConfig, PosteriorEngine
+
+
+def _split16(v: torch.Tensor, scale: torch.Tensor):
+    s = v * scale
+    hi = s.half()
+    lo = (s - hi.float()).half()
+    return hi, lo
+
+
+class SplitFakeBackend(FakeBackend):
+    """FakeBackend + the fp16 hi/lo operand split, the one-/three-product contractions on it, row-tile lists and the
+    three screening entry points (torch restatement of csrc/screen.cu)."""
+    row_tile = 8
+
+    def supports_tensor_path(self) -> bool:
+        return True
+
+    def prepare_rows(self, src, rows, *, noise=None, sigma=None, post=None, fixed_scale=0.0, want_x=False,
+                     want_norms=True, want_split=True) -> dict:
+        r = super().prepare_rows(src, rows, noise=noise, sigma=sigma, post=post)
+        v = r["x"]
+        if fixed_scale > 0:
+            scale = torch.full((v.shape[0], 1), float(fixed_scale))
+        else:
+            amax = v.abs().max(1, keepdim=True).values.clamp(min=1e-30)
+            scale = 2.0 ** (11 - torch.floor(torch.log2(amax)))            # max|v|*scale in [2^11, 2^12)
+        r["hi"], r["lo"] = _split16(v, scale)
+        r["inv_scale"] = (1.0 / scale).reshape(-1)
+        return r
+
+    def posterior_stats(self, *, precision, M, N, d, q_norm, y_norm, inv_temp, q_split=None, y_split=None,
+                        y_inv_scale=1.0, y_aux=None, index_offset=0, n_splits=0, row_tiles=None, n_row_tiles=0, **kw):
+        if precision == "exact":
+            return super().posterior_stats(precision=precision, M=M, N=N, d=d, q_norm=q_norm, y_norm=y_norm,
+                                           inv_temp=inv_temp, y_aux=y_aux, index_offset=index_offset, n_splits=n_splits, **kw)
+        q_hi, q_lo, q_inv = q_split
+        y_hi, y_lo = y_split
+        qv = q_hi.double() if precision == "f16x1" else q_hi.double() + q_lo.double()
+        yv = y_hi.double() if (precision in ("f16x1", "f16x2") or y_lo is None) else y_hi.double() + y_lo.double()
+        q = (qv * q_inv.double()[:, None]).float()
+        y = (yv * y_inv_scale).float()
+        self.calls.append(f"stats:{precision}:{'list' if row_tiles is not None else 'all'}")
+        parts = super().posterior_stats(precision="exact", M=M, N=N, d=d, q_norm=q_norm, y_norm=y_norm, inv_temp=inv_temp,
+                                        q=q, y=y, y_aux=y_aux, index_offset=index_offset, n_splits=n_splits)
+        if row_tiles is not None:
+            keep = torch.zeros(M, dtype=torch.bool)
+            for t in row_tiles[:n_row_tiles].tolist():
+                keep[t * self.row_tile:(t + 1) * self.row_tile] = True
+            parts[~keep] = float("nan")                    # rows outside the list are never written by the kernel
+        return parts
+
+    def screen_temperatures(self, q_norm, inv_temp, y_norm_max, g, e_star, kappa):
+        delta = kappa * 2.0 ** -10 * q_norm.sqrt() * y_norm_max.sqrt()
+        return e_star / (g / inv_temp + 2 * delta)
+
+    def screen_certify(self, screen_out, e_star, rows_per_tile):
+        l = screen_out[7]
+        a1 = screen_out[2] * l
+        flags = ((l > 0.99) & (l < 1.25) & (a1 >= 0) & (a1 < 0.9 * e_star * math.exp(-e_star))).to(torch.uint8)
+        m = flags.numel()
+        tiles = (m + rows_per_tile - 1) // rows_per_tile
+        listed = [t for t in range(tiles) if not bool(flags[t * rows_per_tile:(t + 1) * rows_per_tile].all())]
+        tile_list = torch.zeros(max(1, tiles), dtype=torch.int32)
+        tile_list[:len(listed)] = torch.tensor(listed, dtype=torch.int32)
+        return flags, tile_list, torch.tensor([len(listed)], dtype=torch.int32)
+
+    def screen_finalize(self, flags, screen_argmin, d, q_split, q_norm, y_split, y_inv_scale, y_norm, y_aux, index_offset,
+                        n_local, n_total, out, argmin):
+        q_hi, q_lo, q_inv = q_split
+        y_hi, y_lo = y_split
+        for r in torch.nonzero(flags).flatten().tolist():
+            k = int(screen_argmin[r])
+            j = k - index_offset
+            out[1:5, r] = 0.0
+            out[6, r] = -math.log(n_total)
+            out[7, r] = 1.0
+            argmin[r] = k
+            if j < 0 or j >= n_local:
+                out[0, r], out[5, r] = math.inf, -math.inf
+                continue
+            yv = y_hi[j].double() + (y_lo[j].double() if y_lo is not None else 0.0)
+            s = ((q_hi[r].double() + q_lo[r].double()) * yv).sum().float()
+            u = (s * (-2.0 * q_inv[r] * y_inv_scale) + q_norm[r]) + y_norm[j]
+            out[0, r] = 0.5 * u
+            out[5, r] = y_aux[j] if y_aux is not None else 0.0
+
+
+def _setup(n=400, d=96, b=12, seed=1):
+    data = torch.rand(n, d, generator=syn.gen(seed)) * 2 - 1
+    data[37] = data[5]                                      # a duplicate: the row of query 5 must never be certified
+    return data, data[:b].clone()
+
+
+def _run(data, x0, temp, screen, block_temps, aux=None):
+    be = SplitFakeBackend()
+    cfg = EngineConfig(precision="f16x3", screen=screen)
+    cfg.max_query_bytes = block_temps * x0.shape[0] * data.shape[1] * 12
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=be), cfg)
+    noise = torch.randn(len(temp), x0.shape[0], data.shape[1], generator=syn.gen(9))
+    res = eng.noised_stats(x0, temp, aux=aux, noise_fn=lambda i: noise[i])
+    return eng, be, res, noise
+
+
+def test_screened_schedule_equals_unscreened_and_policy_stops():
+    data, x0 = _setup()
+    temp = torch.tensor([1e-4, 1e-3, 1e-2, 0.05, 0.2, 0.5, 1.0, 3.0, 10.0, 100.0, 1e3, 1e4])
+    aux = torch.rand(len(data), generator=syn.gen(3))
+    eng_s, be_s, r_s, noise = _run(data, x0, temp, True, 2, aux=aux)
+    eng_u, _, r_u, _ = _run(data, x0, temp, False, 2, aux=aux)
+    rep = eng_s.screen_report
+    assert rep["rows_certified"] > 0 and rep["rows_unscreened"] > 0 and rep["tiles_full_pass"] < rep["tiles_screened"], rep
+    assert torch.equal(r_s["argmin"], r_u["argmin"])
+    for k in ("log_l", "mean_e", "mean_e2", "var_e", "entropy", "aux_mean", "l"):
+        assert torch.isfinite(r_s[k]).all(), k               # nothing of an unlisted tile's NaN records leaks
+        assert torch.allclose(r_s[k], r_u[k], rtol=1e-4, atol=2e-6), (k, (r_s[k] - r_u[k]).abs().max())
+    xn = ((noise * temp.sqrt()[:, None, None] + x0[None]) ** 2).sum(-1)
+    assert ((r_s["e_min"] - r_u["e_min"]).abs() <= 8 * 2.0 ** -24 * (xn + data.shape[1])).all()
+    # the one-product pass ran only on the screened blocks, the full pass only on row-tile lists there
+    assert be_s.calls.count("stats:f16x1:all") == rep["rows_screened"] // (2 * len(x0))
+    assert "stats:f16x3:all" in be_s.calls and "stats:f16x3:list" in be_s.calls
+    # the duplicated training point keeps l = 2: its query is never a certified delta
+    assert (r_s["l"][:4, 5] >= 1.9).all() and (r_s["argmin"][:4, 5] == 5).all()
+
+
+def test_certificate_is_sound_in_fp64():
+    """Every certified row: all other points' weights are below exp(-g) in exact arithmetic."""
+    data, x0 = _setup(n=600, d=128, b=16, seed=4)
+    data[100] = data[3] + 0.02 * torch.randn(128, generator=syn.gen(5))     # close pairs around the decision boundary
+    data[101] = data[4] + 0.2 * torch.randn(128, generator=syn.gen(6))
+    temp = torch.logspace(-3, 1.5, 19)
+    eng, _, res, noise = _run(data, x0, temp, True, 19)
+    g = 17.0 + math.log(len(data))
+    xt = (noise.double() * temp.double().sqrt()[:, None, None] + x0.double()[None])
+    e = 0.5 * orc.pairwise_sqdist(xt.reshape(-1, data.shape[1]), data.double())
+    srt = e.sort(dim=1).values
+    gap = ((srt[:, 1] - srt[:, 0]) / temp.double().repeat_interleave(len(x0))).view(len(temp), len(x0))
+    cert = (res["l"] == 1.0) & (res["mean_e"] == 0.0) & (res["log_l"] == 0.0) & (res["var_e"] == 0.0)
+    assert int(cert.sum()) >= eng.screen_report["rows_certified"] > 0
+    strict = cert & (gap < 80)                      # rows whose unscreened result is not itself an exact delta in fp32
+    assert (gap[strict] > g).all(), gap[strict].min()
+    assert (gap[cert] > g).all()
+    # and the test is not vacuous: some rows with a gap above g were left uncertified (the bound is conservative) ...
+    assert int(((gap > g) & ~cert).sum()) > 0
+    # ... while every row with a gap below g went through the full pass
+    assert not bool((cert & (gap <= g)).any())
+
+
+def test_descending_schedule_backs_off():
+    data, x0 = _setup()
+    temp = torch.tensor([1e4, 3e3, 1e3, 300.0, 100.0, 30.0, 10.0, 1e-2, 1e-3, 1e-4])
+    eng_s, be_s, r_s, _ = _run(data, x0, temp, True, 1)
+    eng_u, _, r_u, _ = _run(data, x0, temp, False, 1)
+    rep = eng_s.screen_report
+    # a failed attempt is repeated only once the temperature has dropped fourfold: 1e4, 1e3, 100, 10 fail; 1e-2.. certify
+    assert be_s.calls.count("stats:f16x1:all") <= len(temp) - 3, be_s.calls
+    assert rep["rows_certified"] > 0 and rep["rows_unscreened"] >= 3 * len(x0), rep
+    for k in ("log_l", "mean_e", "entropy"):
+        assert torch.allclose(r_s[k], r_u[k], rtol=1e-4, atol=2e-6), k
+    assert torch.equal(r_s["argmin"], r_u["argmin"])
