@@ -400,19 +400,20 @@ def run_ours(args):
     if os.environ.get("PDM_BENCH_DENOISER", "1") == "1":
         mq = env_int("PDM_BENCH_DENOISER_M", 10_000)
 
-        def denoise_ms(alpha_bar):
+        def denoise_ms(alpha_bar, engine=None):
+            engine = engine or eng
             torch.manual_seed(11)
             ab = torch.tensor(alpha_bar, device=dev)
             xq = ab.sqrt() * data_full[torch.randint(0, n, (mq,), device=dev)] + (1 - ab).sqrt() * torch.randn(mq, d, device=dev)
             t_rows = ((1 - ab) / ab).expand(mq)
             post = ab.rsqrt().expand(mq)
             for _ in range(max(1, args.warmup)):
-                eng.posterior_mean(xq, t_rows, post=post)
+                engine.posterior_mean(xq, t_rows, post=post)
             barrier()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             d0.record()
             for _ in range(args.steps):
-                eng.posterior_mean(xq, t_rows, post=post)
+                engine.posterior_mean(xq, t_rows, post=post)
             d1.record()
             barrier()
             dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
@@ -429,6 +430,13 @@ def run_ours(args):
                          "precision": precision, "ms_per_step": dms, "value": mq * n / (dms * 1e-3), "unit": UNIT,
                          "algorithmic_tflops": 4.0 * d * mq * n / (dms * 1e-3) / 1e12, "flops_per_pair": 4 * d,
                          "ms_per_step_delta_posteriors": dms_delta}
+        if os.environ.get("PDM_BENCH_SCREEN", "1") == "1":
+            import dataclasses
+            eng_s = PosteriorEngine(ds, dataclasses.replace(cfg, screen=True), group=group)
+            if eng_s.screening_usable():
+                # the same low-noise step with EngineConfig.screen: one-product pass + certificate + gather
+                denoiser_line["ms_per_step_delta_posteriors_screened"] = denoise_ms(0.5, eng_s)
+            del eng_s
         torch.cuda.empty_cache()
 
     # ---- e2e through the reference-facing API with host inputs --------------------------------

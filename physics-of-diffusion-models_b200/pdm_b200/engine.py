@@ -233,6 +233,7 @@ class PosteriorEngine:
         self.screen_report = {"rows_screened": 0, "rows_certified": 0, "tiles_screened": 0, "tiles_full_pass": 0,
                               "rows_unscreened": 0}
         self._screen_t_fail = math.inf
+        self._pm_screen_t = math.inf       # posterior_mean: blocks whose temperatures are all below this mark are screened
         self._screen_t_retry = math.inf    # after a screened block that certified nothing: next attempt at T <= this
         self._y_norm_max = None
         if group is not None:
@@ -308,10 +309,9 @@ class PosteriorEngine:
             self._y_norm_max = v
         return self._y_norm_max
 
-    def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
-                        precision: str):
-        """One-product pass at the fictitious temperature -> certificate per row -> full-precision pass over the row
-        tiles that hold an unproven row -> closed form for the proven rows.  One host read (two scalars) per block."""
+    def _screen_certificate(self, prep: dict, rows: int, inv_temp: Tensor):
+        """One-product pass at the fictitious temperature + certificate: (flags, arg-min of the screening pass, list of
+        row tiles with an unproven row, its length (device), rows per tile)."""
         be, ds = self.backend, self.ds
         g = self.cfg.screen_g if self.cfg.screen_g > 0 else 17.0 + math.log(max(2, ds.n_total))
         inv_t1 = be.screen_temperatures(prep["norms"], inv_temp, self._global_y_norm_max(), g, self.SCREEN_E_STAR,
@@ -320,6 +320,14 @@ class PosteriorEngine:
         out1, arg1 = self._merge(parts1, inv_t1)             # across shards too: every rank sees the same certificate
         rows_per_tile = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)     # the fused kernel's row tile
         flags, tile_list, n_listed = be.screen_certify(out1, self.SCREEN_E_STAR, rows_per_tile)
+        return flags, arg1, tile_list, n_listed, rows_per_tile
+
+    def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
+                        precision: str):
+        """One-product pass at the fictitious temperature -> certificate per row -> full-precision pass over the row
+        tiles that hold an unproven row -> closed form for the proven rows.  One host read (two scalars) per block."""
+        be, ds = self.backend, self.ds
+        flags, arg1, tile_list, n_listed, rows_per_tile = self._screen_certificate(prep, rows, inv_temp)
         open_rows = flags == 0
         t_open = torch.where(open_rows, temp_rows, torch.full_like(temp_rows, math.inf)).min()
         n_open_rows = open_rows.sum()
@@ -661,6 +669,27 @@ class PosteriorEngine:
             inv_temp = (1.0 / temp_rows[r0:r1]).contiguous()
             with ph("prepare"):
                 prep = self._prepare(xf[r0:r1], rows, None, None, None if post is None else post[r0:r1], precision, False)
+            if self.screening_usable():
+                # Certified delta posteriors (the low-noise steps of a sampling trajectory): when the one-product pass proves
+                # every row of the block a delta, the mean is a gather of nearest training points -- no full-precision
+                # distances, no energy tile.  A failed attempt at temperature T is repeated below T/2, a success at T moves
+                # the mark up to 1.5 T (the mark persists across calls: one dataset, one boundary).
+                t_lo, t_hi = (float(v) for v in torch.stack([temp_rows[r0:r1].min(), temp_rows[r0:r1].max()]).cpu())
+                if t_hi < self._pm_screen_t:
+                    with ph("screen"):
+                        flags, arg1, _, n_listed, _ = self._screen_certificate(prep, rows, inv_temp)
+                        proven = int(n_listed.item()) == 0
+                    self.screen_report["pm_rows_screened"] = self.screen_report.get("pm_rows_screened", 0) + rows
+                    if proven:
+                        self._pm_screen_t = max(self._pm_screen_t, 1.5 * t_hi) if math.isfinite(self._pm_screen_t) else self._pm_screen_t
+                        self.screen_report["pm_rows_certified"] = self.screen_report.get("pm_rows_certified", 0) + rows
+                        src = ds.y if values is None else values
+                        local = arg1 - ds.index_offset
+                        own = (local >= 0) & (local < ds.n)
+                        out[r0:r1].copy_(src.index_select(0, local.clamp(0, ds.n - 1)) * own[:, None].to(src.dtype))
+                        continue
+                    self._pm_screen_t = 0.5 * t_lo
+            with ph("prepare"):
                 energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
             with ph("fused+energy"):
                 parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)

@@ -172,3 +172,29 @@ def test_screened_descending_schedule(backend):
     rep = scr.screen_report
     assert rep["rows_certified"] >= 2 * b and rep["rows_unscreened"] >= 2 * b, rep
     assert torch.equal(a_s, a_u)
+
+
+def test_screened_posterior_mean(backend):
+    """Ideal denoiser (Scheduler.true_posterior_mean_x0, diffusion/scheduler/scheduler.py:58-69) with screening: low-noise
+    blocks are answered by a gather of certified nearest points, high-noise blocks by the two contractions."""
+    from pdm_b200 import EmpiricalDataset, EngineConfig, PosteriorEngine
+    from oracle import posterior as orc
+    n, d, b = 3000, 512, 200
+    g = syn.gen(8)
+    data = torch.rand(n, d, generator=g) * 2 - 1
+    ds = EmpiricalDataset(data, backend=backend)
+    scr = PosteriorEngine(ds, EngineConfig(screen=True))
+    ref = PosteriorEngine(ds, EngineConfig(screen=False))
+    for alpha_bar, expect_certified in ((0.999, True), (0.9, True), (0.02, False), (0.95, True)):
+        ab = torch.tensor(alpha_bar)
+        xt = ab.sqrt() * data[:b] + (1 - ab).sqrt() * torch.randn(b, d, generator=g)
+        t_rows, post = ((1 - ab) / ab).expand(b), ab.rsqrt().expand(b)
+        before = scr.screen_report.get("pm_rows_certified", 0)
+        got = scr.posterior_mean(xt, t_rows, post=post).cpu()
+        plain = ref.posterior_mean(xt, t_rows, post=post).cpu()
+        want = orc.posterior_mean_x0(xt, ab, data, dtype=torch.float64)
+        assert (scr.screen_report.get("pm_rows_certified", 0) > before) == expect_certified, (alpha_bar, scr.screen_report)
+        assert (got.double() - want).abs().max().item() < 1e-4, alpha_bar
+        assert (got - plain).abs().max().item() < 1e-4, alpha_bar
+    # after the failure at alpha_bar = 0.02 (T = 49) the mark sits at T / 2; T = 0.053 (alpha_bar = 0.95) is screened again
+    assert scr.screen_report["pm_rows_screened"] == 4 * b
