@@ -294,7 +294,12 @@ def run_ours(args):
         eng_s = PosteriorEngine(dataset, dataclasses.replace(cfg, screen=True), group=group)
         if not eng_s.screening_usable():
             return None
-        ms_s, k_ms_s, k_pairs_s, launches_s, _, _ = measure(eng_s, queries)
+        try:
+            ms_s, k_ms_s, k_pairs_s, launches_s, _, _ = measure(eng_s, queries)
+        except Exception as exc:                    # a secondary entry must never cost the headline line
+            backend.kernel_events = None
+            backend.phase_events = None
+            return {"error": f"{type(exc).__name__}: {exc}"[:300]}
         rep = eng_s.screen_report
         runs = args.warmup + args.steps
         return {"value": pairs_per_step * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / max(1, args.steps),
@@ -435,7 +440,10 @@ def run_ours(args):
             eng_s = PosteriorEngine(ds, dataclasses.replace(cfg, screen=True), group=group)
             if eng_s.screening_usable():
                 # the same low-noise step with EngineConfig.screen: one-product pass + certificate + gather
-                denoiser_line["ms_per_step_delta_posteriors_screened"] = denoise_ms(0.5, eng_s)
+                try:
+                    denoiser_line["ms_per_step_delta_posteriors_screened"] = denoise_ms(0.5, eng_s)
+                except Exception as exc:            # secondary entry
+                    denoiser_line["screened_error"] = f"{type(exc).__name__}: {exc}"[:300]
             del eng_s
         torch.cuda.empty_cache()
 
@@ -505,11 +513,12 @@ def run_ours(args):
         if denoiser_line is not None:
             denoiser_line["roofline_frac"] = denoiser_line["algorithmic_tflops"] / (peaks["tflops"] * world)
             line["denoiser_step"] = denoiser_line
-        if screened is not None:
+        if screened is not None and "value" in screened:
             screened["algorithmic_tflops"] = screened["value"] * 2 * d / 1e12
             screened["roofline_frac"] = screened["algorithmic_tflops"] / (peaks["tflops"] * world)
+        if screened is not None:
             line["screened"] = screened
-        if lattice_line is not None and lattice_line.get("screened"):
+        if lattice_line is not None and lattice_line.get("screened") and "value" in lattice_line["screened"]:
             ls = lattice_line["screened"]
             ls["algorithmic_tflops"] = ls["value"] * 2 * d / 1e12
             ls["roofline_frac"] = ls["algorithmic_tflops"] / (peaks["tflops"] * world)
