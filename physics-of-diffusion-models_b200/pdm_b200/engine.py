@@ -296,6 +296,7 @@ class PosteriorEngine:
     # -- certified delta posteriors ----------------------------------------------------------------
     SCREEN_E_STAR = 50.0       # the screening pass certifies (E1_j - E1_min)/T' > e_star for every other point
     SCREEN_KAPPA = 1.25        # safety factor on the first-order bound 2^-10 ||x|| ||y|| of |x.y - x_hi.y_hi|
+    SCREEN_MIN_CHUNK_TILES = 32   # a block is screened in four chunks when each holds at least this many row tiles
 
     def screening_usable(self) -> bool:
         return (self.cfg.screen and self.precision() in ("f16x3", "f16x2") and hasattr(self.backend, "screen_certify"))
@@ -323,25 +324,77 @@ class PosteriorEngine:
         return flags, arg1, tile_list, n_listed, rows_per_tile
 
     def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
-                        precision: str):
+                        precision: str, ascending: bool = True, wide: bool = True):
         """One-product pass at the fictitious temperature -> certificate per row -> full-precision pass over the row
-        tiles that hold an unproven row -> closed form for the proven rows.  One host read (two scalars) per block."""
+        tiles that hold an unproven row -> closed form for the proven rows.
+
+        A large block that spans a wide temperature range (``wide``: more than 8x -- the wider the range, the likelier the
+        certification boundary lies inside) is screened in tile-aligned quarters: the high-temperature quarter first (mostly proven -> the rest
+        in one launch), otherwise up from the low-temperature end until a quarter leaves more than half of its tiles
+        unproven -- a block that straddles the certification boundary pays the one-product pass for a quarter or two of
+        its rows beyond the boundary, not for all of them.  The full pass is ONE launch over the listed tiles of the
+        screened quarters plus every tile of the unscreened ones.  One host read (three scalars) per screening launch."""
         be, ds = self.backend, self.ds
-        flags, arg1, tile_list, n_listed, rows_per_tile = self._screen_certificate(prep, rows, inv_temp)
-        open_rows = flags == 0
-        t_open = torch.where(open_rows, temp_rows, torch.full_like(temp_rows, math.inf)).min()
-        n_open_rows = open_rows.sum()
-        n_tiles, t_open, n_open_rows = (float(v) for v in torch.stack(
-            [n_listed[0].to(torch.float64), t_open.to(torch.float64), n_open_rows.to(torch.float64)]).cpu())
-        n_tiles = int(n_tiles)
+        dev = be.device
+        rpt = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)          # the fused kernel's row tile
+        tiles = (rows + rpt - 1) // rpt
+        n_chunks = 4 if wide and tiles >= 4 * self.SCREEN_MIN_CHUNK_TILES else 1
+        bounds = [tiles * i // n_chunks for i in range(n_chunks + 1)]
+        flags = torch.zeros(rows, dtype=torch.uint8, device=dev)
+        arg1 = torch.zeros(rows, dtype=torch.int64, device=dev)
+        listed, n_tiles = [], 0
         rep = self.screen_report
-        rep["rows_screened"] += rows
-        rep["rows_certified"] += rows - int(n_open_rows)
-        rep["tiles_screened"] += (rows + rows_per_tile - 1) // rows_per_tile
-        rep["tiles_full_pass"] += n_tiles
-        self._screen_t_fail = min(self._screen_t_fail, t_open)
-        if int(n_open_rows) == rows:
-            self._screen_t_retry = 0.25 * t_open
+
+        def leave(ta, tb):                                  # tiles ta..tb-1 go to the full pass unscreened
+            nonlocal n_tiles
+            listed.append(torch.arange(ta, tb, dtype=torch.int32, device=dev))
+            n_tiles += tb - ta
+            rep["rows_unscreened"] += min(rows, tb * rpt) - ta * rpt
+
+        def screen(ta, tb) -> int:                          # one-product pass + certificate on tiles ta..tb-1
+            nonlocal n_tiles
+            r0, r1 = ta * rpt, min(rows, tb * rpt)
+            sub = {k: (v[r0:r1] if isinstance(v, Tensor) else v) for k, v in prep.items()}
+            f, a, tl, nl, _ = self._screen_certificate(sub, r1 - r0, inv_temp[r0:r1])
+            flags[r0:r1] = f
+            arg1[r0:r1] = a
+            open_rows = f == 0
+            t_rows = temp_rows[r0:r1]
+            t_open = torch.where(open_rows, t_rows, torch.full_like(t_rows, math.inf)).min()
+            n_l, t_open, n_open = (float(v) for v in torch.stack(
+                [nl[0].to(torch.float64), t_open.to(torch.float64), open_rows.sum().to(torch.float64)]).cpu())
+            n_l, n_open = int(n_l), int(n_open)
+            if n_l > 0:
+                listed.append(tl[:n_l] + ta)
+                n_tiles += n_l
+            rep["rows_screened"] += r1 - r0
+            rep["rows_certified"] += (r1 - r0) - n_open
+            rep["tiles_screened"] += tb - ta
+            rep["tiles_full_pass"] += n_l
+            self._screen_t_fail = min(self._screen_t_fail, t_open)
+            if n_open == r1 - r0:
+                self._screen_t_retry = min(self._screen_t_retry, 0.25 * t_open)
+            return n_l
+
+        if n_chunks == 1:
+            screen(0, tiles)
+        else:
+            # Probe the high-temperature chunk first: if at least half of its tiles are proven, so will nearly all of the rest be,
+            # and the rest goes through in one launch.  Otherwise walk the remaining chunks up from the low-temperature
+            # end and stop after the first one that leaves more than half of its tiles unproven.
+            top = n_chunks - 1 if ascending else 0
+            rest = (0, bounds[top]) if ascending else (bounds[1], tiles)
+            if 2 * screen(bounds[top], bounds[top + 1]) <= bounds[top + 1] - bounds[top]:
+                screen(*rest)
+            else:
+                stopped = False
+                for c in (range(0, top) if ascending else range(n_chunks - 1, 0, -1)):
+                    ta, tb = bounds[c], bounds[c + 1]
+                    if stopped:
+                        leave(ta, tb)
+                    else:
+                        stopped = 2 * screen(ta, tb) > tb - ta
+        tile_list = torch.cat(listed).contiguous() if len(listed) > 1 else (listed[0].contiguous() if listed else None)
         if n_tiles > 0:
             parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=n_tiles)
             out, argmin = self._merge(parts, inv_temp)
@@ -363,7 +416,7 @@ class PosteriorEngine:
 
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
                     sigma: Optional[Tensor] = None, post: Optional[Tensor] = None, aux: Optional[Tensor] = None,
-                    prep: Optional[dict] = None, screen: bool = False):
+                    prep: Optional[dict] = None, screen: bool = False, ascending: bool = True, wide: bool = True):
         """Statistics for ``rows`` query rows; returns (out (8, rows), argmin (rows,)) device tensors.
         Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional); ``prep`` passes
         already prepared operands (rank-sliced preparation of a sharded run) instead."""
@@ -378,7 +431,7 @@ class PosteriorEngine:
                 prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
         if screen and self.screening_usable():
             with ph("fused"):
-                return self._screened_block(prep, rows, temp_rows.to(torch.float32), inv_temp, aux, precision)
+                return self._screened_block(prep, rows, temp_rows.to(torch.float32), inv_temp, aux, precision, ascending, wide)
         self.screen_report["rows_unscreened"] += rows
         with ph("fused"):
             parts = self._local_partials(prep, rows, inv_temp, aux, precision)
@@ -477,6 +530,8 @@ class PosteriorEngine:
             t1 = min(n_t, t0 + t_per_block)
             nb = t1 - t0
             screen = screen_on and float(temp_host[t0:t1].min()) < min(self._screen_t_fail, self._screen_t_retry)
+            asc = not screen or bool(temp_host[t0] <= temp_host[t1 - 1])
+            wide = screen and float(temp_host[t0:t1].max()) > 8.0 * float(temp_host[t0:t1].min())
             ph = getattr(self.backend, "phase", None)
             if ph is None:
                 import contextlib
@@ -488,7 +543,8 @@ class PosteriorEngine:
                     base = gen.get_offset()
                     prep = self._fused_prepare(gen.initial_seed(), base, step_off, x0f, temp[t0:t1], x0_absmax)
                     gen.set_offset(base + nb * step_off)
-                o, i = self.stats_block(x0f, nb * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep, screen=screen)
+                o, i = self.stats_block(x0f, nb * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep, screen=screen,
+                                        ascending=asc, wide=wide)
                 outs.append(o)
                 idxs.append(i)
                 continue
@@ -506,7 +562,7 @@ class PosteriorEngine:
                                group=self.group)
             t_rows = temp[t0:t1].repeat_interleave(b)
             o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux,
-                                    screen=screen)
+                                    screen=screen, ascending=asc, wide=wide)
             outs.append(o)
             idxs.append(i)
         out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]

@@ -198,3 +198,32 @@ def test_screened_posterior_mean(backend):
         assert (got - plain).abs().max().item() < 1e-4, alpha_bar
     # after the failure at alpha_bar = 0.02 (T = 49) the mark sits at T / 2; T = 0.053 (alpha_bar = 0.95) is screened again
     assert scr.screen_report["pm_rows_screened"] == 4 * b
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24, 25, 26])
+def test_screened_sweep_over_datasets_and_ragged_shapes(backend, seed):
+    """Seeded sweep: clustered / heavy-tailed / pixel / duplicated datasets, shapes ragged against every tile size,
+    unsorted temperatures.  Every row -- certified or not -- must stay inside the oracle tolerance."""
+    g = syn.gen(seed)
+    n = int(torch.randint(300, 2600, (1,), generator=g))
+    d = int(torch.randint(8, 90, (1,), generator=g)) * 8
+    b = int(torch.randint(5, 140, (1,), generator=g))
+    kind = seed % 4
+    if kind == 0:                                               # tight Gaussian clusters: many close pairs
+        centres = torch.randn(7, d, generator=g) * 2
+        data = centres[torch.randint(0, 7, (n,), generator=g)] + 0.05 * torch.randn(n, d, generator=g)
+    elif kind == 1:                                             # heavy tails: row norms spread over decades
+        data = torch.randn(n, d, generator=g) * torch.exp(1.5 * torch.randn(n, 1, generator=g))
+    elif kind == 2:                                             # 8-bit pixels with repeated images
+        px = torch.randint(0, 256, (n, d), generator=g, dtype=torch.uint8)
+        px[n // 2:n // 2 + 20] = px[:20]
+        data = (px.float() / 255 - 0.5) / 0.5
+    else:                                                       # uniform cube, offset from the origin
+        data = torch.rand(n, d, generator=g) * 2 + 3
+    x0 = data[torch.randint(0, n, (b,), generator=g)].clone()
+    temp = torch.exp(torch.empty(9).uniform_(math.log(1e-5), math.log(1e4), generator=g))
+    temp = temp.sort().values if seed % 2 else temp             # odd seeds: ascending; even seeds: as drawn
+    scr, (o_s, a_s), (o_u, a_u), ref = run_both(backend, data, x0, temp, block_temps=2)
+    check_stats(o_s, a_s, ref, what=f"screened sweep seed {seed} kind {kind} n={n} d={d} b={b}")
+    agree = ref["f32"]["argmin"] == ref["f64"]["argmin"]
+    assert torch.equal(a_s[agree], a_u[agree])

@@ -169,3 +169,70 @@ def test_descending_schedule_backs_off():
     for k in ("log_l", "mean_e", "entropy"):
         assert torch.allclose(r_s[k], r_u[k], rtol=1e-4, atol=2e-6), k
     assert torch.equal(r_s["argmin"], r_u["argmin"])
+
+
+def _dataset(kind: int, n: int, d: int, g) -> torch.Tensor:
+    if kind == 0:                                               # tight clusters: many near pairs
+        centres = torch.randn(5, d, generator=g) * 2
+        return centres[torch.randint(0, 5, (n,), generator=g)] + 0.05 * torch.randn(n, d, generator=g)
+    if kind == 1:                                               # heavy tails: row norms over decades
+        return torch.randn(n, d, generator=g) * torch.exp(1.5 * torch.randn(n, 1, generator=g))
+    if kind == 2:                                               # 8-bit pixels, some repeated
+        px = torch.randint(0, 256, (n, d), generator=g, dtype=torch.uint8)
+        px[n // 2:n // 2 + 10] = px[:10]
+        return (px.float() / 255 - 0.5) / 0.5
+    return torch.rand(n, d, generator=g) * 2 + 3                # cube away from the origin
+
+
+def test_certificate_soundness_sweep():
+    """fp64 check of every certified row over dataset families and seeds (no certified row with a gap below g*T)."""
+    total_cert = 0
+    for seed in range(8):
+        g = syn.gen(100 + seed)
+        n, d, b = 300 + 37 * seed, 64 + 8 * seed, 10
+        data = _dataset(seed % 4, n, d, g)
+        x0 = data[torch.randint(0, n, (b,), generator=g)].clone()
+        temp = torch.logspace(-5, 3, 17)
+        eng, _, res, noise = _run(data, x0, temp, True, 17)
+        gthr = 17.0 + math.log(n)
+        xt = (noise.double() * temp.double().sqrt()[:, None, None] + x0.double()[None])
+        e = 0.5 * orc.pairwise_sqdist(xt.reshape(-1, d), data.double())
+        srt = e.sort(dim=1).values
+        gap = ((srt[:, 1] - srt[:, 0]) / temp.double().repeat_interleave(b)).view(len(temp), b)
+        # rows the engine itself reports as certified: closed form AND counted by the report
+        cert = (res["l"] == 1.0) & (res["mean_e"] == 0.0) & (res["log_l"] == 0.0) & (res["var_e"] == 0.0) & (gap < 80)
+        assert (gap[cert] > gthr).all(), (seed, float(gap[cert].min()))
+        total_cert += eng.screen_report["rows_certified"]
+        # arg-min of certified rows is the fp64 arg-min
+        amin64 = e.argmin(dim=1).view(len(temp), b)
+        closed = (res["l"] == 1.0) & (res["log_l"] == 0.0)
+        assert torch.equal(res["argmin"][closed & (gap > 1e-3)], amin64[closed & (gap > 1e-3)]), seed
+    assert total_cert > 200
+
+
+def test_block_screened_in_chunks_from_its_low_temperature_end(monkeypatch):
+    """A block of 16 row tiles is screened in quarters: the high-temperature quarter first; if that fails, up from the
+    low-temperature end until a quarter is mostly unproven.  The full pass is one launch over listed + unscreened tiles.
+    Ascending and descending order of the same schedules."""
+    monkeypatch.setattr(PosteriorEngine, "SCREEN_MIN_CHUNK_TILES", 1)
+    data, x0 = _setup(n=400, d=96, b=16)                        # 16 rows per temperature = 2 row tiles of 8
+    b = len(x0)
+    cases = (
+        # schedule (quarters of 2 temperatures)                      one-product launches, unscreened rows, certified >=
+        (torch.tensor([1e-4, 1e-3, 10.0, 100.0, 1e3, 1e4, 1e5, 1e6]), 3, 2 * b, 2 * b - 2),   # top fails, q0 ok, q1 fails: stop
+        (torch.tensor([1e-4, 1e-3, 1e-2, 0.1, 10.0, 100.0, 1e3, 1e4]), 4, 0, 4 * b - 4),      # boundary in the third quarter
+        (torch.tensor([1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 2e-2, 5e-2, 0.1]), 2, 0, 8 * b - 8),     # top proven: the rest in one launch
+    )
+    for asc, want_x1, want_unscreened, want_cert in cases:
+        for temp in (asc, asc.flip(0)):
+            eng_s, be_s, r_s, _ = _run(data, x0, temp, True, len(temp))      # ONE block
+            eng_u, _, r_u, _ = _run(data, x0, temp, False, len(temp))
+            rep = eng_s.screen_report
+            assert be_s.calls.count("stats:f16x1:all") == want_x1, (temp, be_s.calls)
+            assert be_s.calls.count("stats:f16x3:list") <= 1 and "stats:f16x3:all" not in be_s.calls
+            assert rep["rows_unscreened"] == want_unscreened and rep["rows_certified"] >= want_cert, (temp, rep)
+            assert rep["rows_screened"] + rep["rows_unscreened"] == len(temp) * b
+            for k in ("log_l", "mean_e", "mean_e2", "var_e", "entropy", "l"):
+                assert torch.isfinite(r_s[k]).all(), k
+                assert torch.allclose(r_s[k], r_u[k], rtol=1e-4, atol=2e-6), (k, (r_s[k] - r_u[k]).abs().max())
+            assert torch.equal(r_s["argmin"], r_u["argmin"])
