@@ -374,6 +374,8 @@ class PosteriorEngine:
             self._screen_t_fail = min(self._screen_t_fail, t_open)
             if n_open == r1 - r0:
                 self._screen_t_retry = min(self._screen_t_retry, 0.25 * t_open)
+            elif 2 * n_l <= tb - ta:
+                self._screen_t_retry = math.inf            # the certifiable range has been reached
             return n_l
 
         if n_chunks == 1:
