@@ -15,6 +15,7 @@
 #include "pdm_common.cuh"
 
 #include <curand_kernel.h>
+#include <stdlib.h>
 
 namespace pdm {
 
@@ -88,6 +89,70 @@ __global__ void __launch_bounds__(256) noised_rows_philox_kernel(NoisedParams p)
     }
 }
 
+// Four adjacent Philox subsequences per thread.  Subsequences 4j .. 4j+3 of torch's launch fill the adjacent elements
+// 4j + G*ii + 4G*k + (0..3) (G is a multiple of 256), so a thread that owns all four reads x0 as one float4, looks its
+// row and scale up once and stores 8 bytes of hi and of lo (or 16 bytes of fp32) per step instead of four scalar
+// round trips -- the per-element index / load / store overhead of the one-subsequence kernel above was about as large
+// as Philox + Box-Muller themselves.  Same subsequences, same counters, same cuRAND device functions: the same bits.
+// Needs d % 4 == 0 (a group of four never straddles a row) -- guaranteed on the split path (d % 8 == 0).
+template <bool kX, bool kSplit>
+__global__ void __launch_bounds__(64) noised_rows_philox4_kernel(NoisedParams p) {
+    const unsigned idx0 = 4u * (blockIdx.x * blockDim.x + threadIdx.x);          // first subsequence; < draw_threads
+    const unsigned t = blockIdx.y;
+    const unsigned numel = (unsigned)(p.b * p.d), G = (unsigned)p.draw_threads, d = (unsigned)p.d;
+    const unsigned gq = G / d, gr = G - gq * d;
+    const float sig = p.sigma[t];
+    const float* __restrict__ x0 = p.x0;
+    float* __restrict__ xo = kX ? p.x_out + (size_t)t * numel : nullptr;
+    __half* __restrict__ hi = kSplit ? p.hi + (size_t)t * numel : nullptr;
+    __half* __restrict__ lo = kSplit ? p.lo + (size_t)t * numel : nullptr;
+    const float* __restrict__ inv_scale = kSplit ? p.inv_scale + (size_t)t * p.b : nullptr;
+    curandStatePhilox4_32_10_t st[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        curand_init(p.seed, (unsigned long long)(idx0 + s), p.offset + (unsigned long long)t * p.offset_step, &st[s]);
+    unsigned li = idx0, b = idx0 / d, k = idx0 - (idx0 / d) * d;
+    while (li < numel) {
+        float rv[4][4];                                  // [subsequence][ii]
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float4 r = curand_normal4(&st[s]);
+            rv[s][0] = r.x; rv[s][1] = r.y; rv[s][2] = r.z; rv[s][3] = r.w;
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            if (li < numel) {                            // numel % 4 == 0: the four elements are in or out together
+                const float4 x = __ldg(reinterpret_cast<const float4*>(x0 + li));
+                float v[4];
+                v[0] = __fadd_rn(__fmul_rn(rv[0][ii], sig), x.x);
+                v[1] = __fadd_rn(__fmul_rn(rv[1][ii], sig), x.y);
+                v[2] = __fadd_rn(__fmul_rn(rv[2][ii], sig), x.z);
+                v[3] = __fadd_rn(__fmul_rn(rv[3][ii], sig), x.w);
+                if (kX) *reinterpret_cast<float4*>(xo + li) = make_float4(v[0], v[1], v[2], v[3]);
+                if (kSplit) {
+                    const float scale = __uint_as_float(0x7f000000u - __float_as_uint(__ldg(inv_scale + b)));
+                    __half h[4], l[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const float vs = v[s] * scale;
+                        h[s] = __float2half_rn(vs);
+                        l[s] = __float2half_rn(vs - __half2float(h[s]));
+                    }
+                    uint2 ph, pl;
+                    ph.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
+                    ph.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
+                    pl.x = (unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16);
+                    pl.y = (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16);
+                    *reinterpret_cast<uint2*>(hi + li) = ph;
+                    *reinterpret_cast<uint2*>(lo + li) = pl;
+                }
+            }
+            li += G;
+            if (kSplit) { b += gq; k += gr; if (k >= d) { k -= d; ++b; } }
+        }
+    }
+}
+
 // ||(hi + lo) * inv_scale||^2 per row, fp64 accumulation: the norm of exactly the vector the tensor cores see.
 __global__ void __launch_bounds__(256) split_row_norms_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
                                                               long long ldh, const float* __restrict__ inv_scale,
@@ -150,6 +215,18 @@ extern "C" int pdm_noised_rows_philox(uint64_t seed, uint64_t offset, uint64_t o
         const int64_t rows = n_draws * b;
         noised_row_scales_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(x0_absmax, sigma, b, rows, inv_scale);
         PDM_CUDA_CHECK(cudaGetLastError());
+    }
+    static const bool one_per_thread = getenv("PDM_PHILOX_SCALAR") && atoi(getenv("PDM_PHILOX_SCALAR")) != 0;   // dev knob
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(x0) & 15) == 0 && (!x_out || (reinterpret_cast<uintptr_t>(x_out) & 15) == 0) &&
+                           (!hi || ((reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0));
+    if (d % 4 == 0 && aligned16 && !one_per_thread) {
+        // four adjacent subsequences per thread: draw_threads / 4 threads in blocks of 64 = draw_threads / 256 blocks
+        dim3 grid4((unsigned)(draw_threads / 256), (unsigned)n_draws);
+        if (x_out && hi)  noised_rows_philox4_kernel<true, true><<<grid4, 64, 0, as_stream(stream)>>>(p);
+        else if (hi)      noised_rows_philox4_kernel<false, true><<<grid4, 64, 0, as_stream(stream)>>>(p);
+        else              noised_rows_philox4_kernel<true, false><<<grid4, 64, 0, as_stream(stream)>>>(p);
+        PDM_CUDA_CHECK(cudaGetLastError());
+        return PDM_OK;
     }
     dim3 grid((unsigned)(draw_threads / 256), (unsigned)n_draws);
     if (x_out && hi)  noised_rows_philox_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(p);
