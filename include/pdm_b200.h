@@ -53,6 +53,11 @@ extern "C" {
                                    lattice (8-bit images: y*255 is an integer), y_lo == 0 and the third
                                    product of F16X3 vanishes identically -- same accuracy, 2/3 of the MMAs */
 
+#define PDM_PREC_F8X1       4   /* tcgen05 kind::f8f6f4 on E4M3 operands (4-bit significands, twice the MMA rate): the first
+                                   stage of the screening cascade only.  q_hi / y_hi point at E4M3 BYTES from
+                                   pdm_split_to_e4m3 (ldqh / ldyh in bytes, multiples of 16); q_inv_scale[r] and y_inv_scale
+                                   are the factors that turn the byte operands back into values                   */
+
 /* floats per partial record: m, l, A1, A2, AUX, argmin_lo(bits), argmin_hi(bits), reserved */
 #define PDM_PART_STRIDE 8
 
@@ -244,6 +249,22 @@ int pdm_screen_temperatures(const float* q_norm, const float* inv_temp, int64_t 
                             float g, float e_star, float kappa, float* inv_temp_screen, pdm_stream_t stream);
 int pdm_screen_certify(const float* screen_out, int64_t M, float e_star, int32_t rows_per_tile,
                        uint8_t* flags, int32_t* tile_list, int32_t* n_tiles_out, pdm_stream_t stream);
+/* First stage of the screening cascade: the same certificate from an E4M3 pass (PDM_PREC_F8X1, twice the MMA rate of
+ * the fp16 one-product pass).  pdm_split_to_e4m3 rounds the split operands to bytes, out8 = e4m3((hi + lo)/16), and
+ * returns the EXACT deviation of every row, err[r] = ||(hi + lo)_r - 16 out8_r|| in the split's scaled units (lo may be
+ * NULL); with ex = err_q * q_inv_scale and ey = max_j err_y * y_inv_scale,
+ *     |x.y - x8.y8| <= ex ||y|| + (||x|| + ex) ey  =: delta / kappa
+ * holds rigorously, whatever the data.  pdm_screen_temperatures_f8 forms 1/T' = e_star / (g T + 2 delta) from it; the pass
+ * itself is pdm_posterior_stats with q_hi / y_hi = the byte operands, q_inv_scale = 16 * the split's inverse scales and
+ * y_inv_scale = 16 / scale.  Rows it leaves unproven go to the fp16 one-product stage (row_tiles), then to the full pass.
+ * pdm_screen_tile_list rebuilds the tile list from a combined flag array. */
+int pdm_split_to_e4m3(const uint16_t* hi, const uint16_t* lo, int64_t ldh, int64_t rows, int64_t d,
+                      uint8_t* out8, int64_t ld8, float* err, pdm_stream_t stream);
+int pdm_screen_temperatures_f8(const float* q_norm, const float* q_err, const float* q_inv_scale,
+                               const float* inv_temp, int64_t M, const float* y_norm_max, const float* y_err_max,
+                               float g, float e_star, float kappa, float* inv_temp_screen, pdm_stream_t stream);
+int pdm_screen_tile_list(const uint8_t* flags, int64_t M, int32_t rows_per_tile, int32_t* tile_list,
+                         int32_t* n_tiles_out, pdm_stream_t stream);
 int pdm_screen_finalize(const uint8_t* flags, const int64_t* screen_argmin, int64_t M, int64_t d,
                         const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldqh, const float* q_inv_scale,
                         const float* q_norm,

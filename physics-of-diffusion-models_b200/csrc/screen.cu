@@ -11,6 +11,8 @@
 //                               (one warp per proven row: 8*d B read)
 #include "pdm_common.cuh"
 
+#include <cuda_fp8.h>
+
 namespace pdm {
 
 __global__ void __launch_bounds__(256) screen_temperatures_kernel(const float* __restrict__ q_norm,
@@ -65,6 +67,56 @@ __global__ void __launch_bounds__(1024) tile_list_kernel(const uint8_t* __restri
         __syncthreads();
     }
     if (threadIdx.x == 0) *n_out = base;
+}
+
+// E4M3 operands for the first stage of the screening cascade: out8[r,k] = e4m3((hi + lo)[r,k] / 16) (|hi| <= 4096, so the
+// bytes stay within +-256 of E4M3's +-448), and err[r] = ||(hi + lo)_r - 16 * out8_r|| in the split's scaled units --
+// the EXACT rounding deviation of that row (fp64 accumulation), which is what makes the stage's error bound rigorous
+// without any assumption about the format.  One warp per row; columns d..ld8-1 are zero.
+__global__ void __launch_bounds__(256) split_to_e4m3_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                            int64_t ldh, int64_t rows, int64_t d, uint8_t* __restrict__ out8,
+                                                            int64_t ld8, float* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const __half2* h2 = reinterpret_cast<const __half2*>(hi + r * ldh);
+    const __half2* l2 = lo ? reinterpret_cast<const __half2*>(lo + r * ldh) : nullptr;
+    uint16_t* o2 = reinterpret_cast<uint16_t*>(out8 + r * ld8);
+    double acc = 0.0;
+    for (int64_t i = lane; i < (ld8 >> 1); i += 32) {            // ld8 is even; pairs of columns
+        float2 v = make_float2(0.f, 0.f);
+        if (2 * i < d) {                                         // d is even on the split path (ldh % 8 == 0 == d % 8)
+            const float2 a = __half22float2(h2[i]);
+            const float2 c = l2 ? __half22float2(l2[i]) : make_float2(0.f, 0.f);
+            v = make_float2(a.x + c.x, a.y + c.y);               // hi + lo rounded to fp32: 2^-24 relative, against the
+                                                                 // byte's 2^-4 -- inside the round-up factor below
+        }
+        const __nv_fp8_storage_t b0 = __nv_cvt_float_to_fp8(v.x * 0.0625f, __NV_SATFINITE, __NV_E4M3);
+        const __nv_fp8_storage_t b1 = __nv_cvt_float_to_fp8(v.y * 0.0625f, __NV_SATFINITE, __NV_E4M3);
+        o2[i] = (uint16_t)b0 | ((uint16_t)b1 << 8);
+        const float d0 = __half2float(__half(__nv_cvt_fp8_to_halfraw(b0, __NV_E4M3))) * 16.f;
+        const float d1 = __half2float(__half(__nv_cvt_fp8_to_halfraw(b1, __NV_E4M3))) * 16.f;
+        const double e0 = (double)v.x - (double)d0, e1 = (double)v.y - (double)d1;
+        acc += e0 * e0 + e1 * e1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && err) err[r] = (float)(sqrt(acc) * (1.0 + 1e-5));      // rounded up
+}
+
+// 1/T' for the E4M3 stage: delta = kappa * (ex * ||y||max + (||x|| + ex) * ey) with the exact per-row deviations.
+__global__ void __launch_bounds__(256) screen_temperatures_f8_kernel(const float* __restrict__ q_norm, const float* __restrict__ q_err,
+                                                                     const float* __restrict__ q_inv_scale,
+                                                                     const float* __restrict__ inv_temp, int64_t M,
+                                                                     const float* __restrict__ y_norm_max,
+                                                                     const float* __restrict__ y_err_max, float g, float e_star,
+                                                                     float kappa, float* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const float ex = q_err[r] * q_inv_scale[r], ey = __ldg(y_err_max);
+    const float delta = kappa * (ex * sqrtf(__ldg(y_norm_max)) + (sqrtf(q_norm[r]) + ex) * ey);
+    const float t = 1.f / inv_temp[r];
+    out[r] = e_star / fmaf(g, t, 2.f * delta);
 }
 
 struct FinalizeParams {
@@ -164,6 +216,38 @@ extern "C" int pdm_screen_certify(const float* screen_out, int64_t M, float e_st
         certify_rows_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(screen_out, M, a1_max, flags);
         PDM_CUDA_CHECK(cudaGetLastError());
     }
+    tile_list_kernel<<<1, 1024, 0, as_stream(stream)>>>(flags, M, rows_per_tile, tile_list, n_tiles_out);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_split_to_e4m3(const uint16_t* hi, const uint16_t* lo, int64_t ldh, int64_t rows, int64_t d,
+                                 uint8_t* out8, int64_t ld8, float* err, pdm_stream_t stream) {
+    PDM_REQUIRE(hi && out8 && rows >= 0 && d > 0 && d % 2 == 0 && ldh >= d && ldh % 2 == 0 && ld8 >= d && ld8 % 16 == 0,
+                "pdm_split_to_e4m3: bad arguments (d even, ld8 a multiple of 16)");
+    if (rows == 0) return PDM_OK;
+    split_to_e4m3_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), ldh, rows, d, out8, ld8, err);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_screen_temperatures_f8(const float* q_norm, const float* q_err, const float* q_inv_scale,
+                                          const float* inv_temp, int64_t M, const float* y_norm_max, const float* y_err_max,
+                                          float g, float e_star, float kappa, float* inv_temp_screen, pdm_stream_t stream) {
+    PDM_REQUIRE(q_norm && q_err && q_inv_scale && inv_temp && y_norm_max && y_err_max && inv_temp_screen && M >= 0,
+                "pdm_screen_temperatures_f8: bad arguments");
+    PDM_REQUIRE(g > 0.f && e_star >= 2.f && e_star <= 80.f && kappa >= 1.f, "pdm_screen_temperatures_f8: bad parameters");
+    if (M == 0) return PDM_OK;
+    screen_temperatures_f8_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(
+        q_norm, q_err, q_inv_scale, inv_temp, M, y_norm_max, y_err_max, g, e_star, kappa, inv_temp_screen);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_screen_tile_list(const uint8_t* flags, int64_t M, int32_t rows_per_tile, int32_t* tile_list,
+                                    int32_t* n_tiles_out, pdm_stream_t stream) {
+    PDM_REQUIRE(flags && tile_list && n_tiles_out && M >= 0 && rows_per_tile >= 1, "pdm_screen_tile_list: bad arguments");
     tile_list_kernel<<<1, 1024, 0, as_stream(stream)>>>(flags, M, rows_per_tile, tile_list, n_tiles_out);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;

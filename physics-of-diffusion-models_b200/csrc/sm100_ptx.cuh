@@ -157,6 +157,23 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
             ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// kind::f8f6f4 with both operands E4M3 (format 0): K = 32 one-byte elements per instruction, i.e. the same 32-byte K
+// slice and the same instruction descriptor bits as kind::f16 (cute/arch/mma_sm100_desc.hpp: a_format / b_format 0 is
+// F16 for kind::f16 and E4M3 for kind::f8f6f4); twice the multiply rate.
+template <int CG>
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // Arrive on `bar` (same offset in every CTA of the MMA group) once all previously issued MMAs retire.
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -139,7 +139,9 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 // 50x the fp32 SGEMM noise of the reference).  So the accumulator only ever holds `flush_kb` k-blocks
 // (12 MMAs at flush_kb = 1); the epilogue warps drain it into fp32 registers with round-to-nearest adds
 // while the MMA warp fills the other accumulator stage, and the statistics are computed from the registers.
-template <int CG, int TERMS, int EPI, bool AUX>
+// F8: one-product mode on E4M3 operands (TERMS == 1 only): a k-block is 128 one-byte elements (the same 128-byte
+// swizzled row, the same four K slices of 32 bytes), MMAs are kind::f8f6f4.  Used by the screening cascade.
+template <int CG, int TERMS, int EPI, bool AUX, bool F8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -221,7 +223,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         { PDM_STALL_BEGIN(); mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns); PDM_STALL_END(st_empty); }
                         const uint32_t dst = smem_base + (uint32_t)stage * C::kStageBytes;
                         const uint32_t fb = full_bar(stage);
-                        const int32_t kc = kb * kBlockK;
+                        const int32_t kc = kb * (F8 ? 2 * kBlockK : kBlockK);          // element coordinate of the k-block
                         if (CG == 1) {
                             mbar_arrive_expect_tx(fb, C::kStageBytes);
                             tma_load_2d(dst, &tm_a_hi, fb, kc, a_row, p.hint_a);
@@ -279,8 +281,9 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t ko = (uint64_t)(k * 2);
-                                umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc,
-                                             (TERMS >= 2 || kb > kb0 || k > 0) ? 1u : 0u);
+                                if (F8) umma_f8<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                                else umma_f16<CG>(d_tmem, a_hi + ko, b_hi + ko, C::kIdesc,
+                                                  (TERMS >= 2 || kb > kb0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit<CG>(empty_bar(stage));                 // smem slot reusable once these retire
                             if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(as)); // chunk accumulator complete
@@ -314,7 +317,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 ? (p.energy_out && (p.lde % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.energy_out) & 15) == 0))
                 : ((p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0));
             // |y_k| <= 4096 * y_inv_scale by construction of the split, so |y|^2 <= d_pad * (4096 y_inv_scale)^2
-            const float yn_bound = (float)(p.num_kb * kBlockK) * (4096.f * p.y_inv_scale) * (4096.f * p.y_inv_scale);
+            const float yn_bound = (float)(p.num_kb * (F8 ? 2 * kBlockK : kBlockK)) * (4096.f * p.y_inv_scale) * (4096.f * p.y_inv_scale);
             const float half_mult = 0.5f * p.energy_mult;
             for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
                 const int tile = p.tile_list ? __ldg(p.tile_list + mt) : mt;
@@ -539,10 +542,28 @@ static int make_tile_map(CUtensorMap* map, const uint16_t* base, int64_t rows, i
     return PDM_OK;
 }
 
-template <int CG, int TERMS, int EPI, bool AUX>
+// E4M3 matrix (rows, k) of bytes with leading dimension ld -> box of 128 k-elements x 128 rows, 128B swizzle.
+static int make_tile_map_u8(CUtensorMap* map, const uint8_t* base, int64_t rows, int64_t k, int64_t ld) {
+    EncodeTiledFn fn;
+    int rc = get_encode_fn(&fn);
+    if (rc != PDM_OK) return rc;
+    PDM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 16 == 0 && ld >= k,
+                "e4m3 operand must be 16-byte aligned with ld %% 16 == 0 and ld >= k");
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * kBlockK), (cuuint32_t)kRowsPerCta};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (u8) failed with CUresult %d", (int)r); return PDM_ERR_CUDA; }
+    return PDM_OK;
+}
+
+template <int CG, int TERMS, int EPI, bool AUX, bool F8 = false>
 static int launch_variant(const CUtensorMap* maps, const GemmParams& p, int sm_count, cudaStream_t stream) {
     using C = Cfg<CG, TERMS>;
-    auto kern = fused_gemm_kernel<CG, TERMS, EPI, AUX>;
+    auto kern = fused_gemm_kernel<CG, TERMS, EPI, AUX, F8>;
     static std::atomic<uint64_t> configured{0};          // one bit per device ordinal (function attributes are per device)
     int dev = 0;
     PDM_CUDA_CHECK(cudaGetDevice(&dev));
@@ -656,7 +677,9 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     if (rc != PDM_OK) return rc;
     const int cg = a.cta_group;
     const int terms = a.precision == PDM_PREC_F16X3 ? 3 : a.precision == PDM_PREC_F16X2 ? 2 : 1;
+    const bool f8 = a.precision == PDM_PREC_F8X1;
     PDM_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
+    PDM_REQUIRE(!f8 || !a.y_aux, "the e4m3 mode is a screening pass: no aux accumulator");
     PDM_REQUIRE(a.q_hi && a.y_hi && a.q_inv_scale && a.y_inv_scale > 0.f, "tensor path: q_hi / y_hi / scales missing");
     PDM_REQUIRE(terms < 2 || a.q_lo, "f16x2 / f16x3 need the lo part of the queries");
     PDM_REQUIRE(terms < 3 || a.y_lo, "f16x3 needs the lo part of the dataset");
@@ -664,14 +687,22 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
                 "y_norm / y_aux must be 16-byte aligned");
     PDM_REQUIRE(a.M < (1ll << 31) - 512 && a.N < (1ll << 31) - 512, "M and N must fit in int32 for the TMA coordinates");
     CUtensorMap maps[4];
+    if (f8) {       // q_hi / y_hi carry E4M3 bytes, leading dimensions in bytes
+        const uint8_t* q8 = reinterpret_cast<const uint8_t*>(a.q_hi);
+        const uint8_t* y8 = reinterpret_cast<const uint8_t*>(a.y_hi);
+        if ((rc = make_tile_map_u8(&maps[0], q8, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
+        if ((rc = make_tile_map_u8(&maps[2], y8, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
+        maps[1] = maps[0]; maps[3] = maps[2];
+    } else {
     if ((rc = make_tile_map(&maps[0], a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
     if ((rc = make_tile_map(&maps[1], terms >= 2 ? a.q_lo : a.q_hi, a.M, a.d, a.ldqh)) != PDM_OK) return rc;
     if ((rc = make_tile_map(&maps[2], a.y_hi, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
     if ((rc = make_tile_map(&maps[3], terms == 3 ? a.y_lo : a.y_hi, a.N, a.d, a.ldyh)) != PDM_OK) return rc;
+    }
     const int block_n = cg == 2 ? 256 : 128;
     GemmParams p = {};
     p.M = a.M; p.ncols = a.N;
-    p.num_kb = (int32_t)ceil_div(a.d, kBlockK);
+    p.num_kb = (int32_t)ceil_div(a.d, f8 ? 2 * kBlockK : kBlockK);
     p.flush_kb = flush_kb_setting(terms);
     p.wait_hint_ns = wait_hint_setting();
     p.hint_a = evict_hint_setting("PDM_HINT_A", kEvictNormal);
@@ -704,6 +735,8 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.q_norm = a.q_norm; p.q_inv_scale = a.q_inv_scale; p.inv_temp = a.inv_temp;
     p.y_norm = a.y_norm; p.y_aux = a.y_aux; p.y_inv_scale = a.y_inv_scale; p.index_offset = a.index_offset;
     p.partials = a.partials; p.energy_out = a.energy_out; p.lde = a.lde; p.energy_mult = a.energy_mult;
+    if (f8) return cg == 2 ? launch_variant<2, 1, EPI_STATS, false, true>(maps, p, info.sm_count, stream)
+                           : launch_variant<1, 1, EPI_STATS, false, true>(maps, p, info.sm_count, stream);
     if (a.y_aux) return dispatch<EPI_STATS, true>(cg, terms, maps, p, info.sm_count, stream);
     return dispatch<EPI_STATS, false>(cg, terms, maps, p, info.sm_count, stream);
 }
@@ -735,7 +768,8 @@ extern "C" int pdm_posterior_stats_plan(pdm_stats_args* a, int device, int64_t* 
         const int64_t m_tiles = a->row_tiles ? std::max<int64_t>(1, a->n_row_tiles) : std::max<int64_t>(1, ceil_div(a->M, 128 * cg));
         const int64_t n_tiles = ceil_div(a->N, cg == 2 ? 256 : 128);
         const int64_t k_pad = round_up(a->d, 64);
-        const int64_t a_tile_bytes = 128ll * cg * k_pad * 2 * (a->precision == PDM_PREC_F16X1 ? 1 : 2);
+        const int64_t a_tile_bytes = a->precision == PDM_PREC_F8X1 ? 128ll * cg * k_pad
+                                   : 128ll * cg * k_pad * 2 * (a->precision == PDM_PREC_F16X1 ? 1 : 2);
         int g = a->m_group, s = a->n_splits;
         if (g <= 0 && s <= 0) tc::plan_schedule(pairs, m_tiles, n_tiles, a_tile_bytes, &g, &s);
         else if (g <= 0) g = (int)std::max<int64_t>(1, std::min<int64_t>(pairs / s, m_tiles));
@@ -762,7 +796,8 @@ extern "C" int pdm_posterior_stats(const pdm_stats_args* a, pdm_stream_t stream)
         case PDM_PREC_EXACT_F32: return launch_exact_stats(*a, as_stream(stream));
         case PDM_PREC_F16X3:
         case PDM_PREC_F16X2:
-        case PDM_PREC_F16X1: return tc::launch_tensor_stats(*a, as_stream(stream));
+        case PDM_PREC_F16X1:
+        case PDM_PREC_F8X1: return tc::launch_tensor_stats(*a, as_stream(stream));
         default: set_error("unknown precision %d", a->precision); return PDM_ERR_INVALID_ARG;
     }
 }

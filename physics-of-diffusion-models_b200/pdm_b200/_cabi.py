@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("PDM_B200_LIB") or os.path.join(PKG_ROOT, "lib", "libpdm_b200.so")   # env: dev variants
 
 PDM_OK = 0
-PREC_EXACT_F32, PREC_F16X3, PREC_F16X1, PREC_F16X2 = 0, 1, 2, 3
+PREC_EXACT_F32, PREC_F16X3, PREC_F16X1, PREC_F16X2, PREC_F8X1 = 0, 1, 2, 3, 4
 PART_STRIDE = 8
 OUT_E_MIN, OUT_LOG_L, OUT_MEAN_E, OUT_MEAN_E2, OUT_VAR_E, OUT_AUX_MEAN, OUT_ENTROPY, OUT_L = range(8)
 OUT_ROWS = 8
@@ -62,6 +62,9 @@ SIGNATURES = {
     "pdm_reduce_partials": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "pdm_screen_temperatures": (C.c_int, [_P, _P, _I64, _P, _F, _F, _F, _P, _P]),
     "pdm_screen_certify": (C.c_int, [_P, _I64, _F, _I32, _P, _P, _P, _P]),
+    "pdm_split_to_e4m3": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _P]),
+    "pdm_screen_temperatures_f8": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F, _F, _F, _P, _P]),
+    "pdm_screen_tile_list": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "pdm_screen_finalize": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _I64, _F, _P, _P, _I64, _I64, _I64,
                                       _P, _P, _P]),
     "pdm_weights_from_energy": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),

@@ -13,7 +13,7 @@ from . import _cabi
 from ._cabi import PdmError, StatsArgs, check
 
 PRECISIONS = {"exact": _cabi.PREC_EXACT_F32, "f16x3": _cabi.PREC_F16X3, "f16x1": _cabi.PREC_F16X1,
-              "f16x2": _cabi.PREC_F16X2}
+              "f16x2": _cabi.PREC_F16X2, "f8x1": _cabi.PREC_F8X1}
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
@@ -282,6 +282,35 @@ class CudaBackend:
               "pdm_screen_temperatures")
         self.launches += 1
         return out
+
+    def split_to_e4m3(self, hi: Tensor, lo: Optional[Tensor], d: int):
+        """fp16 split operands -> (E4M3 bytes (rows, round_up(d, 16)), exact per-row rounding deviation in scaled units)."""
+        rows = hi.shape[0]
+        out8 = torch.empty(rows, _round_up(d, 16), dtype=torch.uint8, device=self.device)
+        err = torch.empty(rows, dtype=torch.float32, device=self.device)
+        check(self.lib.pdm_split_to_e4m3(hi.data_ptr(), _ptr(lo), _ld(hi), rows, d, out8.data_ptr(), _ld(out8), err.data_ptr(),
+                                         self._stream()), "pdm_split_to_e4m3")
+        self.launches += 1
+        return out8, err
+
+    def screen_temperatures_f8(self, q_norm: Tensor, q_err: Tensor, q_inv_scale: Tensor, inv_temp: Tensor, y_norm_max: Tensor,
+                               y_err_max: Tensor, g: float, e_star: float, kappa: float) -> Tensor:
+        out = torch.empty_like(inv_temp)
+        check(self.lib.pdm_screen_temperatures_f8(q_norm.data_ptr(), q_err.data_ptr(), q_inv_scale.data_ptr(), inv_temp.data_ptr(),
+                                                  inv_temp.numel(), y_norm_max.data_ptr(), y_err_max.data_ptr(), float(g),
+                                                  float(e_star), float(kappa), out.data_ptr(), self._stream()),
+              "pdm_screen_temperatures_f8")
+        self.launches += 1
+        return out
+
+    def screen_tile_list(self, flags: Tensor, rows_per_tile: int):
+        m = flags.numel()
+        tile_list = torch.empty(max(1, (m + rows_per_tile - 1) // rows_per_tile), dtype=torch.int32, device=self.device)
+        n_listed = torch.empty(1, dtype=torch.int32, device=self.device)
+        check(self.lib.pdm_screen_tile_list(flags.data_ptr(), m, int(rows_per_tile), tile_list.data_ptr(), n_listed.data_ptr(),
+                                            self._stream()), "pdm_screen_tile_list")
+        self.launches += 1
+        return tile_list, n_listed
 
     def screen_certify(self, screen_out: Tensor, e_star: float, rows_per_tile: int):
         """-> flags (M,) uint8, tile_list (tiles,) int32, n_listed (1,) int32 -- all on the device."""

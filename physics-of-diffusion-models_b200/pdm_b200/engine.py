@@ -108,6 +108,16 @@ class EmpiricalDataset:
         self._moments = None
         self._scale = None
         self._y_norm_max = None
+        self._e4m3 = None
+
+    def e4m3(self):
+        """(E4M3 bytes of the dataset split, max_j of the rows' exact rounding deviation in data units, one-element
+        device tensor): operands of the first stage of the screening cascade."""
+        if self._e4m3 is None:
+            y_hi, y_lo = self.split()
+            y8, err = self.backend.split_to_e4m3(y_hi, y_lo, self.d)
+            self._e4m3 = (y8, (err.max() / self.scale).reshape(1).contiguous())
+        return self._e4m3
 
     @property
     def y_norm_max(self) -> Tensor:
@@ -194,6 +204,8 @@ class EngineConfig:
                                        # exp(-screen_g) of the nearest one's; proven rows take the closed form and only the
                                        # row tiles with an unproven row run the full-precision pass (include/pdm_b200.h,
                                        # pdm_screen_*).  PDM_SCREEN=1 turns it on.
+    screen_f8: bool = True             # screening cascade: an E4M3 pass (twice the MMA rate) first, the fp16 one-product pass
+                                       # only on the row tiles it leaves unproven (PDM_SCREEN_F8=0 turns the first stage off)
     screen_g: float = 0.0              # weight cut-off exponent; 0 = 17 + log N (everything dropped sums to < 2^-24)
     slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows on a side
                                        # stream, one block ahead, and the operands are all-gathered.  Off: measured on
@@ -208,6 +220,8 @@ class EngineConfig:
                            n_splits=_env_int("PDM_N_SPLITS"))
         if os.environ.get("PDM_SCREEN", "") in ("0", "1"):
             cfg.screen = os.environ["PDM_SCREEN"] == "1"
+        if os.environ.get("PDM_SCREEN_F8", "") in ("0", "1"):
+            cfg.screen_f8 = os.environ["PDM_SCREEN_F8"] == "1"
         if os.environ.get("PDM_SLICE_NOISE", "") in ("0", "1"):
             cfg.slice_noise = os.environ["PDM_SLICE_NOISE"] == "1"
         return cfg
@@ -233,6 +247,9 @@ class PosteriorEngine:
         self.screen_report = {"rows_screened": 0, "rows_certified": 0, "tiles_screened": 0, "tiles_full_pass": 0,
                               "rows_unscreened": 0}
         self._screen_t_fail = math.inf
+        self._y_err8_max = None
+        self._screen_f8_live = True        # the E4M3 first stage is still proving enough in this call
+        self._pm_f8_t = math.inf           # posterior_mean: blocks below this mark try the E4M3 stage first
         self._pm_screen_t = math.inf       # posterior_mean: blocks whose temperatures are all below this mark are screened
         self._screen_t_retry = math.inf    # after a screened block that certified nothing: next attempt at T <= this
         self._y_norm_max = None
@@ -310,18 +327,68 @@ class PosteriorEngine:
             self._y_norm_max = v
         return self._y_norm_max
 
-    def _screen_certificate(self, prep: dict, rows: int, inv_temp: Tensor):
-        """One-product pass at the fictitious temperature + certificate: (flags, arg-min of the screening pass, list of
-        row tiles with an unproven row, its length (device), rows per tile)."""
+    SCREEN_KAPPA_F8 = 1.02     # the E4M3 stage's bound uses the exact rounding deviations; this covers the accumulation
+
+    def _global_max(self, v: Tensor) -> Tensor:
+        v = v.clone()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(v, op=dist.ReduceOp.MAX, group=self.group)
+        return v
+
+    def _screen_certificate(self, prep: dict, rows: int, inv_temp: Tensor, stage: str = "f16x1",
+                            row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0):
+        """One-product pass (stage "f16x1": fp16 hi parts; "f8x1": E4M3 bytes) at the fictitious temperature + certificate:
+        (flags, arg-min of the pass, list of row tiles with an unproven row, its length (device), rows per tile).
+        With ``row_tiles`` the pass covers the listed row tiles only; flags of other rows are meaningless."""
         be, ds = self.backend, self.ds
         g = self.cfg.screen_g if self.cfg.screen_g > 0 else 17.0 + math.log(max(2, ds.n_total))
-        inv_t1 = be.screen_temperatures(prep["norms"], inv_temp, self._global_y_norm_max(), g, self.SCREEN_E_STAR,
-                                        self.SCREEN_KAPPA)
-        parts1 = self._local_partials(prep, rows, inv_t1, None, "f16x1")
+        kw = {} if row_tiles is None else dict(row_tiles=row_tiles, n_row_tiles=n_row_tiles)
+        if stage == "f8x1":
+            if self._y_err8_max is None:
+                self._y_err8_max = self._global_max(ds.e4m3()[1])
+            q8, q_err = be.split_to_e4m3(prep["hi"], prep["lo"], ds.d)
+            inv_t1 = be.screen_temperatures_f8(prep["norms"], q_err, prep["inv_scale"], inv_temp, self._global_y_norm_max(),
+                                               self._y_err8_max, g, self.SCREEN_E_STAR, self.SCREEN_KAPPA_F8)
+            parts1 = be.posterior_stats(precision="f8x1", M=rows, N=ds.n, d=ds.d, q_norm=prep["norms"], y_norm=ds.y_norm,
+                                        inv_temp=inv_t1, q_split=(q8, None, prep["inv_scale"] * 16.0),
+                                        y_split=(ds.e4m3()[0], None), y_inv_scale=16.0 / ds.scale,
+                                        index_offset=ds.index_offset, cta_group=self.cfg.cta_group, **kw)
+        else:
+            inv_t1 = be.screen_temperatures(prep["norms"], inv_temp, self._global_y_norm_max(), g, self.SCREEN_E_STAR,
+                                            self.SCREEN_KAPPA)
+            parts1 = self._local_partials(prep, rows, inv_t1, None, "f16x1", **kw)
         out1, arg1 = self._merge(parts1, inv_t1)             # across shards too: every rank sees the same certificate
         rows_per_tile = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)     # the fused kernel's row tile
         flags, tile_list, n_listed = be.screen_certify(out1, self.SCREEN_E_STAR, rows_per_tile)
         return flags, arg1, tile_list, n_listed, rows_per_tile
+
+    def _f8_stage_usable(self) -> bool:
+        return self.cfg.screen_f8 and hasattr(self.backend, "split_to_e4m3") and self.ds.d % 8 == 0
+
+    def _screen_cascade(self, prep: dict, rows: int, inv_temp: Tensor, use_f8: bool):
+        """E4M3 stage on every row (``use_f8``), fp16 one-product stage on the row tiles it leaves unproven.  Returns the
+        values of _screen_certificate plus the fraction of row tiles the E4M3 stage left unproven (None: stage not run)."""
+        be = self.backend
+        if not (use_f8 and self._f8_stage_usable()):
+            return self._screen_certificate(prep, rows, inv_temp) + (None,)
+        f8, a8, tl8, nl8, rpt = self._screen_certificate(prep, rows, inv_temp, stage="f8x1")
+        n8 = int(nl8.item())
+        tiles = (rows + rpt - 1) // rpt
+        rep = self.screen_report
+        rep["f8_tiles_screened"] = rep.get("f8_tiles_screened", 0) + tiles
+        rep["f8_tiles_left"] = rep.get("f8_tiles_left", 0) + n8
+        if n8 == 0:
+            return f8, a8, tl8, nl8, rpt, 0.0
+        f1, a1, _, _, _ = self._screen_certificate(prep, rows, inv_temp, row_tiles=tl8, n_row_tiles=n8)
+        in_list = torch.zeros(tiles, dtype=torch.bool, device=be.device)
+        in_list[tl8[:n8].long()] = True
+        row_in_list = in_list.repeat_interleave(rpt)[:rows]
+        proven8 = f8 != 0
+        flags = (proven8 | (row_in_list & (f1 != 0))).to(torch.uint8)
+        arg = torch.where(proven8, a8, a1)
+        tile_list, n_listed = be.screen_tile_list(flags, rpt)
+        return flags, arg, tile_list, n_listed, rpt, n8 / tiles
 
     def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
                         precision: str, ascending: bool = True, wide: bool = True):
@@ -355,7 +422,9 @@ class PosteriorEngine:
             nonlocal n_tiles
             r0, r1 = ta * rpt, min(rows, tb * rpt)
             sub = {k: (v[r0:r1] if isinstance(v, Tensor) else v) for k, v in prep.items()}
-            f, a, tl, nl, _ = self._screen_certificate(sub, r1 - r0, inv_temp[r0:r1])
+            f, a, tl, nl, _, left8 = self._screen_cascade(sub, r1 - r0, inv_temp[r0:r1], self._screen_f8_live)
+            if left8 is not None and left8 > 0.75:
+                self._screen_f8_live = False                 # the E4M3 stage no longer pays in this call
             flags[r0:r1] = f
             arg1[r0:r1] = a
             open_rows = f == 0
@@ -496,6 +565,7 @@ class PosteriorEngine:
         temp_host = temp.detach().cpu() if screen_on else None
         self._screen_t_fail = math.inf
         self._screen_t_retry = math.inf
+        self._screen_f8_live = True
         if sliced:
             # Opt-in (EngineConfig.slice_noise): each rank draws + prepares 1/world of a block's rows on a side stream
             # and the operands are all-gathered there, one block ahead of the fused pass on the main stream.  The
@@ -735,8 +805,11 @@ class PosteriorEngine:
                 t_lo, t_hi = (float(v) for v in torch.stack([temp_rows[r0:r1].min(), temp_rows[r0:r1].max()]).cpu())
                 if t_hi < self._pm_screen_t:
                     with ph("screen"):
-                        flags, arg1, _, n_listed, _ = self._screen_certificate(prep, rows, inv_temp)
+                        flags, arg1, _, n_listed, _, left8 = self._screen_cascade(prep, rows, inv_temp, t_hi < self._pm_f8_t)
                         proven = int(n_listed.item()) == 0
+                    if left8 is not None:                      # same kind of mark for the E4M3 first stage
+                        self._pm_f8_t = 0.5 * t_lo if left8 > 0.75 else (
+                            max(self._pm_f8_t, 1.5 * t_hi) if math.isfinite(self._pm_f8_t) else self._pm_f8_t)
                     self.screen_report["pm_rows_screened"] = self.screen_report.get("pm_rows_screened", 0) + rows
                     if proven:
                         self._pm_screen_t = max(self._pm_screen_t, 1.5 * t_hi) if math.isfinite(self._pm_screen_t) else self._pm_screen_t

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import synthetic as syn
+from oracle.posterior import pairwise_sqdist as orc_sqdist
 from test_gpu_kernels import check_stats, oracle_rows
 
 pytestmark = pytest.mark.gpu
@@ -227,3 +228,53 @@ def test_screened_sweep_over_datasets_and_ragged_shapes(backend, seed):
     check_stats(o_s, a_s, ref, what=f"screened sweep seed {seed} kind {kind} n={n} d={d} b={b}")
     agree = ref["f32"]["argmin"] == ref["f64"]["argmin"]
     assert torch.equal(a_s[agree], a_u[agree])
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_one_product_error_bounds_hold_for_every_pair(backend, kind):
+    """The certificates rest on |E_pass - E| <= delta for EVERY pair.  Energy tiles of the fp16 one-product pass and of the
+    E4M3 pass against fp64 energies, with kappa = 1 (the engine adds 25 % / 2 % on top), over dataset families."""
+    from pdm_b200.engine import pow2_scale_for
+    dev = backend.device
+    g = syn.gen(40 + kind)
+    n, d, m = 1500, 384, 300
+    if kind == 0:
+        data = torch.rand(n, d, generator=g) * 2 - 1
+    elif kind == 1:
+        data = torch.randn(n, d, generator=g) * torch.exp(1.5 * torch.randn(n, 1, generator=g))
+    elif kind == 2:
+        data = (torch.randint(0, 256, (n, d), generator=g, dtype=torch.uint8).float() / 255 - 0.5) / 0.5
+    else:
+        data = torch.rand(n, d, generator=g) * 2 + 3
+    x = data[torch.randint(0, n, (m,), generator=g)] + torch.randn(m, d, generator=g) * torch.logspace(-3, 2, m)[:, None]
+    y = data.to(dev).contiguous()
+    scale = pow2_scale_for(float(backend.absmax(y).item()))
+    ys = backend.prepare_rows(y, n, fixed_scale=scale, want_norms=False)
+    prep = backend.prepare_rows(x.to(dev).contiguous(), m)
+    y_norm = backend.row_norms(y)
+    e64 = 0.5 * orc_sqdist(x.double(), data.double())
+    xn, yn_max = (x.double() ** 2).sum(1), (data.double() ** 2).sum(1).max()
+    slack = 8 * 2.0 ** -24 * (xn + yn_max)[:, None]                         # fp32 round-off of the norm expansion itself
+    common = dict(M=m, N=n, d=d, q_norm=prep["norms"], y_norm=y_norm, inv_temp=None, want_partials=False)
+    # fp16 one-product pass: delta = 2^-10 ||x|| max||y||
+    e1 = torch.empty(m, n, device=dev)
+    backend.posterior_stats(precision="f16x1", q_split=(prep["hi"], prep["lo"], prep["inv_scale"]), y_split=(ys["hi"], ys["lo"]),
+                            y_inv_scale=1.0 / scale, energy_out=e1, **common)
+    d1 = 2.0 ** -10 * xn.sqrt() * yn_max.sqrt()
+    assert ((e1.cpu().double() - e64).abs() <= d1[:, None] + slack).all()
+    # E4M3 pass: delta = ex ||y||max + (||x|| + ex) ey from the exact rounding deviations
+    q8, q_err = backend.split_to_e4m3(prep["hi"], prep["lo"], d)
+    y8, y_err = backend.split_to_e4m3(ys["hi"], ys["lo"], d)
+    ex = (q_err * prep["inv_scale"]).cpu().double()
+    ey = float(y_err.max().item()) / scale
+    e8 = torch.empty(m, n, device=dev)
+    backend.posterior_stats(precision="f8x1", q_split=(q8, None, prep["inv_scale"] * 16.0), y_split=(y8, None),
+                            y_inv_scale=16.0 / scale, energy_out=e8, **common)
+    d8 = ex * yn_max.sqrt() + (xn.sqrt() + ex) * ey
+    err8 = (e8.cpu().double() - e64).abs()
+    assert (err8 <= d8[:, None] + slack).all(), (err8 / (d8[:, None] + slack)).max()
+    assert (err8.max(1).values > 1e-3 * d8).any()          # the pass really ran on 4-bit significands
+    # the deviations are what they claim to be
+    rec = (prep["hi"].double() + prep["lo"].double())[:, :d].cpu()
+    from_bytes = q8.view(torch.float8_e4m3fn).double()[:, :d].cpu() * 16
+    assert torch.allclose((rec - from_bytes).norm(dim=1), q_err.cpu().double(), rtol=1e-4, atol=1e-12)

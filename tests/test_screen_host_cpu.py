@@ -47,8 +47,10 @@ class SplitFakeBackend(FakeBackend):
                                            inv_temp=inv_temp, y_aux=y_aux, index_offset=index_offset, n_splits=n_splits, **kw)
         q_hi, q_lo, q_inv = q_split
         y_hi, y_lo = y_split
-        qv = q_hi.double() if precision == "f16x1" else q_hi.double() + q_lo.double()
-        yv = y_hi.double() if (precision in ("f16x1", "f16x2") or y_lo is None) else y_hi.double() + y_lo.double()
+        if precision == "f8x1":                             # E4M3 bytes; the inverse scales already carry the factor 16
+            q_hi, y_hi = q_hi.view(torch.float8_e4m3fn), y_hi.view(torch.float8_e4m3fn)
+        qv = q_hi.double() if precision in ("f16x1", "f8x1") else q_hi.double() + q_lo.double()
+        yv = y_hi.double() if (precision in ("f16x1", "f16x2", "f8x1") or y_lo is None) else y_hi.double() + y_lo.double()
         q = (qv * q_inv.double()[:, None]).float()
         y = (yv * y_inv_scale).float()
         self.calls.append(f"stats:{precision}:{'list' if row_tiles is not None else 'all'}")
@@ -60,6 +62,25 @@ class SplitFakeBackend(FakeBackend):
                 keep[t * self.row_tile:(t + 1) * self.row_tile] = True
             parts[~keep] = float("nan")                    # rows outside the list are never written by the kernel
         return parts
+
+    # ---- E4M3 first stage (class attribute ``with_f8`` switches it on) ----
+    def split_to_e4m3(self, hi, lo, d):
+        v = hi.float() + (lo.float() if lo is not None else 0.0)
+        b = (v / 16).to(torch.float8_e4m3fn)
+        err = (v.double() - b.double() * 16).norm(dim=1).float() * (1 + 1e-5)
+        return b.view(torch.uint8), err
+
+    def screen_temperatures_f8(self, q_norm, q_err, q_inv_scale, inv_temp, y_norm_max, y_err_max, g, e_star, kappa):
+        ex = q_err * q_inv_scale
+        delta = kappa * (ex * y_norm_max.sqrt() + (q_norm.sqrt() + ex) * y_err_max)
+        return e_star / (g / inv_temp + 2 * delta)
+
+    def screen_tile_list(self, flags, rows_per_tile):
+        tiles = (flags.numel() + rows_per_tile - 1) // rows_per_tile
+        listed = [t for t in range(tiles) if not bool(flags[t * rows_per_tile:(t + 1) * rows_per_tile].all())]
+        tile_list = torch.zeros(max(1, tiles), dtype=torch.int32)
+        tile_list[:len(listed)] = torch.tensor(listed, dtype=torch.int32)
+        return tile_list, torch.tensor([len(listed)], dtype=torch.int32)
 
     def screen_temperatures(self, q_norm, inv_temp, y_norm_max, g, e_star, kappa):
         delta = kappa * 2.0 ** -10 * q_norm.sqrt() * y_norm_max.sqrt()
@@ -103,9 +124,9 @@ def _setup(n=400, d=96, b=12, seed=1):
     return data, data[:b].clone()
 
 
-def _run(data, x0, temp, screen, block_temps, aux=None):
+def _run(data, x0, temp, screen, block_temps, aux=None, f8=False):
     be = SplitFakeBackend()
-    cfg = EngineConfig(precision="f16x3", screen=screen)
+    cfg = EngineConfig(precision="f16x3", screen=screen, screen_f8=f8)
     cfg.max_query_bytes = block_temps * x0.shape[0] * data.shape[1] * 12
     eng = PosteriorEngine(EmpiricalDataset(data, backend=be), cfg)
     noise = torch.randn(len(temp), x0.shape[0], data.shape[1], generator=syn.gen(9))
@@ -236,3 +257,34 @@ def test_block_screened_in_chunks_from_its_low_temperature_end(monkeypatch):
                 assert torch.isfinite(r_s[k]).all(), k
                 assert torch.allclose(r_s[k], r_u[k], rtol=1e-4, atol=2e-6), (k, (r_s[k] - r_u[k]).abs().max())
             assert torch.equal(r_s["argmin"], r_u["argmin"])
+
+
+def test_e4m3_cascade_is_sound_and_falls_through_to_the_fp16_stage():
+    """Cascade: E4M3 stage on every row, fp16 one-product stage on the tiles it leaves, full pass on the rest.  Every
+    certified row is checked in fp64; the cascade certifies at least what the fp16 stage alone certifies."""
+    total8 = 0
+    for seed in range(6):
+        g = syn.gen(200 + seed)
+        n, d, b = 350 + 31 * seed, 64 + 16 * seed, 16
+        data = _dataset(seed % 4, n, d, g)
+        x0 = data[torch.randint(0, n, (b,), generator=g)].clone()
+        temp = torch.logspace(-5, 3, 17)
+        eng8, be8, r8, noise = _run(data, x0, temp, True, 17, f8=True)
+        eng1, _, r1, _ = _run(data, x0, temp, True, 17, f8=False)
+        eng_u, _, r_u, _ = _run(data, x0, temp, False, 17)
+        assert "stats:f8x1:all" in be8.calls
+        gthr = 17.0 + math.log(n)
+        xt = (noise.double() * temp.double().sqrt()[:, None, None] + x0.double()[None])
+        e = 0.5 * orc.pairwise_sqdist(xt.reshape(-1, d), data.double())
+        srt = e.sort(dim=1).values
+        gap = ((srt[:, 1] - srt[:, 0]) / temp.double().repeat_interleave(b)).view(len(temp), b)
+        cert = (r8["l"] == 1.0) & (r8["mean_e"] == 0.0) & (r8["log_l"] == 0.0) & (r8["var_e"] == 0.0) & (gap < 80)
+        assert (gap[cert] > gthr).all(), (seed, float(gap[cert].min()))
+        assert eng8.screen_report["rows_certified"] >= eng1.screen_report["rows_certified"], seed
+        total8 += eng8.screen_report["f8_tiles_screened"] - eng8.screen_report["f8_tiles_left"]
+        for k in ("log_l", "mean_e", "entropy"):
+            assert torch.isfinite(r8[k]).all()
+            assert torch.allclose(r8[k], r_u[k], rtol=1e-4, atol=2e-6), (seed, k)
+        ok = gap > 1e-3
+        assert torch.equal(r8["argmin"][ok], r_u["argmin"][ok]), seed
+    assert total8 > 0                                        # the E4M3 stage proved tiles on its own
