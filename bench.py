@@ -286,7 +286,7 @@ def run_ours(args):
     # stays on continuous-valued data (the general case).
     # ---- certified delta posteriors (EngineConfig.screen), reported NEXT TO the headline, never as it -------------------
     # The headline above sends every (query, point) pair through the full-precision contraction.  With screening on, a
-    # one-product tensor pass proves row by row (rigorous error bound, include/pdm_b200.h: pdm_screen_*) that the posterior
+    # cascade of cheap tensor passes (E4M3, then one fp16 product) proves row by row (rigorous error bound, include/pdm_b200.h: pdm_screen_*) that the posterior
     # is a delta to fp32 resolution; proven rows take the closed form and skip the full pass.  Same workload, same outputs
     # within the parity tolerance (tests/test_gpu_screen.py); how much is skipped depends on the data and the schedule.
     def screened_line(dataset, queries):
@@ -303,7 +303,10 @@ def run_ours(args):
         rep = eng_s.screen_report
         runs = args.warmup + args.steps
         return {"value": pairs_per_step * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / max(1, args.steps),
-                "precision": eng_s.precision() + " + f16x1 screening pass", "gpu_launches": launches_s,
+                "precision": eng_s.precision() + (" + screening cascade (e4m3 pass, then fp16 one-product pass)"
+                                                  if eng_s.cfg.screen_f8 else " + fp16 one-product screening pass"),
+                "e4m3_row_tiles_screened_per_step": rep.get("f8_tiles_screened", 0) // runs,
+                "e4m3_row_tiles_left_per_step": rep.get("f8_tiles_left", 0) // runs, "gpu_launches": launches_s,
                 "rows_per_step": b * n_t, "rows_screened_per_step": rep["rows_screened"] // runs,
                 "rows_certified_per_step": rep["rows_certified"] // runs,
                 "row_tiles_full_pass_per_step": rep["tiles_full_pass"] // runs,
