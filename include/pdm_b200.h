@@ -229,8 +229,9 @@ int pdm_reduce_partials(const float* parts, int64_t M, int64_t n_outer, int64_t 
  * and only the row tiles holding an unproven row go through the full-precision pass (row_tiles above).
  *
  * Step 1, pdm_screen_temperatures: the screening pass runs at a fictitious temperature T' per row,
- *     1/T' = e_star / (g*T + 2*delta),   delta = kappa * 2^-10 * ||x|| * max_j ||y_j||
- * (delta bounds |E1 - E| of the one-product energies: each operand is rounded to 11 significant bits).
+ *     1/T' = e_star / (g*T + 2*delta),   delta = kappa * 2^-10 * ||x|| * max_j ||y_j|| + 2^-22 (||x||^2 + max_j ||y_j||^2)
+ * (delta bounds |E1 - E| of the one-product energies: each operand is rounded to 11 significant bits; the second
+ * term is the fp32 round-off of the norm expansion itself, which only matters for extreme norm ratios).
  * Step 2, pdm_screen_certify on the merged output of that pass: a row is certified when
  *     l' < 1.25   and   <e>' l' < 0.9 * e_star * exp(-e_star).
  * Every other point j then has (E1_j - E1_min)/T' > e_star  (e exp(-e) decreases for e > 1, and a point with

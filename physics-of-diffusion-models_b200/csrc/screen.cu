@@ -21,7 +21,10 @@ __global__ void __launch_bounds__(256) screen_temperatures_kernel(const float* _
                                                                   float e_star, float kappa, float* __restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
-    const float delta = kappa * 0.0009765625f * sqrtf(q_norm[r]) * sqrtf(__ldg(y_norm_max));
+    // operand rounding (2^-10 ||x|| ||y||, with kappa) + the fp32 round-off of the norm expansion itself (two roundings
+    // of size 2^-24 (||x||^2 + ||y||^2) in each of the two energies of a gap; matters only for extreme norm ratios)
+    const float delta = kappa * 0.0009765625f * sqrtf(q_norm[r]) * sqrtf(__ldg(y_norm_max)) +
+                        2.4e-7f * (q_norm[r] + __ldg(y_norm_max));
     const float t = 1.f / inv_temp[r];
     out[r] = e_star / fmaf(g, t, 2.f * delta);
 }
@@ -114,7 +117,8 @@ __global__ void __launch_bounds__(256) screen_temperatures_f8_kernel(const float
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
     const float ex = q_err[r] * q_inv_scale[r], ey = __ldg(y_err_max);
-    const float delta = kappa * (ex * sqrtf(__ldg(y_norm_max)) + (sqrtf(q_norm[r]) + ex) * ey);
+    const float delta = kappa * (ex * sqrtf(__ldg(y_norm_max)) + (sqrtf(q_norm[r]) + ex) * ey) +
+                        2.4e-7f * (q_norm[r] + __ldg(y_norm_max));          // + fp32 round-off of the norm expansion
     const float t = 1.f / inv_temp[r];
     out[r] = e_star / fmaf(g, t, 2.f * delta);
 }

@@ -72,7 +72,7 @@ class SplitFakeBackend(FakeBackend):
 
     def screen_temperatures_f8(self, q_norm, q_err, q_inv_scale, inv_temp, y_norm_max, y_err_max, g, e_star, kappa):
         ex = q_err * q_inv_scale
-        delta = kappa * (ex * y_norm_max.sqrt() + (q_norm.sqrt() + ex) * y_err_max)
+        delta = kappa * (ex * y_norm_max.sqrt() + (q_norm.sqrt() + ex) * y_err_max) + 2.4e-7 * (q_norm + y_norm_max)
         return e_star / (g / inv_temp + 2 * delta)
 
     def screen_tile_list(self, flags, rows_per_tile):
@@ -83,7 +83,7 @@ class SplitFakeBackend(FakeBackend):
         return tile_list, torch.tensor([len(listed)], dtype=torch.int32)
 
     def screen_temperatures(self, q_norm, inv_temp, y_norm_max, g, e_star, kappa):
-        delta = kappa * 2.0 ** -10 * q_norm.sqrt() * y_norm_max.sqrt()
+        delta = kappa * 2.0 ** -10 * q_norm.sqrt() * y_norm_max.sqrt() + 2.4e-7 * (q_norm + y_norm_max)
         return e_star / (g / inv_temp + 2 * delta)
 
     def screen_certify(self, screen_out, e_star, rows_per_tile):
