@@ -288,3 +288,22 @@ def test_e4m3_cascade_is_sound_and_falls_through_to_the_fp16_stage():
         ok = gap > 1e-3
         assert torch.equal(r8["argmin"][ok], r_u["argmin"][ok]), seed
     assert total8 > 0                                        # the E4M3 stage proved tiles on its own
+
+
+def test_posterior_mean_of_a_fully_proven_block_is_a_gather():
+    """Low-noise ideal-denoiser call: every row certified -> x0_hat = the nearest training points, no energy tile, no
+    weights, no second contraction (the test double has none: reaching them would raise)."""
+    data, _ = _setup(n=300, d=64, b=8)
+    g = syn.gen(77)
+    idx = torch.tensor([1, 7, 50, 120, 299, 200, 10, 11])         # none of them the duplicated point 5 / 37
+    for f8 in (False, True):
+        be = SplitFakeBackend()
+        eng = PosteriorEngine(EmpiricalDataset(data, backend=be), EngineConfig(precision="f16x3", screen=True, screen_f8=f8))
+        ab = torch.tensor(0.9999)
+        xt = ab.sqrt() * data[idx] + (1 - ab).sqrt() * torch.randn(len(idx), 64, generator=g)
+        got = eng.posterior_mean(xt, ((1 - ab) / ab).expand(len(idx)), post=ab.rsqrt().expand(len(idx)))
+        assert torch.equal(got, data[idx])
+        want = orc.posterior_mean_x0(xt, ab, data, dtype=torch.float64)
+        assert (got.double() - want).abs().max() < 1e-6
+        assert eng.screen_report["pm_rows_certified"] == len(idx)
+        assert ("stats:f8x1:all" in be.calls) == f8
