@@ -154,22 +154,33 @@ def cpu_sample(w, b_cpu, nt_cpu, seed):
     return orc, data, x0, temps[idx]
 
 
-def cpu_step(orc, data, x0, temps):
-    """One bounded sample of the step: the reference's per-temperature loop with its DataLoader chunking
-    (dataloader batch 5000) on the CPU."""
+def cpu_step(orc, data, x0, temps, chunk=5000):
+    """One bounded sample of the step: the reference's per-temperature loop with its DataLoader chunking of the dataset
+    (``chunk`` rows per distance GEMM; 100 is the stock ``dataloader_batch_size`` of config/groups/forward_stats.yaml,
+    5000 what a user who has read utils/stats.py:276-280 would set) on the CPU."""
     xt = orc.draw_noised_queries(x0, temps)
-    ent = orc.entropy_batch(xt, data, temps, chunk=5000)
+    ent = orc.entropy_batch(xt, data, temps, chunk=chunk)
     return ent, x0.shape[0] * len(temps) * data.shape[0]
+
+
+def host_threads():
+    """Every host core for the CPU arm: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the reference
+    on one thread."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if "PDM_BENCH_CPU_THREADS" in os.environ:
+        n = int(os.environ["PDM_BENCH_CPU_THREADS"])
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cores = host_threads()
     w = workload()
     b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 8)
     orc, data, x0, temps = cpu_sample(w, b_cpu, nt_cpu, 0)
-    cores = torch.get_num_threads()
     for _ in range(args.warmup):
         cpu_step(orc, data, x0, temps)
     t0 = time.perf_counter()
@@ -178,14 +189,20 @@ def run_reference(args):
         pairs += cpu_step(orc, data, x0, temps)[1]
     dt = time.perf_counter() - t0
     value = pairs / dt
-    sample = f"B={b_cpu} queries x {nt_cpu} temperatures x full N={w['N']}, d={w['d']} per step"
+    # beside it: the stock configuration (dataloader_batch_size = 100), one bounded pass
+    t1 = time.perf_counter()
+    _, p100 = cpu_step(orc, data, x0[:min(b_cpu, 128)], temps[:2], chunk=100)
+    stock = p100 / (time.perf_counter() - t1)
+    sample = f"B={b_cpu} queries x {nt_cpu} temperatures x full N={w['N']}, d={w['d']} per step, dataset in chunks of 5000 rows"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: N=50000 d=3072 B=1024 x 1000-step linear-beta DDPM temperatures",
                    "reference_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "stock_dataloader_batch_size_100": {"value": stock, "unit": UNIT,
+                                                             "sample": f"B={min(b_cpu, 128)} x 2 temperatures, dataset in chunks of 100 rows"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,19 +214,52 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import contextlib
+    import dataclasses
+    import io
     import torch.distributed as dist
-    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig, IdealSampler
     from pdm_b200.backend import CudaBackend
+    from pdm_b200.engine import detect_lattice_scale
+    from pdm_b200.sharding import ShardGrid, make_grid
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    group = None
+    grid = ShardGrid()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
+        grid = make_grid(env_int("PDM_BENCH_DATA_SHARDS", 0))
+    backend = CudaBackend(dev)
+    peaks = measured_peaks()
+    extra_steps = max(1, min(args.steps, env_int("PDM_BENCH_EXTRA_STEPS", 3)))      # secondary entries: a few steps each
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sharded_dataset(data_full, g):
+        """This rank's rows of ``data_full`` (a view) with the whole-set facts every rank must agree on."""
+        n_all = data_full.shape[0]
+        lo, hi = g.rows(n_all)
+        amax = float(backend.absmax(data_full.reshape(n_all, -1)).item())
+        return EmpiricalDataset(data_full[lo:hi], backend=backend, index_offset=lo, n_total=n_all, global_absmax=amax,
+                                lattice_scale=detect_lattice_scale(backend, data_full.reshape(n_all, -1), amax))
+
+    def engine_on(ds, g, config):
+        e = PosteriorEngine(ds, config, group=g.data_group, query_group=g.query_group)
+        if e.precision() != "exact":
+            ds.split()
+        return e
 
     w = workload()
     n, d, b, n_t = w["N"], w["d"], w["B"], w["n_T"]
@@ -217,34 +267,23 @@ def run_ours(args):
     data_full = torch.rand(n, d, device=dev) * 2 - 1                      # synthetic CIFAR-10-shaped set
     x0 = data_full[:b].clone()
     temps = ddpm_temperatures(n_t, w["min_temp"], w["max_temp"]).to(dev)
-    per = (n + world - 1) // world
-    lo, hi = rank * per, min(n, (rank + 1) * per)
-    backend = CudaBackend(dev)
-    from pdm_b200.engine import detect_lattice_scale
-    amax = float(data_full.abs().max().item())
-    ds = EmpiricalDataset(data_full[lo:hi], backend=backend, index_offset=lo, n_total=n, global_absmax=amax,
-                          lattice_scale=detect_lattice_scale(backend, data_full, amax))   # whole-set facts, same on every rank
     cfg = EngineConfig.from_env()
     cfg.sync_noise = False                      # every rank seeds its generator identically below
-    eng = PosteriorEngine(ds, cfg, group=group)
+    ds = sharded_dataset(data_full, grid)
+    eng = engine_on(ds, grid, dataclasses.replace(cfg, screen=False))      # headline: every pair through the full-precision pass
     precision = eng.precision()
-    if precision != "exact":
-        ds.split()
     torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def measure(engine, queries, temps_, steps, warmup, clock_sampler=None, n_points=None):
+        """warm-up + timed steps of noised_stats; returns (ms_total, kernel ms, kernel pairs, launches, phases, clocks)."""
+        n_points = n_points or n
 
-    def measure(engine, queries, clock_sampler=None):
-        """warm-up + timed steps of noised_stats; returns (ms_total, kernel ms, kernel pairs, launches, phases)."""
         def step(i):
             torch.manual_seed(1000 + i)             # same stream on every rank
-            st = engine.noised_stats(queries, temps)
+            st = engine.noised_stats(queries, temps_)
             return st["entropy"].mean(dim=1)        # (n_T,) stays on the device
 
-        for i in range(args.warmup):
+        for i in range(warmup):
             step(i)
         barrier()
         backend.kernel_events = []
@@ -254,64 +293,114 @@ def run_ours(args):
             clock_sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            last = step(args.warmup + i)
+        for i in range(steps):
+            last = step(warmup + i)
         e1.record()
         barrier()
         # the timed steps produced real statistics: S = logZ' + <e> - log N lies in [-log N, 0] at every temperature
         lo_s, hi_s = float(last.min().item()), float(last.max().item())
-        if not (math.isfinite(lo_s) and math.isfinite(hi_s) and lo_s >= -math.log(n) - 1e-3 and hi_s <= 1e-3):
+        if not (math.isfinite(lo_s) and math.isfinite(hi_s) and lo_s >= -math.log(n_points) - 1e-3 and hi_s <= 1e-3):
             raise RuntimeError(f"bench: entropy out of range [{lo_s}, {hi_s}] -- the timed path did not compute the statistics")
         clk = clock_sampler.stop() if clock_sampler is not None else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = max_over_ranks(e0.elapsed_time(e1))
         phases = backend.phase_totals() if backend.phase_events is not None else None
         backend.phase_events = None
         kev = backend.kernel_events
         backend.kernel_events = None
-        return (float(ms.item()), sum(a.elapsed_time(bb) for a, bb, _ in kev), sum(pp for _, _, pp in kev),
+        return (ms, sum(a.elapsed_time(bb) for a, bb, _ in kev), sum(pp for _, _, pp in kev),
                 backend.launches - launches0, phases, clk)
 
-    ms_total, k_ms, k_pairs, launches, phases, clocks = measure(eng, x0, ClockSampler(local) if rank == 0 else None)
+    ms_total, k_ms, k_pairs, launches, phases, clocks = measure(eng, x0, temps, args.steps, args.warmup,
+                                                                ClockSampler(local) if rank == 0 else None)
     plan = list(getattr(backend, "last_plan", ()))       # (n_splits, m_group, cta_group) of the headline launches
     if phases is not None and rank == 0:
         print("phase ms/step:", {k: round(v / max(1, args.steps), 2) for k, v in phases.items()}, file=sys.stderr)
     pairs_per_step = b * n_t * n
     value = pairs_per_step * args.steps / (ms_total * 1e-3)
+    # with a grid each rank's fused kernel sees 1/world of the pairs: sum of the ranks' algorithmic rates
+    k_pairs_all = torch.tensor([float(k_pairs)], device=dev, dtype=torch.float64)
+    k_ms_max = torch.tensor([k_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(k_pairs_all)
+        dist.all_reduce(k_ms_max, op=dist.ReduceOp.MAX)
+    k_pairs_all, k_ms_max = float(k_pairs_all.item()), float(k_ms_max.item())
 
-    # ---- the same workload on 8-bit pixel data (what the reference's image pipeline produces) ----------
-    # ToTensor + Normalize(0.5, 0.5) of uint8 pixels (utils/data.py:43-52) is an fp16-exact lattice: the engine
-    # detects it and drops the third split product (precision f16x2).  Reported next to the headline, which
-    # stays on continuous-valued data (the general case).
+    # ---- parity carried by the measurement itself --------------------------------------------------------------------
+    # (1) world > 1: the grid's statistics against an unsharded engine on this very GPU, same queries, same noise stream.
+    # (2) any world size: the entropy curve of the workload (mean over the B queries, fixed seed) against the curve a
+    #     one-GPU run committed to tests/golden/c2_entropy_curve.npz (PDM_BENCH_WRITE_CURVE=1 rewrites it).
+    parity = {}
+    if world > 1 and os.environ.get("PDM_BENCH_PARITY", "1") == "1":
+        bq = min(b, 32)
+        whole = engine_on(EmpiricalDataset(data_full, backend=backend, global_absmax=ds._absmax(), lattice_scale=ds.lattice_scale),
+                          ShardGrid(), dataclasses.replace(cfg, screen=False))
+        torch.manual_seed(777)
+        ref = whole.noised_stats(x0[:bq], temps)
+        torch.manual_seed(777)
+        got = eng.noised_stats(x0[:bq], temps)
+        xn = (x0[:bq].double() ** 2).sum(1)[None, :] + d * temps.double()[:, None]
+        floor = 8 * 2.0 ** -24 * (xn + float(whole.ds.y_norm.max().item())) / temps.double()[:, None]
+        worst = {}
+        for k in ("log_l", "mean_e", "var_e", "entropy"):
+            err = (got[k].double() - ref[k].double()).abs()
+            tol = torch.maximum(2e-5 * ref[k].double().abs() + 2e-6, 0.25 * floor * (1 + 2 * ref["mean_e"].double() if k == "var_e" else 1))
+            worst[k] = float(err.max().item())
+            if bool((err > tol).any()):
+                raise RuntimeError(f"bench: sharded {k} differs from the unsharded engine by {worst[k]:.3e} (rank {rank})")
+        if not torch.equal(got["argmin"], ref["argmin"]) or not torch.equal(got["e_min"], ref["e_min"]):
+            raise RuntimeError(f"bench: sharded arg-min / E_min differ from the unsharded engine (rank {rank})")
+        parity["grid_vs_unsharded"] = {"rows": bq * n_t, "max_abs_diff": worst, "argmin_identical": True, "e_min_bit_identical": True}
+        del whole, ref, got
+        torch.cuda.empty_cache()
+    curve_path = os.path.join(ROOT, "tests", "golden", "c2_entropy_curve.npz")
+    default_workload = (n, b, n_t) == (50_000, 1024, 1000)
+    if default_workload and os.environ.get("PDM_BENCH_PARITY", "1") == "1":
+        import numpy as np
+        torch.manual_seed(4242)
+        curve = eng.noised_stats(x0, temps)["entropy"].double().mean(dim=1).cpu()
+        if os.environ.get("PDM_BENCH_WRITE_CURVE") == "1" and world == 1 and rank == 0:
+            np.savez(curve_path, entropy_mean=curve.numpy(), seed=4242, N=n, B=b, n_T=n_t,
+                     note="mean over the B queries of compute_stats_batch's entropy, C2 workload of bench.py, one B200")
+        if os.path.exists(curve_path):
+            with np.load(curve_path) as z:
+                want = torch.from_numpy(z["entropy_mean"])
+            diff = float((curve - want).abs().max().item())
+            if diff > 5e-5:
+                raise RuntimeError(f"bench: entropy curve differs from the committed one-GPU curve by {diff:.3e}")
+            parity["entropy_curve_vs_committed_one_gpu_run"] = {"temperatures": n_t, "max_abs_diff": diff, "tolerance": 5e-5}
+
     # ---- certified delta posteriors (EngineConfig.screen), reported NEXT TO the headline, never as it -------------------
     # The headline above sends every (query, point) pair through the full-precision contraction.  With screening on, a
-    # cascade of cheap tensor passes (E4M3, then one fp16 product) proves row by row (rigorous error bound, include/pdm_b200.h: pdm_screen_*) that the posterior
-    # is a delta to fp32 resolution; proven rows take the closed form and skip the full pass.  Same workload, same outputs
-    # within the parity tolerance (tests/test_gpu_screen.py); how much is skipped depends on the data and the schedule.
+    # cascade of cheap tensor passes (E4M3, then one fp16 product) proves row by row (rigorous error bound,
+    # include/pdm_b200.h: pdm_screen_*) that the posterior is a delta to fp32 resolution; proven rows take the closed form
+    # and skip the full pass.  Same workload, same outputs within the parity tolerance (tests/test_gpu_screen.py,
+    # tests/test_gpu_named_configs.py); how much is skipped depends on the data and the schedule.
     def screened_line(dataset, queries):
-        import dataclasses
-        eng_s = PosteriorEngine(dataset, dataclasses.replace(cfg, screen=True), group=group)
+        eng_s = PosteriorEngine(dataset, dataclasses.replace(cfg, screen=True), group=grid.data_group, query_group=grid.query_group)
         if not eng_s.screening_usable():
             return None
         try:
-            ms_s, k_ms_s, k_pairs_s, launches_s, _, _ = measure(eng_s, queries)
+            ms_s, k_ms_s, k_pairs_s, launches_s, _, _ = measure(eng_s, queries, temps, extra_steps, 1)
         except Exception as exc:                    # a secondary entry must never cost the headline line
             backend.kernel_events = None
             backend.phase_events = None
             return {"error": f"{type(exc).__name__}: {exc}"[:300]}
         rep = eng_s.screen_report
-        runs = args.warmup + args.steps
-        return {"value": pairs_per_step * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / max(1, args.steps),
+        runs = 1 + extra_steps
+        val = pairs_per_step * extra_steps / (ms_s * 1e-3)
+        return {"value": val, "unit": UNIT, "ms_per_step": ms_s / extra_steps, "steps": extra_steps,
                 "precision": eng_s.precision() + (" + screening cascade (e4m3 pass, then fp16 one-product pass)"
                                                   if eng_s.cfg.screen_f8 else " + fp16 one-product screening pass"),
-                "e4m3_row_tiles_screened_per_step": rep.get("f8_tiles_screened", 0) // runs,
-                "e4m3_row_tiles_left_per_step": rep.get("f8_tiles_left", 0) // runs, "gpu_launches": launches_s,
-                "rows_per_step": b * n_t, "rows_screened_per_step": rep["rows_screened"] // runs,
-                "rows_certified_per_step": rep["rows_certified"] // runs,
-                "row_tiles_full_pass_per_step": rep["tiles_full_pass"] // runs,
-                "pairs_through_tensor_kernels_per_step": k_pairs_s // max(1, args.steps),
-                "tensor_kernel_ms_per_step": k_ms_s / max(1, args.steps),
+                "per_rank": {"e4m3_row_tiles_screened_per_step": rep.get("f8_tiles_screened", 0) // runs,
+                             "e4m3_row_tiles_left_per_step": rep.get("f8_tiles_left", 0) // runs,
+                             "rows_per_step": len(range(eng_s.q_rank, n_t, eng_s.q_world)) * b,
+                             "rows_screened_per_step": rep["rows_screened"] // runs,
+                             "rows_certified_per_step": rep["rows_certified"] // runs,
+                             "row_tiles_full_pass_per_step": rep["tiles_full_pass"] // runs,
+                             "pairs_through_tensor_kernels_per_step": k_pairs_s // extra_steps,
+                             "tensor_kernel_ms_per_step": k_ms_s / extra_steps},
+                "gpu_launches": launches_s, "algorithmic_tflops": val * 2 * d / 1e12,
+                "roofline_frac": val * 2 * d / 1e12 / (peaks["tflops"] * world),
                 "note": "value counts all query x dataset pairs of the workload; certified rows are answered by the closed "
                         "form after the one-product pass (no full-precision contraction for them)"}
 
@@ -319,29 +408,30 @@ def run_ours(args):
     if os.environ.get("PDM_BENCH_SCREEN", "1") == "1":
         screened = screened_line(ds, x0)
 
+    # ---- the same workload on 8-bit pixel data (what the reference's image pipeline produces) ----------
+    # ToTensor + Normalize(0.5, 0.5) of uint8 pixels (utils/data.py:43-52) is an fp16-exact lattice: the engine
+    # detects it and drops the third split product (precision f16x2).  Reported next to the headline, which
+    # stays on continuous-valued data (the general case).
     lattice_line = None
     if os.environ.get("PDM_BENCH_LATTICE", "1") == "1":
         # generated on the host exactly like the reference's transforms (true division by 255, then (v - 0.5) / 0.5)
         px = torch.randint(0, 256, (n, d), dtype=torch.uint8, generator=torch.Generator().manual_seed(7))
         data_px = ((px.float() / 255 - 0.5) / 0.5).to(dev)
         del px
-        ds_px = EmpiricalDataset(data_px[lo:hi], backend=backend, index_offset=lo, n_total=n, global_absmax=1.0,
-                                 lattice_scale=detect_lattice_scale(backend, data_px, 1.0))
-        eng_px = PosteriorEngine(ds_px, cfg, group=group)
+        ds_px = sharded_dataset(data_px, grid)
+        eng_px = engine_on(ds_px, grid, dataclasses.replace(cfg, screen=False))
         prec_px = eng_px.precision()
-        if prec_px != "exact":
-            ds_px.split()
         x0_px = data_px[:b].clone()
-        del data_px
-        ms_px, k_ms_px, k_pairs_px, _, _, _ = measure(eng_px, x0_px)
-        ach_px = (2.0 * d * k_pairs_px / (k_ms_px * 1e-3)) / 1e12 if k_ms_px > 0 else 0.0
+        ms_px, k_ms_px, k_pairs_px, _, _, _ = measure(eng_px, x0_px, temps, extra_steps, 1)
+        val_px = pairs_per_step * extra_steps / (ms_px * 1e-3)
         lattice_line = {"data": "synthetic uint8 pixels through ToTensor+Normalize(0.5,0.5)", "precision": prec_px,
-                        "lattice_scale": ds_px.lattice_scale, "value": pairs_per_step * args.steps / (ms_px * 1e-3),
-                        "unit": UNIT, "ms_per_step": ms_px / max(1, args.steps), "kernel_algorithmic_tflops": ach_px,
-                        "kernel_ms_per_step": k_ms_px / max(1, args.steps)}
+                        "lattice_scale": ds_px.lattice_scale, "value": val_px, "steps": extra_steps,
+                        "unit": UNIT, "ms_per_step": ms_px / extra_steps, "algorithmic_tflops": val_px * 2 * d / 1e12,
+                        "roofline_frac": val_px * 2 * d / 1e12 / (peaks["tflops"] * world),
+                        "kernel_ms_per_step_this_rank": k_ms_px / extra_steps}
         if os.environ.get("PDM_BENCH_SCREEN", "1") == "1":
             lattice_line["screened"] = screened_line(ds_px, x0_px)
-        del eng_px, ds_px, x0_px
+        del eng_px, ds_px, x0_px, data_px
         torch.cuda.empty_cache()
 
     # ---- the HBM-bound kernels of the path (north star: norm and merge kernels against the HBM roofline) -------------
@@ -367,14 +457,13 @@ def run_ours(args):
 
         rows_blk = min(b * n_t, (6 << 30) // (d * 12) // b * b)
         recs = 2 * max(1, plan[0]) if plan else 12
-        hbm_peak = measured_peaks()["hbm_gbs"]
         hbm_lines = []
-        ys = [ds.y, ds.y.clone()]                                                   # 2 x 0.6 GB
-        outs_n = torch.empty(ds.n, dtype=torch.float32, device=dev)
+        ys = [data_full, data_full.clone()]                                         # 2 x 0.6 GB
+        outs_n = torch.empty(n, dtype=torch.float32, device=dev)
         lib, stream = backend.lib, backend._stream()
-        fns = [lambda y=y: lib.pdm_row_norms_f32(y.data_ptr(), ds.n, d, d, outs_n.data_ptr(), stream) for y in ys] * 4
+        fns = [lambda y=y: lib.pdm_row_norms_f32(y.data_ptr(), n, d, d, outs_n.data_ptr(), stream) for y in ys] * 4
         ms_k = stream_ms(fns)
-        hbm_lines.append({"kernel": "pdm::row_norms_kernel (dataset rows, 4*d B read per row)", "bytes": ds.n * d * 4, "ms": ms_k})
+        hbm_lines.append({"kernel": "pdm::row_norms_kernel (dataset rows, 4*d B read per row)", "bytes": n * d * 4, "ms": ms_k})
         del ys
         k_bufs = 8
         parts_k = [torch.rand(recs, rows_blk, 8, device=dev).add_(0.5) for _ in range(k_bufs)]      # record-major, 8 x 73 MB
@@ -398,56 +487,98 @@ def run_ours(args):
         del hi_b, lo_b
         for h in hbm_lines:
             h["gbs"] = h["bytes"] / h["ms"] / 1e6
-            h["frac_of_measured_hbm_peak"] = h["gbs"] / hbm_peak
+            h["frac_of_measured_hbm_peak"] = h["gbs"] / peaks["hbm_gbs"]
         torch.cuda.empty_cache()
 
-    # ---- ideal-denoiser step at the sampling shape (config C5: B = 10 000 queries) --------
-    # One call of PosteriorEngine.posterior_mean = what DDPMTrue.forward runs per sampling step: distances +
-    # statistics, weights, and the weighted mean (two contractions: 4*d algorithmic flop per pair).
-    denoiser_line = None
+    # ---- ideal denoiser at the sampling shape (config C5: 10 000 samples) ------------------------
+    # Multi-GPU mode of the sampling path (mode 2): the dataset (0.6 GB) is replicated, every rank
+    # owns 1/world of the trajectories, no collective inside a step.
+    denoiser_line = c5_line = None
     if os.environ.get("PDM_BENCH_DENOISER", "1") == "1":
         mq = env_int("PDM_BENCH_DENOISER_M", 10_000)
+        per_q = (mq + world - 1) // world
+        q_lo, q_hi = min(mq, rank * per_q), min(mq, (rank + 1) * per_q)
+        mq_local = q_hi - q_lo
+        ds_rep = ds if world == 1 else EmpiricalDataset(data_full, backend=backend, global_absmax=ds._absmax(),
+                                                        lattice_scale=ds.lattice_scale)
+        eng_rep = PosteriorEngine(ds_rep, dataclasses.replace(cfg, screen=False))
+        eng_rep_s = PosteriorEngine(ds_rep, dataclasses.replace(cfg, screen=True))
 
-        def denoise_ms(alpha_bar, engine=None):
-            engine = engine or eng
+        def denoise_ms(alpha_bar, engine):
             torch.manual_seed(11)
             ab = torch.tensor(alpha_bar, device=dev)
             xq = ab.sqrt() * data_full[torch.randint(0, n, (mq,), device=dev)] + (1 - ab).sqrt() * torch.randn(mq, d, device=dev)
-            t_rows = ((1 - ab) / ab).expand(mq)
-            post = ab.rsqrt().expand(mq)
-            for _ in range(max(1, args.warmup)):
+            xq = xq[q_lo:q_hi].contiguous()
+            t_rows = ((1 - ab) / ab).expand(mq_local)
+            post = ab.rsqrt().expand(mq_local)
+            for _ in range(2):
                 engine.posterior_mean(xq, t_rows, post=post)
             barrier()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             d0.record()
-            for _ in range(args.steps):
+            for _ in range(extra_steps):
                 engine.posterior_mean(xq, t_rows, post=post)
             d1.record()
             barrier()
-            dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
-            if world > 1:
-                dist.all_reduce(dms, op=dist.ReduceOp.MAX)
-            return float(dms.item()) / max(1, args.steps)
+            return max_over_ranks(d0.elapsed_time(d1)) / extra_steps
 
         # alpha_bar = 0.002 (T ~ 500): every training point carries weight, both contractions run -> the roofline entry.
         # alpha_bar = 0.5 (T = 1): on this dataset every posterior is a delta to fp32 resolution; those rows are gathered
-        # from the dataset instead of contracted (EngineConfig.delta_shortcut), reported separately as wall time only.
-        dms = denoise_ms(0.002)
-        dms_delta = denoise_ms(0.5)
-        denoiser_line = {"workload": f"C5 step: {mq} queries x N={n}, d={d} (posterior mean, VP form, alpha_bar=0.002)",
+        # from the dataset instead of contracted, reported separately as wall time only.
+        dms = denoise_ms(0.002, eng_rep)
+        denoiser_line = {"workload": f"C5 step: {mq} queries x N={n}, d={d} (posterior mean, VP form, alpha_bar=0.002); "
+                                     f"queries / {world}, dataset replicated",
                          "precision": precision, "ms_per_step": dms, "value": mq * n / (dms * 1e-3), "unit": UNIT,
                          "algorithmic_tflops": 4.0 * d * mq * n / (dms * 1e-3) / 1e12, "flops_per_pair": 4 * d,
-                         "ms_per_step_delta_posteriors": dms_delta}
-        if os.environ.get("PDM_BENCH_SCREEN", "1") == "1":
-            import dataclasses
-            eng_s = PosteriorEngine(ds, dataclasses.replace(cfg, screen=True), group=group)
-            if eng_s.screening_usable():
-                # the same low-noise step with EngineConfig.screen: one-product pass + certificate + gather
-                try:
-                    denoiser_line["ms_per_step_delta_posteriors_screened"] = denoise_ms(0.5, eng_s)
-                except Exception as exc:            # secondary entry
-                    denoiser_line["screened_error"] = f"{type(exc).__name__}: {exc}"[:300]
-            del eng_s
+                         "ms_per_step_delta_posteriors": denoise_ms(0.5, eng_rep)}
+        denoiser_line["roofline_frac"] = denoiser_line["algorithmic_tflops"] / (peaks["tflops"] * world)
+        if eng_rep_s.screening_usable():
+            try:
+                denoiser_line["ms_per_step_delta_posteriors_screened"] = denoise_ms(0.5, eng_rep_s)
+            except Exception as exc:            # secondary entry
+                denoiser_line["screened_error"] = f"{type(exc).__name__}: {exc}"[:300]
+
+        # ---- C5 trajectory slice: consecutive DDPM steps of the 1000-step schedule around the transition band ------------
+        # IdealSampler = posterior mean + one fused update kernel per step (reference loop: diffusion/ddpm_sampling.py:114-132
+        # around scheduler.py:58-69).  Steps 600 -> 550 of the linear-beta schedule: T from 40 down to 22, where the posterior
+        # goes from a few hundred contributing points to a delta; and steps 150 -> 100 (T ~ 0.25 -> 0.1), all delta.
+        try:
+            log_t = temps.log().double().cpu()
+            c5_line = {"workload": f"C5 slice: {mq} samples x 50 consecutive DDPM steps, N={n}, d={d}; samples / {world}, "
+                                   "dataset replicated, no collective", "flops_per_pair": 4 * d}
+            for tag, (i0, i1), engine in (("transition_steps_600_to_550", (550, 600), eng_rep_s if eng_rep_s.screening_usable() else eng_rep),
+                                          ("low_noise_steps_150_to_100", (100, 150), eng_rep_s if eng_rep_s.screening_usable() else eng_rep)):
+                if i1 > n_t:
+                    continue
+                sampler = IdealSampler(data_full.view(n, *w["shape"]), log_t[i0:i1], step_type="ddpm", engine=engine)
+                ab = torch.sigmoid(-log_t[i1 - 1]).float().to(dev)
+                torch.manual_seed(31 + rank)
+                x_init = (ab.sqrt() * data_full[torch.randint(0, n, (mq_local,), device=dev)]
+                          + (1 - ab).sqrt() * torch.randn(mq_local, d, device=dev)).view(mq_local, *w["shape"])
+                sampler.batch_sample(mq_local, x_init=x_init.clone())              # warm-up pass over the slice
+                barrier()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                out = sampler.batch_sample(mq_local, x_init=x_init.clone())["x"]
+                s1.record()
+                barrier()
+                if not bool(torch.isfinite(out).all()):
+                    raise RuntimeError("C5 slice produced non-finite samples")
+                sms = max_over_ranks(s0.elapsed_time(s1))
+                n_steps = i1 - i0
+                pps = n_steps * mq * n / (sms * 1e-3)
+                c5_line[tag] = {"steps": n_steps, "ms_per_step": sms / n_steps, "steps_per_s": n_steps / (sms * 1e-3),
+                                "value": pps, "unit": UNIT, "screening": engine is eng_rep_s}
+                if tag.startswith("transition"):        # every pair is contracted there; the low-noise steps are gathers
+                    c5_line[tag]["algorithmic_tflops"] = pps * 4 * d / 1e12
+                    c5_line[tag]["roofline_frac"] = pps * 4 * d / 1e12 / (peaks["tflops"] * world)
+                else:
+                    c5_line[tag]["note"] = ("certified delta posteriors: a one-product screening pass proves every row, the mean is a "
+                                            "gather of nearest training points -- no flop rate is claimed for these steps")
+                del sampler
+        except Exception as exc:                # secondary entry
+            c5_line = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        del eng_rep, eng_rep_s, ds_rep
         torch.cuda.empty_cache()
 
     # ---- e2e through the reference-facing API with host inputs --------------------------------
@@ -455,13 +586,13 @@ def run_ours(args):
     import utils.stats as ustats
     if world > 1:
         os.environ["PDM_SHARD_DATASET"] = "1"
+        os.environ["PDM_DATA_SHARDS"] = str(grid.data_shards)
     host_data = data_full.cpu().view(n, *w["shape"])
     loader = DataLoader(TensorDataset(host_data), batch_size=5000, shuffle=False)
     x0_host = x0.cpu().view(b, *w["shape"]).pin_memory()
     temps_host = temps.cpu().pin_memory()
-    del data_full
-    import contextlib
-    import io
+    del data_full, eng, ds
+    torch.cuda.empty_cache()
     with contextlib.redirect_stdout(io.StringIO()):
         torch.manual_seed(1)
         ustats.compute_stats_batch(loader, x0_host, temps_host)         # uploads + caches the dataset
@@ -477,10 +608,93 @@ def run_ours(args):
     e2e_value = pairs_per_step * args.steps / float(e2e_s.item())
     h2d = x0_host.numel() * 4 + temps_host.numel() * 4
     d2h = ent.numel() * 4
+    e2e_engine = ustats._engine_for(loader)
+    e2e_screen = bool(e2e_engine.screening_usable())
+    ustats._ENGINES.clear()
+    del loader, host_data, e2e_engine
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations BASELINE.json names: C3 and C4 ------------------------------------------------------
+    def config_entry(tag, make_data, temps_c, batches, g, what):
+        """One more workload through the same engine: ``batches`` query batches x ``temps_c`` per step."""
+        try:
+            data_c = make_data()
+            n_c, d_c = data_c.shape
+            ds_c = sharded_dataset(data_c, g)
+            eng_c = engine_on(ds_c, g, dataclasses.replace(cfg, screen=False))
+            qs = [data_c[a:bb].clone() for a, bb in batches]
+            if g.data_shards > 1:
+                del data_c                       # the shard is a view: keep only that... (storage stays alive through it)
+
+            def step_c(i):
+                torch.manual_seed(5000 + i)
+                acc = None
+                for q in qs:
+                    st = eng_c.noised_stats(q, temps_c)
+                    v = torch.stack([st["entropy"].mean(dim=1), st["var_e"].mean(dim=1)])       # entropy + heat capacity curves
+                    acc = v if acc is None else acc + v
+                return acc
+
+            step_c(0)
+            barrier()
+            backend.kernel_events = []
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(extra_steps):
+                last_c = step_c(1 + i)
+            c1.record()
+            barrier()
+            kev = backend.kernel_events
+            backend.kernel_events = None
+            if not bool(torch.isfinite(last_c).all()):
+                raise RuntimeError("non-finite statistics")
+            cms = max_over_ranks(c0.elapsed_time(c1)) / extra_steps
+            pairs_c = sum(bb - a for a, bb in batches) * len(temps_c) * n_c
+            k_ms_c = sum(a.elapsed_time(bb) for a, bb, _ in kev) / extra_steps
+            k_pairs_c = sum(pp for _, _, pp in kev) / extra_steps
+            val_c = pairs_c / (cms * 1e-3)
+            line_c = {"workload": what, "N": n_c, "d": d_c, "temperatures": len(temps_c),
+                      "queries_per_step": sum(bb - a for a, bb in batches), "sharding": g.describe(), "precision": eng_c.precision(),
+                      "steps": extra_steps, "ms_per_step": cms, "value": val_c, "unit": UNIT,
+                      "algorithmic_tflops": val_c * 2 * d_c / 1e12, "flops_per_pair": 2 * d_c,
+                      "roofline_frac": val_c * 2 * d_c / 1e12 / (peaks["tflops"] * world),
+                      "kernel_roofline_frac_this_rank": (2.0 * d_c * k_pairs_c / (k_ms_c * 1e-3) / 1e12 / peaks["tflops"]) if k_ms_c > 0 else None,
+                      "plan_splits_group_cta": list(getattr(backend, "last_plan", ()))}
+            del eng_c, ds_c, qs
+            return line_c
+        except Exception as exc:                 # secondary entry
+            backend.kernel_events = None
+            return {"workload": what, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        finally:
+            torch.cuda.empty_cache()
+
+    c3_line = c4_line = None
+    if os.environ.get("PDM_BENCH_C3", "1") == "1":
+        n3, d3 = env_int("PDM_BENCH_C3_N", 100_000), env_int("PDM_BENCH_C3_D", 16384)
+
+        def sphere():                            # sample_on_hypersphere(d, n): utils/synthetic_datasets.py:14-17, radius sqrt(d)
+            torch.manual_seed(3)
+            sp = torch.randn(n3, d3, device=dev)
+            sp /= sp.norm(dim=1, keepdim=True) / math.sqrt(d3)
+            return sp
+        g3 = grid if world == 1 else make_grid(world)          # C3 is named "sharded across 8 B200": dataset rows / world
+        c3_line = config_entry(
+            "C3", sphere, torch.logspace(-4, 4, 200, device=dev), [(100 * i, 100 * (i + 1)) for i in range(11)], g3,
+            "C3: scripts/reproduce_high_dim.py:150-156 flow (compute_stats on 100 queries + compute_metric_stats on 1000, batches "
+            "of 100, 200 temperatures logspace(-4,4)) on sample_on_hypersphere(16384, 100000)")
+    if os.environ.get("PDM_BENCH_C4", "1") == "1":
+        n4, d4 = env_int("PDM_BENCH_C4_N", 200_000), env_int("PDM_BENCH_C4_D", 12288)
+
+        def celeba():
+            torch.manual_seed(4)
+            return torch.rand(n4, d4, device=dev) * 2 - 1
+        c4_line = config_entry(
+            "C4", celeba, torch.logspace(-4, 8, 100, device=dev), [(0, 1024)], grid,
+            "C4: CelebA-64 shape, B=1024 queries x 100 temperatures logspace(-4,8) (scripts/compute_cifar10_metric.py:24-26 grid): "
+            "entropy / free energy and Var(E)/T^2 (heat capacity) curves")
 
     if rank == 0:
-        peaks = measured_peaks()
-        ach = (2.0 * d * k_pairs / (k_ms * 1e-3)) / 1e12 if k_ms > 0 else 0.0
+        ach = (2.0 * d * k_pairs_all / (k_ms_max * 1e-3)) / 1e12 / world if k_ms_max > 0 else 0.0      # per GPU
         terms = {"f16x3": 3, "f16x2": 2}.get(precision, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -490,55 +704,45 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "C2: N=50000 d=3072 B=1024 x 1000-step linear-beta DDPM temperatures "
                                    "(compute_stats_batch)", "N": n, "d": d, "B": b, "n_T": n_t,
-                       "precision": precision, "sharding": f"dataset rows / {world}",
+                       "precision": precision, "sharding": grid.describe(),
                        "arithmetic": ("fp32-equivalent: fp16 hi/lo split operands (22 significant bits), exact products, "
                                       "fp32 accumulation on tcgen05 tensor cores" if precision != "exact" else "fp32 FMA on CUDA cores"),
                        "l2": "inputs (dataset 614 MB + queries) exceed the 126 MB L2; no flush needed",
                        "plan_splits_group_cta": plan},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "utils.stats.compute_stats_batch(dataloader, x0_traj, temp), dataset cached on device "
-                           "after the first call"},
+                           "after the first call", "certified_delta_posteriors": e2e_screen},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": ach / peaks["tflops"], "traffic": profiled_traffic() if (world == 1 and n_t * b >= 172032) else None,
                          "traffic_note": "HBM bytes (read + write) of ONE launch = one 6 GiB block of the step, 172032 query rows x the "
-                                         "full dataset, from the ncu --set full capture summarised in profiles/"
-                                         "r1_fused_gemm_ncu_full_bench_block.csv; algorithmic minimum 2.7e9 (operands once)",
-                         "kernel": "pdm::tc::fused_gemm_kernel",
-                         "executed_tflops": terms * ach, "kernel_ms_per_step": k_ms / max(1, args.steps),
+                                         "full dataset, from the ncu --set full capture summarised in profiles/; algorithmic minimum "
+                                         "2.7e9 (operands once)",
+                         "kernel": "pdm::tc::fused_gemm_kernel", "per_gpu": True,
+                         "executed_tflops": terms * ach, "kernel_ms_per_step": k_ms_max / max(1, args.steps),
                          "peak_source": peaks["source"], "flops_per_pair": 2 * d},
             "clocks": clocks,
         }
+        if parity:
+            line["parity"] = parity
         if hbm_lines is not None:
             line["hbm_kernels"] = {"peak_gbs": peaks["hbm_gbs"],
                                    "method": "K back-to-back launches over distinct buffers (together >> L2), CUDA events, best of 3",
                                    "kernels": hbm_lines}
-        if denoiser_line is not None:
-            denoiser_line["roofline_frac"] = denoiser_line["algorithmic_tflops"] / (peaks["tflops"] * world)
-            line["denoiser_step"] = denoiser_line
-        if screened is not None and "value" in screened:
-            screened["algorithmic_tflops"] = screened["value"] * 2 * d / 1e12
-            screened["roofline_frac"] = screened["algorithmic_tflops"] / (peaks["tflops"] * world)
-        if screened is not None:
-            line["screened"] = screened
-        if lattice_line is not None and lattice_line.get("screened") and "value" in lattice_line["screened"]:
-            ls = lattice_line["screened"]
-            ls["algorithmic_tflops"] = ls["value"] * 2 * d / 1e12
-            ls["roofline_frac"] = ls["algorithmic_tflops"] / (peaks["tflops"] * world)
-        if lattice_line is not None:
-            peak = peaks["tflops"]
-            lattice_line["roofline_frac"] = lattice_line["kernel_algorithmic_tflops"] / peak
-            line["lattice_8bit"] = lattice_line
+        for key, val in (("denoiser_step", denoiser_line), ("c5_trajectory", c5_line), ("screened", screened),
+                         ("lattice_8bit", lattice_line), ("c3_hypersphere", c3_line), ("c4_celeba64", c4_line)):
+            if val is not None:
+                line[key] = val
         if world == 1:
+            cores = host_threads()
             b_cpu, nt_cpu = env_int("PDM_BENCH_CPU_B", 256), env_int("PDM_BENCH_CPU_NT", 96)
             orc, cdata, cx0, ctemps = cpu_sample(w, b_cpu, nt_cpu, 0)
             cpu_step(orc, cdata[:2000], cx0, ctemps[:1])           # warm the BLAS threads
             t0 = time.perf_counter()
             _, cpairs = cpu_step(orc, cdata, cx0, ctemps)
             cdt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": cpairs / cdt, "unit": UNIT, "cores": torch.get_num_threads(),
-                                    "kind": "port",
-                                    "sample": f"B={b_cpu} queries x {nt_cpu} temperatures x full N={n}, d={d}"}
+            line["cpu_baseline"] = {"value": cpairs / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"B={b_cpu} queries x {nt_cpu} temperatures x full N={n}, d={d}, dataset in chunks of 5000 rows"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

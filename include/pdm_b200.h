@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PDM_ABI_VERSION 3
+#define PDM_ABI_VERSION 4
 
 #define PDM_OK               0
 #define PDM_ERR_INVALID_ARG (-1)
@@ -194,6 +194,11 @@ typedef struct pdm_stats_args {
        NULL = every row.  pdm_posterior_stats_plan sizes the schedule for n_row_tiles tiles. */
     const int32_t* row_tiles;   /* (n_row_tiles) device, or NULL                                   */
     int64_t  n_row_tiles;
+    /* ABI v4: optional DEVICE-side length of row_tiles (one int32): the launch covers the first
+       min(n_row_tiles, *n_row_tiles_dev) tiles of the list, so a caller can chain screening pass -> tile list -> full
+       pass without reading the count back (no host synchronisation inside a sampling step).  n_row_tiles is then the
+       upper bound the schedule is planned for; a count of 0 makes the launch a no-op.                               */
+    const int32_t* n_row_tiles_dev;
 } pdm_stats_args;
 
 /* Fills args->n_splits / m_group / cta_group when they are 0, sets args->records_per_row and reports the
@@ -266,6 +271,11 @@ int pdm_screen_temperatures_f8(const float* q_norm, const float* q_err, const fl
                                float g, float e_star, float kappa, float* inv_temp_screen, pdm_stream_t stream);
 int pdm_screen_tile_list(const uint8_t* flags, int64_t M, int32_t rows_per_tile, int32_t* tile_list,
                          int32_t* n_tiles_out, pdm_stream_t stream);
+/* Second stage of a cascade run over the listed tiles of the first (tile_list, *n_tiles_dev <= max_tiles): rows the
+ * first stage left open (flags[r] == 0) take the second stage's verdict and arg-min, in place. */
+int pdm_screen_merge_stage(const int32_t* tile_list, const int32_t* n_tiles_dev, int64_t max_tiles, int32_t rows_per_tile,
+                           int64_t M, const uint8_t* flags_b, const int64_t* arg_b, uint8_t* flags, int64_t* arg,
+                           pdm_stream_t stream);
 int pdm_screen_finalize(const uint8_t* flags, const int64_t* screen_argmin, int64_t M, int64_t d,
                         const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldqh, const float* q_inv_scale,
                         const float* q_norm,
@@ -284,6 +294,27 @@ int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t M, int64_t
                             float* p_f32, int64_t ldp32,
                             uint16_t* p_hi, uint16_t* p_lo, int64_t ldph, pdm_stream_t stream);
 
+/* Same over a list of row tiles of `rows_per_tile` rows whose length may live on the device (see
+ * pdm_stats_args.n_row_tiles_dev): rows outside the listed tiles are not touched. */
+int pdm_weights_from_energy_tiles(const float* energy, int64_t lde, int64_t M, int64_t N,
+                                  const float* e_min, const float* l, const float* inv_temp,
+                                  float* p_f32, int64_t ldp32,
+                                  uint16_t* p_hi, uint16_t* p_lo, int64_t ldph,
+                                  const int32_t* row_tiles, int32_t rows_per_tile, int64_t n_row_tiles,
+                                  const int32_t* n_row_tiles_dev, pdm_stream_t stream);
+
+/* Delta posteriors (scheduler.py:66-69 at low noise): flags[r] = 1 when l[r] - 1 <= 2^-23, i.e. every weight but the
+ * nearest point's sums to at most one ulp -- the posterior mean IS that point; tile_list / n_tiles_out[0] = the row tiles
+ * holding a row that is not a delta (the only ones whose weights have to be formed and contracted). */
+int pdm_delta_tile_list(const float* l, int64_t M, int32_t rows_per_tile, uint8_t* flags, int32_t* tile_list,
+                        int32_t* n_tiles_out, pdm_stream_t stream);
+/* out[r, :] = src[idx[r] - index_offset, :] for rows with flags[r] != 0 (flags NULL = every row) whose index lies in
+ * [index_offset, index_offset + n_local); zeros for flagged rows owned by another shard (shard outputs are summed);
+ * rows with flags[r] == 0 are left as they are. */
+int pdm_gather_rows_f32(const float* src, int64_t lds, int64_t n_local, int64_t d, const int64_t* idx,
+                        int64_t index_offset, const uint8_t* flags, int64_t M, float* out, int64_t ldo,
+                        pdm_stream_t stream);
+
 /* out (M, d) [+]= scale * (A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T), A (M, K) and B (d, K) fp16
  * K-major (lda, ldb multiples of 8).  For the posterior mean A = weights, B = transposed dataset,
  * K = N, scale = 2^-14 * y_inv_scale.  accumulate != 0 adds into `out`.  b_lo == NULL drops the third
@@ -292,6 +323,14 @@ int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
                          const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
                          float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
                          pdm_stream_t stream);
+
+/* Same contraction over a list of row tiles of 128*cta_group rows of A (length on the host, or on the device through
+ * n_row_tiles_dev as in pdm_stats_args); output rows outside the listed tiles are not touched. */
+int pdm_split_gemm_f16x3_tiles(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
+                               const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
+                               float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
+                               const int32_t* row_tiles, int64_t n_row_tiles, const int32_t* n_row_tiles_dev,
+                               pdm_stream_t stream);
 
 /* Exact fp32 CUDA-core version: out (M, d) [+]= P (M, N) @ Y (N, d). */
 int pdm_weighted_mean_exact_f32(const float* p, int64_t ldp, int64_t M, int64_t N,

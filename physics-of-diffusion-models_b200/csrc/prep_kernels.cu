@@ -318,8 +318,18 @@ __global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ 
                                                       const float* __restrict__ e_min, const float* __restrict__ l,
                                                       const float* __restrict__ inv_temp,
                                                       float* __restrict__ p32, int64_t ldp32,
-                                                      __half* __restrict__ ph, __half* __restrict__ pl, int64_t ldph, int vec) {
-    const int64_t row = blockIdx.y;
+                                                      __half* __restrict__ ph, __half* __restrict__ pl, int64_t ldph, int vec,
+                                                      const int32_t* __restrict__ row_tiles, int32_t rows_per_tile,
+                                                      const int32_t* __restrict__ n_tiles_dev, int64_t row0) {
+    // blockIdx.y = a row (row0 + y), or with a tile list slot (row0 + y) of the listed tiles' rows; blocks beyond the
+    // device-side length of the list (or beyond M) have nothing to do
+    int64_t row = row0 + blockIdx.y;
+    if (row_tiles) {
+        const int64_t t = row / rows_per_tile;
+        if (n_tiles_dev && t >= __ldg(n_tiles_dev)) return;
+        row = (int64_t)__ldg(row_tiles + t) * rows_per_tile + (row - t * rows_per_tile);
+        if (row >= M) return;
+    }
     const float m = e_min[row], it = inv_temp[row], inv_l = 1.f / l[row];
     const int64_t width = ph ? ldph : N;
     if (vec) {
@@ -469,15 +479,17 @@ __global__ void __launch_bounds__(256) topk_smallest_kernel(const float* __restr
 // diffusion/ddpm_sampling.py:94-110 with the x0 / eps algebra of diffusion/ddpm/ddpm.py:17-20 folded into three
 // host-computed coefficients.  HBM-bound: 12-16 B per element.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sampler_step_kernel(const float* __restrict__ x0_hat, const float* __restrict__ xt,
+// `out` may alias `xt` (the sampler updates its state in place): xt is read with plain loads through a pointer that is
+// not declared restrict, every thread reads its elements before it writes them.
+__global__ void __launch_bounds__(256) sampler_step_kernel(const float* __restrict__ x0_hat, const float* xt,
                                                            const float* __restrict__ noise, float c_x0, float c_xt, float c_noise,
-                                                           float* __restrict__ out, int64_t n, int vec) {
+                                                           float* out, int64_t n, int vec) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
         const int64_t n4 = n >> 2;
         for (; i < n4; i += stride) {
-            const float4 a = ldg_f4(x0_hat + 4 * i), b = ldg_f4(xt + 4 * i);
+            const float4 a = ldg_f4(x0_hat + 4 * i), b = *reinterpret_cast<const float4*>(xt + 4 * i);
             float4 r = make_float4(fmaf(c_xt, b.x, c_x0 * a.x), fmaf(c_xt, b.y, c_x0 * a.y), fmaf(c_xt, b.z, c_x0 * a.z),
                                    fmaf(c_xt, b.w, c_x0 * a.w));
             if (noise) {
@@ -489,7 +501,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const float* __restri
         i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // scalar tail
     }
     for (; i < n; i += stride) {
-        float r = fmaf(c_xt, __ldg(xt + i), c_x0 * __ldg(x0_hat + i));
+        float r = fmaf(c_xt, xt[i], c_x0 * __ldg(x0_hat + i));
         if (noise) r = fmaf(c_noise, __ldg(noise + i), r);
         out[i] = r;
     }
@@ -581,31 +593,42 @@ extern "C" int pdm_column_moments_f32(const float* y, int64_t n, int64_t d, int6
     return PDM_OK;
 }
 
-extern "C" int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t M, int64_t N,
-                                       const float* e_min, const float* l, const float* inv_temp,
-                                       float* p_f32, int64_t ldp32,
-                                       uint16_t* p_hi, uint16_t* p_lo, int64_t ldph, pdm_stream_t stream) {
+extern "C" int pdm_weights_from_energy_tiles(const float* energy, int64_t lde, int64_t M, int64_t N,
+                                             const float* e_min, const float* l, const float* inv_temp,
+                                             float* p_f32, int64_t ldp32,
+                                             uint16_t* p_hi, uint16_t* p_lo, int64_t ldph,
+                                             const int32_t* row_tiles, int32_t rows_per_tile, int64_t n_row_tiles,
+                                             const int32_t* n_row_tiles_dev, pdm_stream_t stream) {
     PDM_REQUIRE(energy && e_min && l && inv_temp && M >= 0 && N > 0 && lde >= N, "pdm_weights_from_energy: bad arguments");
     PDM_REQUIRE(p_f32 || p_hi, "pdm_weights_from_energy: no output requested");
     PDM_REQUIRE((p_hi == nullptr) == (p_lo == nullptr), "pdm_weights_from_energy: p_hi and p_lo go together");
     PDM_REQUIRE(!p_hi || (ldph >= N && ldph % 8 == 0), "pdm_weights_from_energy: ldph must be >= N and a multiple of 8");
     PDM_REQUIRE(!p_f32 || ldp32 >= N, "pdm_weights_from_energy: ldp32 < N");
-    if (M == 0) return PDM_OK;
-    PDM_REQUIRE(M <= 65535 * 1024LL, "pdm_weights_from_energy: M too large for one launch");
+    PDM_REQUIRE(!row_tiles || (rows_per_tile > 0 && n_row_tiles >= 0), "pdm_weights_from_energy_tiles: bad tile list");
+    PDM_REQUIRE(row_tiles || !n_row_tiles_dev, "pdm_weights_from_energy_tiles: a device-side count needs a tile list");
+    const int64_t slots = row_tiles ? n_row_tiles * rows_per_tile : M;      // rows to visit (upper bound with a device count)
+    if (M == 0 || slots == 0) return PDM_OK;
+    PDM_REQUIRE(slots <= 65535 * 1024LL, "pdm_weights_from_energy: M too large for one launch");
     const int64_t width = p_hi ? ldph : N;
     const bool vec = lde % 4 == 0 && aligned16(energy) && (!p_hi || (aligned16(p_hi) && aligned16(p_lo))) &&
                      (!p_f32 || (ldp32 % 4 == 0 && aligned16(p_f32)));
-    for (int64_t r0 = 0; r0 < M; r0 += 65535) {
-        const int64_t rows = std::min<int64_t>(65535, M - r0);
+    for (int64_t r0 = 0; r0 < slots; r0 += 65535) {
+        const int64_t rows = std::min<int64_t>(65535, slots - r0);
         dim3 grid((unsigned)std::min<int64_t>(ceil_div(width, vec ? 2048 : 256), 64), (unsigned)rows);
         weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(
-            energy + r0 * lde, lde, rows, N, e_min + r0, l + r0, inv_temp + r0,
-            p_f32 ? p_f32 + r0 * ldp32 : nullptr, ldp32,
-            p_hi ? reinterpret_cast<__half*>(p_hi) + r0 * ldph : nullptr,
-            p_lo ? reinterpret_cast<__half*>(p_lo) + r0 * ldph : nullptr, ldph, vec ? 1 : 0);
+            energy, lde, M, N, e_min, l, inv_temp, p_f32, ldp32, reinterpret_cast<__half*>(p_hi), reinterpret_cast<__half*>(p_lo),
+            ldph, vec ? 1 : 0, row_tiles, rows_per_tile, n_row_tiles_dev, r0);
         PDM_CUDA_CHECK(cudaGetLastError());
     }
     return PDM_OK;
+}
+
+extern "C" int pdm_weights_from_energy(const float* energy, int64_t lde, int64_t M, int64_t N,
+                                       const float* e_min, const float* l, const float* inv_temp,
+                                       float* p_f32, int64_t ldp32,
+                                       uint16_t* p_hi, uint16_t* p_lo, int64_t ldph, pdm_stream_t stream) {
+    return pdm_weights_from_energy_tiles(energy, lde, M, N, e_min, l, inv_temp, p_f32, ldp32, p_hi, p_lo, ldph, nullptr, 0, 0,
+                                         nullptr, stream);
 }
 
 extern "C" int pdm_denoiser_backward_weights(const float* energy, int64_t lde, const float* sdot, int64_t lds,

@@ -39,6 +39,48 @@ __global__ void __launch_bounds__(256) certify_rows_kernel(const float* __restri
     flags[r] = (l > 0.99f && l < 1.25f && a1 >= 0.f && a1 < a1_max) ? 1 : 0;
 }
 
+// flags[r] = 1 when the posterior of row r is a delta to fp32 resolution: every other weight together is at most one
+// ulp of the dominant one (l - 1 <= 2^-23).  NaN fails the comparison: such rows stay on the contraction path.
+__global__ void __launch_bounds__(256) delta_flags_kernel(const float* __restrict__ l, int64_t M, uint8_t* __restrict__ flags) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    flags[r] = (l[r] - 1.f <= 1.1920929e-7f) ? 1 : 0;
+}
+
+// Second stage of a cascade, run over the listed row tiles of the first: rows the first stage left open take the second
+// stage's verdict and arg-min; everything else is untouched.  One block per slot of the list, rows_per_tile <= 1024 threads.
+__global__ void __launch_bounds__(1024) merge_stage_kernel(const int32_t* __restrict__ tile_list, const int32_t* __restrict__ n_tiles_dev,
+                                                           int32_t rows_per_tile, int64_t M, const uint8_t* __restrict__ flags_b,
+                                                           const int64_t* __restrict__ arg_b, uint8_t* __restrict__ flags,
+                                                           int64_t* __restrict__ arg) {
+    if ((int)blockIdx.x >= __ldg(n_tiles_dev)) return;
+    for (int i = threadIdx.x; i < rows_per_tile; i += blockDim.x) {
+        const int64_t r = (int64_t)__ldg(tile_list + blockIdx.x) * rows_per_tile + i;
+        if (r < M && flags[r] == 0) { flags[r] = flags_b[r]; arg[r] = arg_b[r]; }
+    }
+}
+
+// out[r, :] = src[idx[r] - index_offset, :] for flagged rows whose index falls in this shard, zeros for flagged rows owned
+// by another shard (the shards' outputs are summed), untouched otherwise.  One warp per row, 128-bit copies when aligned.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int64_t lds, int64_t d,
+                                                          const int64_t* __restrict__ idx, int64_t index_offset, int64_t n_local,
+                                                          const uint8_t* __restrict__ flags, int64_t M, float* __restrict__ out,
+                                                          int64_t ldo, int vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M || (flags && flags[r] == 0)) return;
+    const int64_t j = idx[r] - index_offset;
+    const bool own = j >= 0 && j < n_local;
+    float* o = out + r * ldo;
+    const float* s = src + (own ? j : 0) * lds;
+    if (vec) {
+        for (int64_t k = lane; k < (d >> 2); k += 32)
+            reinterpret_cast<float4*>(o)[k] = own ? __ldg(reinterpret_cast<const float4*>(s) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (int64_t k = lane; k < d; k += 32) o[k] = own ? __ldg(s + k) : 0.f;
+    }
+}
+
 // One block walks the tiles in order; a tile is listed unless every one of its rows is certified.
 __global__ void __launch_bounds__(1024) tile_list_kernel(const uint8_t* __restrict__ flags, int64_t M, int32_t rows_per_tile,
                                                          int32_t* __restrict__ tile_list, int32_t* __restrict__ n_out) {
@@ -221,6 +263,43 @@ extern "C" int pdm_screen_certify(const float* screen_out, int64_t M, float e_st
         PDM_CUDA_CHECK(cudaGetLastError());
     }
     tile_list_kernel<<<1, 1024, 0, as_stream(stream)>>>(flags, M, rows_per_tile, tile_list, n_tiles_out);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_delta_tile_list(const float* l, int64_t M, int32_t rows_per_tile, uint8_t* flags, int32_t* tile_list,
+                                   int32_t* n_tiles_out, pdm_stream_t stream) {
+    PDM_REQUIRE(l && flags && tile_list && n_tiles_out && M >= 0 && rows_per_tile > 0, "pdm_delta_tile_list: bad arguments");
+    if (M > 0) {
+        delta_flags_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(l, M, flags);
+        PDM_CUDA_CHECK(cudaGetLastError());
+    }
+    tile_list_kernel<<<1, 1024, 0, as_stream(stream)>>>(flags, M, rows_per_tile, tile_list, n_tiles_out);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_screen_merge_stage(const int32_t* tile_list, const int32_t* n_tiles_dev, int64_t max_tiles, int32_t rows_per_tile,
+                                      int64_t M, const uint8_t* flags_b, const int64_t* arg_b, uint8_t* flags, int64_t* arg,
+                                      pdm_stream_t stream) {
+    PDM_REQUIRE(tile_list && n_tiles_dev && flags_b && arg_b && flags && arg && M >= 0 && rows_per_tile > 0 && max_tiles >= 0,
+                "pdm_screen_merge_stage: bad arguments");
+    if (M == 0 || max_tiles == 0) return PDM_OK;
+    merge_stage_kernel<<<(unsigned)max_tiles, (unsigned)std::min<int64_t>(1024, round_up(rows_per_tile, 32)), 0, as_stream(stream)>>>(
+        tile_list, n_tiles_dev, rows_per_tile, M, flags_b, arg_b, flags, arg);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_gather_rows_f32(const float* src, int64_t lds, int64_t n_local, int64_t d, const int64_t* idx,
+                                   int64_t index_offset, const uint8_t* flags, int64_t M, float* out, int64_t ldo,
+                                   pdm_stream_t stream) {
+    PDM_REQUIRE(src && idx && out && n_local > 0 && d > 0 && lds >= d && ldo >= d && M >= 0, "pdm_gather_rows_f32: bad arguments");
+    if (M == 0) return PDM_OK;
+    const bool vec = d % 4 == 0 && lds % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    gather_rows_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, as_stream(stream)>>>(src, lds, d, idx, index_offset, n_local, flags, M,
+                                                                              out, ldo, vec ? 1 : 0);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

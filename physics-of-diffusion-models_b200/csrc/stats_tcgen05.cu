@@ -103,6 +103,7 @@ struct GemmParams {
     int32_t sync_tiles;        // column tiles between two rendezvous
     int32_t m_tiles;      // row super-tiles of 128*CG rows at work (all of them, or the length of tile_list)
     const int32_t* tile_list;  // optional: the row super-tiles to process (screened launches); nullptr = 0..m_tiles-1
+    const int32_t* m_tiles_dev; // optional device-side length of tile_list (<= m_tiles, which then is its upper bound)
     int32_t n_tiles;      // column tiles of kBlockN
     int32_t m_group, n_splits;
     // EPI_STATS
@@ -193,6 +194,8 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
     const bool active = pair < p.m_group * p.n_splits;
     const int mi = pair % p.m_group, sp = pair / p.m_group;
+    // a tile list whose length only the device knows (sync-free callers): every role reads the same word once
+    const int m_tiles = p.m_tiles_dev ? min(p.m_tiles, __ldg(p.m_tiles_dev)) : p.m_tiles;
     const int n_chunks = (p.num_kb + p.flush_kb - 1) / p.flush_kb;
 
     if (warp < kEpiWarp0) {
@@ -204,11 +207,11 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #ifdef PDM_STALL_STATS
             const uint64_t t_begin = global_timer_ns();
 #endif
-            for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+            for (int mt = mi; mt < m_tiles; mt += p.m_group) {
                 const int tile = p.tile_list ? __ldg(p.tile_list + mt) : mt;
                 const int32_t a_row = (tile * CG + (int)rank) * kRowsPerCta;
                 const int round = mt / p.m_group;
-                const int row_groups = min(p.m_group, p.m_tiles - round * p.m_group);     // row tiles at work this round
+                const int row_groups = min(p.m_group, m_tiles - round * p.m_group);     // row tiles at work this round
                 const int per_round = (ceil_div(p.n_tiles, p.n_splits) + p.sync_tiles - 1) / max(1, p.sync_tiles);
                 int j = 0;
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits, ++j) {
@@ -250,7 +253,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             // ===================== MMA issuer =====================
             int stage = 0; uint32_t phase = 0; uint32_t chunk_iter = 0;
             unsigned long long st_full = 0, st_tempty = 0; (void)st_full; (void)st_tempty;
-            for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+            for (int mt = mi; mt < m_tiles; mt += p.m_group) {
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
                     for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.flush_kb, ++chunk_iter) {
                         const uint32_t as = chunk_iter & 1u, aphase = (chunk_iter >> 1) & 1u;
@@ -319,7 +322,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             // |y_k| <= 4096 * y_inv_scale by construction of the split, so |y|^2 <= d_pad * (4096 y_inv_scale)^2
             const float yn_bound = (float)(p.num_kb * (F8 ? 2 * kBlockK : kBlockK)) * (4096.f * p.y_inv_scale) * (4096.f * p.y_inv_scale);
             const float half_mult = 0.5f * p.energy_mult;
-            for (int mt = mi; mt < p.m_tiles; mt += p.m_group) {
+            for (int mt = mi; mt < m_tiles; mt += p.m_group) {
                 const int tile = p.tile_list ? __ldg(p.tile_list + mt) : mt;
                 const int64_t grow = (int64_t)(tile * CG + (int)rank) * kRowsPerCta + row_in_cta;
                 const bool row_ok = grow < p.M;
@@ -727,6 +730,7 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
         PDM_REQUIRE(a.n_row_tiles >= 1 && a.n_row_tiles <= p.m_tiles, "n_row_tiles must be between 1 and the number of row tiles");
         p.m_tiles = (int32_t)a.n_row_tiles;
         p.tile_list = a.row_tiles;
+        p.m_tiles_dev = a.n_row_tiles_dev;
     }
     p.n_tiles = (int32_t)ceil_div(a.N, block_n);
     p.m_group = a.m_group; p.n_splits = a.n_splits;
@@ -802,13 +806,15 @@ extern "C" int pdm_posterior_stats(const pdm_stats_args* a, pdm_stream_t stream)
     }
 }
 
-extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
-                                    const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
-                                    float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
-                                    pdm_stream_t stream) {
+extern "C" int pdm_split_gemm_f16x3_tiles(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
+                                          const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
+                                          float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
+                                          const int32_t* row_tiles, int64_t n_row_tiles, const int32_t* n_row_tiles_dev,
+                                          pdm_stream_t stream) {
     PDM_REQUIRE(a_hi && a_lo && b_hi && out && M >= 0 && d > 0 && K > 0 && ldo >= d, "pdm_split_gemm_f16x3: bad arguments");
+    PDM_REQUIRE(row_tiles || !n_row_tiles_dev, "pdm_split_gemm_f16x3_tiles: a device-side count needs a tile list");
     const int terms = b_lo ? 3 : 2;
-    if (M == 0) return PDM_OK;
+    if (M == 0 || (row_tiles && n_row_tiles == 0)) return PDM_OK;
     DeviceInfo info;
     int rc = tc::require_sm100(&info);
     if (rc != PDM_OK) return rc;
@@ -829,6 +835,12 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     p.hint_a = tc::evict_hint_setting("PDM_HINT_A", ptx::kEvictNormal);
     p.hint_b = tc::evict_hint_setting("PDM_HINT_B", ptx::kEvictNormal);
     p.m_tiles = (int32_t)ceil_div(M, (int64_t)tc::kRowsPerCta * cg);
+    if (row_tiles) {
+        PDM_REQUIRE(n_row_tiles >= 1 && n_row_tiles <= p.m_tiles, "n_row_tiles must be between 1 and the number of row tiles");
+        p.m_tiles = (int32_t)n_row_tiles;
+        p.tile_list = row_tiles;
+        p.m_tiles_dev = n_row_tiles_dev;
+    }
     p.n_tiles = (int32_t)ceil_div(d, block_n);
     // every (row tile, column tile) is an independent output tile: spread column tiles first
     const int pairs = info.sm_count / cg;
@@ -836,6 +848,14 @@ extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, 
     p.m_group = (int32_t)std::max<int64_t>(1, std::min<int64_t>(pairs / p.n_splits, p.m_tiles));
     p.out = out; p.ldo = ldo; p.out_scale = scale; p.accumulate = accumulate;
     return tc::dispatch<tc::EPI_STORE, false>(cg, terms, maps, p, info.sm_count, as_stream(stream));
+}
+
+extern "C" int pdm_split_gemm_f16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t M,
+                                    const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t d, int64_t K,
+                                    float scale, float* out, int64_t ldo, int32_t accumulate, int32_t cta_group,
+                                    pdm_stream_t stream) {
+    return pdm_split_gemm_f16x3_tiles(a_hi, a_lo, lda, M, b_hi, b_lo, ldb, d, K, scale, out, ldo, accumulate, cta_group,
+                                      nullptr, 0, nullptr, stream);
 }
 
 #ifdef PDM_STALL_STATS

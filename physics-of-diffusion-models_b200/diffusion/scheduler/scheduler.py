@@ -10,7 +10,10 @@ T = (1 - ab)/ab, so the resident dataset (norms, fp16 split, transposed split) i
 """
 from __future__ import annotations
 
+import os
+import weakref
 from abc import ABC, abstractmethod
+from collections import OrderedDict
 from typing import Optional
 
 import torch
@@ -32,19 +35,40 @@ def cast_log_temp(log_temp: Tensor, target: Tensor) -> Tensor:
     return log_temp.view(-1, *[1] * (target.ndim - 1))
 
 
-_DENOISER_ENGINES: dict[tuple, PosteriorEngine] = {}
+_DENOISER_ENGINES: "OrderedDict[tuple, tuple]" = OrderedDict()
+_MAX_RESIDENT_DATASETS = 4
 
 
 def _engine_for_data(data: Tensor) -> PosteriorEngine:
-    """One resident dataset per training-data tensor (keyed by storage, shape and version)."""
+    """One resident dataset per training-data tensor: keyed by storage address, shape, dtype, device and version, and
+    tied to the tensor itself by a weak reference -- a different tensor that happens to be allocated at a freed
+    tensor's address (loops over equally shaped synthetic datasets) never hits a stale entry.  Least recently used out."""
     key = (data.data_ptr(), tuple(data.shape), data.dtype, str(data.device), data._version)
-    eng = _DENOISER_ENGINES.get(key)
-    if eng is None:
-        if len(_DENOISER_ENGINES) >= 4:
-            _DENOISER_ENGINES.clear()
-        eng = PosteriorEngine(EmpiricalDataset(data, backend=default_backend()))
-        _DENOISER_ENGINES[key] = eng
+    hit = _DENOISER_ENGINES.get(key)
+    if hit is not None and hit[0]() is data:
+        _DENOISER_ENGINES.move_to_end(key)
+        return hit[1]
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=default_backend()))
+    _DENOISER_ENGINES[key] = (weakref.ref(data), eng)
+    _DENOISER_ENGINES.move_to_end(key)
+    for k in [k for k, (ref, _) in _DENOISER_ENGINES.items() if ref() is None]:       # their tensors are gone
+        del _DENOISER_ENGINES[k]
+    while len(_DENOISER_ENGINES) > _MAX_RESIDENT_DATASETS:
+        _DENOISER_ENGINES.popitem(last=False)
     return eng
+
+
+def _query_shards():
+    """(group, rank, world) over which ``true_posterior_mean_x0`` splits the rows of a batch when PDM_SHARD_QUERIES=1 and
+    torch.distributed is initialised (mode 2: the dataset is replicated, every rank evaluates a
+    contiguous slice of the queries and the slices are all-gathered -- the reference's own DDPMSampler loop, run with the
+    same seed on every rank, then samples on all GPUs of the node unchanged)."""
+    if os.environ.get("PDM_SHARD_QUERIES", "0") != "1":
+        return None, 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None, 0, 1
+    return dist.group.WORLD, dist.get_rank(), dist.get_world_size()
 
 
 class Scheduler(ABC):
@@ -92,7 +116,19 @@ class Scheduler(ABC):
 def _denoise(eng: PosteriorEngine, x: Tensor, alpha_bar: Tensor) -> Tensor:
     ab = alpha_bar.detach().expand(x.shape[0])
     temp_rows = ((1 - ab) / ab).clamp_min(1e-30)
-    return eng.posterior_mean(x.detach(), temp_rows, post=ab.rsqrt()).to(x.device).view_as(x)
+    group, rank, world = _query_shards()
+    if world == 1 or x.shape[0] < world:
+        return eng.posterior_mean(x.detach(), temp_rows, post=ab.rsqrt()).to(x.device).view_as(x)
+    import torch.distributed as dist
+    b = x.shape[0]
+    per = (b + world - 1) // world
+    lo, hi = min(b, rank * per), min(b, (rank + 1) * per)
+    mine = eng.posterior_mean(x.detach()[lo:hi], temp_rows[lo:hi], post=ab.rsqrt()[lo:hi])
+    send = torch.zeros(per, mine.shape[1], dtype=mine.dtype, device=mine.device)
+    send[:hi - lo] = mine
+    recv = torch.empty(world * per, mine.shape[1], dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:b].to(x.device).view_as(x)
 
 
 class _IdealDenoiser(torch.autograd.Function):

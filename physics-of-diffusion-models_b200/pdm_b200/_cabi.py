@@ -35,7 +35,7 @@ class StatsArgs(C.Structure):
         ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldyh", C.c_int64), ("y_inv_scale", C.c_float),
         ("q_norm", C.c_void_p), ("y_norm", C.c_void_p), ("inv_temp", C.c_void_p), ("y_aux", C.c_void_p),
         ("partials", C.c_void_p), ("energy_out", C.c_void_p), ("lde", C.c_int64), ("energy_mult", C.c_float),
-        ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int64),
+        ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int64), ("n_row_tiles_dev", C.c_void_p),
     ]
 
 
@@ -68,6 +68,11 @@ SIGNATURES = {
     "pdm_screen_finalize": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _I64, _F, _P, _P, _I64, _I64, _I64,
                                       _P, _P, _P]),
     "pdm_weights_from_energy": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
+    "pdm_weights_from_energy_tiles": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _I32, _I64, _P, _P]),
+    "pdm_split_gemm_f16x3_tiles": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
+    "pdm_delta_tile_list": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P]),
+    "pdm_screen_merge_stage": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P]),
+    "pdm_gather_rows_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     "pdm_split_gemm_f16x3": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P]),
     "pdm_sampler_step_f32": (C.c_int, [_P, _P, _P, _F, _F, _F, _P, _I64, _P]),
     "pdm_topk_smallest_f32": (C.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P, _P]),
@@ -92,7 +97,7 @@ def load() -> C.CDLL:
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
-            if lib.pdm_abi_version() != 3:
+            if lib.pdm_abi_version() != 4:
                 raise PdmError("libpdm_b200.so ABI version mismatch; rebuild the library")
             _lib = lib
     return _lib

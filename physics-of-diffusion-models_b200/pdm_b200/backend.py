@@ -213,9 +213,11 @@ class CudaBackend:
                         index_offset: int = 0, n_splits: int = 0, m_group: int = 0, cta_group: int = 0,
                         want_partials: bool = True, energy_out: Optional[Tensor] = None,
                         energy_mult: float = 1.0, row_tiles: Optional[Tensor] = None,
-                        n_row_tiles: int = 0) -> Optional[Tensor]:
+                        n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None) -> Optional[Tensor]:
         """``row_tiles`` (int32, device) / ``n_row_tiles``: screened launch over the listed row tiles of
-        128*cta_group rows only; records of the other rows are left as allocated (uninitialised)."""
+        128*cta_group rows only; records of the other rows are left as allocated (uninitialised).
+        ``n_row_tiles_dev`` (one int32 on the device): the list's actual length, read by the kernel -- ``n_row_tiles`` is
+        then only the upper bound the schedule is planned for, and nothing is read back to the host."""
         a = StatsArgs()
         a.precision = PRECISIONS[precision]
         a.n_splits, a.m_group, a.cta_group = n_splits, m_group, cta_group
@@ -234,6 +236,10 @@ class CudaBackend:
             assert row_tiles.dtype == torch.int32 and row_tiles.is_contiguous() and n_row_tiles <= row_tiles.numel()
             a.row_tiles, a.n_row_tiles = row_tiles.data_ptr(), int(n_row_tiles)
             keep.append(row_tiles)
+            if n_row_tiles_dev is not None:
+                assert n_row_tiles_dev.dtype == torch.int32
+                a.n_row_tiles_dev = n_row_tiles_dev.data_ptr()
+                keep.append(n_row_tiles_dev)
         nfloats = C.c_int64()
         check(self.lib.pdm_posterior_stats_plan(C.byref(a), self.device.index or 0, C.byref(nfloats)),
               "pdm_posterior_stats_plan")
@@ -347,32 +353,70 @@ class CudaBackend:
         return out
 
     # ---- posterior mean ------------------------------------------------------------------------
-    def weights_from_energy(self, energy: Tensor, e_min: Tensor, l: Tensor, inv_temp: Tensor, *, split: bool):
+    def weights_from_energy(self, energy: Tensor, e_min: Tensor, l: Tensor, inv_temp: Tensor, *, split: bool,
+                            tiles=None):
+        """``tiles`` = (row_tiles int32, rows_per_tile, upper bound of listed tiles, device count or None): only the rows
+        of the listed tiles are formed; the other rows of the outputs stay as allocated."""
         m, n = energy.shape
+        tl, rpt, n_max, n_dev = tiles if tiles is not None else (None, 0, 0, None)
         if split:
             ld = _round_up(n, 8)
             hi = torch.empty(m, ld, dtype=torch.float16, device=self.device)
             lo = torch.empty(m, ld, dtype=torch.float16, device=self.device)
-            check(self.lib.pdm_weights_from_energy(energy.data_ptr(), _ld(energy), m, n, e_min.data_ptr(),
-                                                   l.data_ptr(), inv_temp.data_ptr(), None, 0, hi.data_ptr(),
-                                                   lo.data_ptr(), ld, self._stream()), "pdm_weights_from_energy")
+            check(self.lib.pdm_weights_from_energy_tiles(energy.data_ptr(), _ld(energy), m, n, e_min.data_ptr(),
+                                                         l.data_ptr(), inv_temp.data_ptr(), None, 0, hi.data_ptr(),
+                                                         lo.data_ptr(), ld, _ptr(tl), int(rpt), int(n_max), _ptr(n_dev),
+                                                         self._stream()), "pdm_weights_from_energy")
             self.launches += 1
             return hi, lo
         p = torch.empty(m, n, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_weights_from_energy(energy.data_ptr(), _ld(energy), m, n, e_min.data_ptr(),
-                                               l.data_ptr(), inv_temp.data_ptr(), p.data_ptr(), n, None, None, 0,
-                                               self._stream()), "pdm_weights_from_energy")
+        check(self.lib.pdm_weights_from_energy_tiles(energy.data_ptr(), _ld(energy), m, n, e_min.data_ptr(),
+                                                     l.data_ptr(), inv_temp.data_ptr(), p.data_ptr(), n, None, None, 0,
+                                                     _ptr(tl), int(rpt), int(n_max), _ptr(n_dev), self._stream()),
+              "pdm_weights_from_energy")
         self.launches += 1
         return p
 
+    def delta_tile_list(self, l: Tensor, rows_per_tile: int):
+        """-> (flags uint8 (M,): posterior is a delta to fp32 resolution, tile_list int32, n_listed int32 (1,)): the row
+        tiles that hold a row whose weights have to be contracted."""
+        m = l.numel()
+        flags = torch.empty(m, dtype=torch.uint8, device=self.device)
+        tile_list = torch.empty(max(1, (m + rows_per_tile - 1) // rows_per_tile), dtype=torch.int32, device=self.device)
+        n_listed = torch.empty(1, dtype=torch.int32, device=self.device)
+        check(self.lib.pdm_delta_tile_list(l.data_ptr(), m, int(rows_per_tile), flags.data_ptr(), tile_list.data_ptr(),
+                                           n_listed.data_ptr(), self._stream()), "pdm_delta_tile_list")
+        self.launches += 2
+        return flags, tile_list, n_listed
+
+    def screen_merge_stage(self, tile_list: Tensor, n_listed: Tensor, max_tiles: int, rows_per_tile: int, flags_b: Tensor,
+                           arg_b: Tensor, flags: Tensor, arg: Tensor) -> None:
+        check(self.lib.pdm_screen_merge_stage(tile_list.data_ptr(), n_listed.data_ptr(), int(max_tiles), int(rows_per_tile),
+                                              flags.numel(), flags_b.data_ptr(), arg_b.data_ptr(), flags.data_ptr(),
+                                              arg.data_ptr(), self._stream()), "pdm_screen_merge_stage")
+        self.launches += 1
+
+    def gather_rows(self, src: Tensor, idx: Tensor, index_offset: int, flags: Optional[Tensor], out: Tensor) -> Tensor:
+        """out[r] = src[idx[r] - index_offset] for flagged rows (zeros when another shard owns the index)."""
+        src = self._f32(src)
+        check(self.lib.pdm_gather_rows_f32(src.data_ptr(), _ld(src), src.shape[0], src.shape[1], idx.data_ptr(),
+                                           int(index_offset), _ptr(flags), idx.numel(), out.data_ptr(), _ld(out),
+                                           self._stream()), "pdm_gather_rows_f32")
+        self.launches += 1
+        return out
+
     def split_gemm(self, a_hi: Tensor, a_lo: Tensor, b_hi: Tensor, b_lo: Optional[Tensor], k: int, scale: float,
-                   out: Optional[Tensor] = None, accumulate: bool = False, cta_group: int = 0) -> Tensor:
+                   out: Optional[Tensor] = None, accumulate: bool = False, cta_group: int = 0, tiles=None) -> Tensor:
+        """``tiles`` = (row_tiles int32, upper bound of listed tiles, device count or None): only the listed tiles of
+        128*cta_group rows are contracted and written."""
         m, d = a_hi.shape[0], b_hi.shape[0]
         if out is None:
             out = torch.empty(m, d, dtype=torch.float32, device=self.device)
-        check(self.lib.pdm_split_gemm_f16x3(a_hi.data_ptr(), a_lo.data_ptr(), _ld(a_hi), m, b_hi.data_ptr(),
-                                            _ptr(b_lo), _ld(b_hi), d, k, float(scale), out.data_ptr(),
-                                            _ld(out), int(accumulate), cta_group, self._stream()),
+        tl, n_max, n_dev = tiles if tiles is not None else (None, 0, None)
+        check(self.lib.pdm_split_gemm_f16x3_tiles(a_hi.data_ptr(), a_lo.data_ptr(), _ld(a_hi), m, b_hi.data_ptr(),
+                                                  _ptr(b_lo), _ld(b_hi), d, k, float(scale), out.data_ptr(),
+                                                  _ld(out), int(accumulate), cta_group, _ptr(tl), int(n_max), _ptr(n_dev),
+                                                  self._stream()),
               "pdm_split_gemm_f16x3")
         self.launches += 1
         return out

@@ -207,11 +207,6 @@ class EngineConfig:
     screen_f8: bool = True             # screening cascade: an E4M3 pass (twice the MMA rate) first, the fp16 one-product pass
                                        # only on the row tiles it leaves unproven (PDM_SCREEN_F8=0 turns the first stage off)
     screen_g: float = 0.0              # weight cut-off exponent; 0 = 17 + log N (everything dropped sums to < 2^-24)
-    slice_noise: bool = False          # sharded CUDA runs: each rank draws + prepares 1/world of the query rows on a side
-                                       # stream, one block ahead, and the operands are all-gathered.  Off: measured on
-                                       # 8 B200s the exchange does not hide under the persistent tensor kernel --
-                                       # 113.6 ms per step against 109.5 ms with every rank regenerating all rows
-                                       # in-kernel (17 ms per step).  PDM_SLICE_NOISE=1 turns it on.
 
     @staticmethod
     def from_env() -> "EngineConfig":
@@ -222,27 +217,31 @@ class EngineConfig:
             cfg.screen = os.environ["PDM_SCREEN"] == "1"
         if os.environ.get("PDM_SCREEN_F8", "") in ("0", "1"):
             cfg.screen_f8 = os.environ["PDM_SCREEN_F8"] == "1"
-        if os.environ.get("PDM_SLICE_NOISE", "") in ("0", "1"):
-            cfg.slice_noise = os.environ["PDM_SLICE_NOISE"] == "1"
         return cfg
 
 
 class PosteriorEngine:
     """Fused posterior statistics / posterior mean of query rows against one dataset shard.
 
-    ``group``: optional torch.distributed process group over which the dataset is row-sharded; every rank
+    ``group``: optional torch.distributed process group over which the dataset is row-sharded; every rank of it
     must present the same query rows, partial records are all-gathered and merged.
+    ``query_group``: optional group of ranks that hold the SAME dataset shard and split the work of ``noised_stats``
+    between them: the temperatures of the schedule are dealt round-robin, each rank draws and evaluates only its own
+    (at the Philox offsets they have in the one stream a single-GPU run consumes) and the (n_T, B) results are
+    all-gathered at the end of the call (pdm_b200/sharding.py builds both groups).
     """
 
     # test hook: callable (temperature index, shape, device) -> standard-normal tensor replacing torch.randn
     noise_hook = None
 
-    def __init__(self, dataset: EmpiricalDataset, config: Optional[EngineConfig] = None, group=None):
+    def __init__(self, dataset: EmpiricalDataset, config: Optional[EngineConfig] = None, group=None, query_group=None):
         self.ds = dataset
         self.backend = dataset.backend
         self.cfg = config if config is not None else EngineConfig.from_env()
         self.group = group
         self.world = 1
+        self.query_group = query_group
+        self.q_world, self.q_rank = 1, 0
         # screening bookkeeping: rows / row tiles seen by the screening pass and what it left for the full pass
         self.screen_report = {"rows_screened": 0, "rows_certified": 0, "tiles_screened": 0, "tiles_full_pass": 0,
                               "rows_unscreened": 0}
@@ -252,10 +251,28 @@ class PosteriorEngine:
         self._pm_f8_t = math.inf           # posterior_mean: blocks below this mark try the E4M3 stage first
         self._pm_screen_t = math.inf       # posterior_mean: blocks whose temperatures are all below this mark are screened
         self._screen_t_retry = math.inf    # after a screened block that certified nothing: next attempt at T <= this
+        self._pm_pending: list = []        # posterior_mean: screening counts in flight to the host (lagged feedback)
         self._y_norm_max = None
         if group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(group)
+        if query_group is not None:
+            import torch.distributed as dist
+            self.q_world, self.q_rank = dist.get_world_size(query_group), dist.get_rank(query_group)
+
+    def _local_aux(self, aux: Optional[Tensor]) -> Optional[Tensor]:
+        """The per-point aux vector as the kernels index it: by LOCAL dataset row.  A vector over the whole (row-sharded)
+        dataset is cut to this rank's rows (a fresh tensor: the kernels need 16-byte alignment)."""
+        if aux is None:
+            return None
+        ds = self.ds
+        aux = aux.to(device=self.backend.device, dtype=torch.float32).reshape(-1)
+        if aux.numel() == ds.n_total and ds.n_total != ds.n:
+            return aux[ds.index_offset:ds.index_offset + ds.n].clone()
+        if aux.numel() != ds.n:
+            raise PdmError(f"aux must hold one value per dataset row: got {aux.numel()}, this shard has {ds.n} rows "
+                           f"of {ds.n_total}")
+        return aux.contiguous()
 
     # -- precision -------------------------------------------------------------------------------
     def precision(self) -> str:
@@ -285,7 +302,7 @@ class PosteriorEngine:
 
     def _local_partials(self, prep: dict, rows: int, inv_temp: Tensor, aux: Optional[Tensor], precision: str,
                         energy_out: Optional[Tensor] = None, energy_mult: float = 1.0, want_partials: bool = True,
-                        row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0):
+                        row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None):
         ds = self.ds
         kw = dict(precision=precision, M=rows, N=ds.n, d=ds.d, q_norm=prep["norms"], y_norm=ds.y_norm,
                   inv_temp=inv_temp, y_aux=aux, index_offset=ds.index_offset, n_splits=self.cfg.n_splits,
@@ -293,6 +310,8 @@ class PosteriorEngine:
                   energy_out=energy_out, energy_mult=energy_mult)
         if row_tiles is not None:
             kw.update(row_tiles=row_tiles, n_row_tiles=n_row_tiles)
+            if n_row_tiles_dev is not None:
+                kw.update(n_row_tiles_dev=n_row_tiles_dev)
         if precision == "exact":
             return self.backend.posterior_stats(q=prep["x"], y=ds.y, **kw)
         y_hi, y_lo = ds.split()
@@ -337,13 +356,15 @@ class PosteriorEngine:
         return v
 
     def _screen_certificate(self, prep: dict, rows: int, inv_temp: Tensor, stage: str = "f16x1",
-                            row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0):
+                            row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None):
         """One-product pass (stage "f16x1": fp16 hi parts; "f8x1": E4M3 bytes) at the fictitious temperature + certificate:
         (flags, arg-min of the pass, list of row tiles with an unproven row, its length (device), rows per tile).
         With ``row_tiles`` the pass covers the listed row tiles only; flags of other rows are meaningless."""
         be, ds = self.backend, self.ds
         g = self.cfg.screen_g if self.cfg.screen_g > 0 else 17.0 + math.log(max(2, ds.n_total))
         kw = {} if row_tiles is None else dict(row_tiles=row_tiles, n_row_tiles=n_row_tiles)
+        if row_tiles is not None and n_row_tiles_dev is not None:
+            kw["n_row_tiles_dev"] = n_row_tiles_dev
         if stage == "f8x1":
             if self._y_err8_max is None:
                 self._y_err8_max = self._global_max(ds.e4m3()[1])
@@ -389,6 +410,58 @@ class PosteriorEngine:
         arg = torch.where(proven8, a8, a1)
         tile_list, n_listed = be.screen_tile_list(flags, rpt)
         return flags, arg, tile_list, n_listed, rpt, n8 / tiles
+
+    def _screen_cascade_async(self, prep: dict, rows: int, inv_temp: Tensor, use_f8: bool):
+        """The cascade without a single host read (the ideal-denoiser path inside a sampling loop): the E4M3 stage's list of
+        unproven row tiles and its length stay on the device and drive the fp16 one-product stage, whose verdicts are folded
+        into the flags in place.  Returns (flags, arg-min of the passes, tile list, its length (device), rows per tile,
+        length of the E4M3 stage's list (device) or None)."""
+        be = self.backend
+        if not (use_f8 and self._f8_stage_usable()):
+            return self._screen_certificate(prep, rows, inv_temp) + (None,)
+        f8, a8, tl8, nl8, rpt = self._screen_certificate(prep, rows, inv_temp, stage="f8x1")
+        tiles = (rows + rpt - 1) // rpt
+        f1, a1, _, _, _ = self._screen_certificate(prep, rows, inv_temp, row_tiles=tl8, n_row_tiles=tiles, n_row_tiles_dev=nl8)
+        be.screen_merge_stage(tl8, nl8, tiles, rpt, f1, a1, f8, a8)
+        tile_list, n_listed = be.screen_tile_list(f8, rpt)
+        return f8, a8, tile_list, n_listed, rpt, nl8
+
+    # lagged feedback for the screening marks of posterior_mean: the counts of a call are copied to pinned memory behind an
+    # event and read when a LATER call finds the event complete -- the loop never waits for the device.
+    def _pm_report(self, n_listed: Tensor, n_left8: Optional[Tensor], tiles: int, rows: int, t_lo: float, t_hi: float) -> None:
+        dev = self.backend.device
+        vals = torch.cat([n_listed.reshape(1), n_left8.reshape(1) if n_left8 is not None else n_listed.new_full((1,), -1)])
+        if dev.type == "cuda":
+            buf = torch.empty(2, dtype=torch.int32, pin_memory=True)
+            buf.copy_(vals, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:
+            buf, ev = vals.clone(), None
+        self._pm_pending.append((ev, buf, tiles, rows, t_lo, t_hi))
+
+    def _pm_poll(self, wait: bool = False) -> None:
+        rep = self.screen_report
+        while self._pm_pending and (wait or self._pm_pending[0][0] is None or self._pm_pending[0][0].query()):
+            ev, buf, tiles, rows, t_lo, t_hi = self._pm_pending.pop(0)
+            if ev is not None and wait:
+                ev.synchronize()
+            n_left, n8 = int(buf[0]), int(buf[1])
+            rep["pm_rows_screened"] = rep.get("pm_rows_screened", 0) + rows
+            rep["pm_tiles_screened"] = rep.get("pm_tiles_screened", 0) + tiles
+            rep["pm_tiles_full_pass"] = rep.get("pm_tiles_full_pass", 0) + n_left
+            if n_left == 0:
+                rep["pm_rows_certified"] = rep.get("pm_rows_certified", 0) + rows
+            if n8 >= 0:                                        # same kind of mark for the E4M3 first stage
+                if n8 > 0.75 * tiles:
+                    self._pm_f8_t = min(self._pm_f8_t, 0.5 * t_lo)
+                elif math.isfinite(self._pm_f8_t):
+                    self._pm_f8_t = max(self._pm_f8_t, 1.5 * t_hi)
+            if 2 * n_left <= tiles:                            # at least half of the tiles proven: worth it up to 1.5 T
+                if math.isfinite(self._pm_screen_t):
+                    self._pm_screen_t = max(self._pm_screen_t, 1.5 * t_hi)
+            else:                                              # a failed attempt at temperature T is repeated below T/2
+                self._pm_screen_t = min(self._pm_screen_t, 0.5 * t_lo)
 
     def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
                         precision: str, ascending: bool = True, wide: bool = True):
@@ -521,6 +594,7 @@ class PosteriorEngine:
         xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
         temp_rows = temp_rows.to(device=dev, dtype=torch.float32).reshape(-1).expand(xf.shape[0]).contiguous()
         outs, idxs = [], []
+        aux = self._local_aux(aux)
         if xf.shape[0] == 0:
             return self._empty_stats((0,), dev)
         step = self.rows_per_block()
@@ -538,111 +612,132 @@ class PosteriorEngine:
         """Statistics of xt = randn * sqrt(T_i) + x0 for every temperature of ``temp``.
 
         The noise is drawn with one ``torch.randn(*x0.shape, device=...)`` per temperature in schedule
-        order -- the reference's RNG stream (utils/stats.py:74, :273).  Returns tensors of shape (n_T, B)."""
+        order -- the reference's RNG stream (utils/stats.py:74, :273).  With a ``query_group`` this rank draws and
+        evaluates temperatures q_rank, q_rank + q_world, ... only (same stream: each draw sits at its own Philox offset)
+        and the results are all-gathered.  Returns tensors of shape (n_T, B)."""
         dev = self.backend.device
         b = x0.shape[0]
         x0f = _flat2d(x0).to(device=dev, dtype=torch.float32).contiguous()
         temp = temp.to(device=dev, dtype=torch.float32).reshape(-1)
         n_t = temp.shape[0]
+        aux = self._local_aux(aux)
         if b == 0 or n_t == 0:
             return self._empty_stats((n_t, b), dev)
+        qw, qr = self.q_world, self.q_rank
+        temp_mine = temp[qr::qw].contiguous()                 # temperature k of mine is number qr + k*qw of the schedule
+        n_mine = temp_mine.shape[0]
         t_per_block = max(1, self.rows_per_block() // b)
         outs, idxs = [], []
         if noise_fn is None and PosteriorEngine.noise_hook is not None:
             noise_fn = lambda i: PosteriorEngine.noise_hook(i, tuple(x0.shape), dev)     # noqa: E731
         draw = noise_fn
-        sliced = self.world > 1 and draw is None and dev.type == "cuda" and self.cfg.slice_noise
         fused = draw is None and self._fused_noise_usable(x0, dev)
-        if self.world > 1 and fused and not sliced:
-            self._sync_generator(dev)            # every rank regenerates rank 0's stream: 16 bytes instead of the noise
+        if (self.world > 1 or qw > 1) and draw is None:
+            self._sync_generator(dev)            # every rank continues rank 0's stream: 16 bytes instead of the noise
         x0_absmax = self.backend.row_absmax(x0f) if fused and self.precision() != "exact" else None
+        # Where the draws sit in the generator's stream.  CUDA: draw number i of the call starts at Philox offset
+        # base + i*step (step measured once per shape), so a rank can jump straight to its own.  CPU generator (test
+        # double of the backend): no random access -- the draws of other ranks are made and dropped.
+        on_cuda = dev.type == "cuda"
+        gen = base = step_off = None
+        if draw is None and on_cuda:
+            gen = self._cuda_generator(dev)
+            step_off = self._randn_offset_step(tuple(x0.shape), dev)
+            base = gen.get_offset()
+        drawn = 0                                 # CPU stream position, in draws of this call
+
+        def draw_into(dst: Tensor, i: int) -> None:
+            nonlocal drawn
+            if draw is not None:
+                dst.copy_(draw(i).reshape(b, -1))
+            elif on_cuda:
+                gen.set_offset(base + i * step_off)
+                torch.randn(*x0.shape, device=dev, out=dst.view(x0.shape))    # the generator calls of torch.randn(*shape)
+            else:
+                while drawn < i:
+                    torch.randn(*x0.shape)
+                    drawn += 1
+                torch.randn(*x0.shape, out=dst.view(x0.shape))
+                drawn += 1
+
         # Screening policy: a block is screened while its lowest temperature is below the lowest temperature at which a
         # row has failed the certificate so far in this call (schedules run from low to high noise; a block above that
         # mark would pay the one-product pass for nothing).  After a screened block that certifies nothing the
         # next attempt waits for a block that reaches a quarter of its lowest temperature (schedules that start at the
         # high-noise end pay a logarithmic number of failed attempts).
         screen_on = self.screening_usable()
-        temp_host = temp.detach().cpu() if screen_on else None
+        temp_host = temp_mine.detach().cpu() if screen_on else None
         self._screen_t_fail = math.inf
         self._screen_t_retry = math.inf
         self._screen_f8_live = True
-        if sliced:
-            # Opt-in (EngineConfig.slice_noise): each rank draws + prepares 1/world of a block's rows on a side stream
-            # and the operands are all-gathered there, one block ahead of the fused pass on the main stream.  The
-            # replicated Philox work shrinks by `world`; whether the exchange hides depends on SMs being free beside
-            # the persistent tensor kernel (on 8 B200s it did not: see the note on the config field).
-            t_per_block = max(self.world, t_per_block // self.world * self.world)
-            self._sync_generator(dev)
-            blocks = [(t0, min(n_t, t0 + t_per_block)) for t0 in range(0, n_t, t_per_block)]
-            main = torch.cuda.current_stream(dev)
-            side = self._side_stream(dev)
-
-            def launch(t0, t1):
-                side.wait_stream(main)                     # inputs (and the buffers of earlier blocks) are ready
-                with torch.cuda.stream(side):
-                    return self._sliced_prepare(x0, x0f, temp[t0:t1], dev, fused, x0_absmax)
-
-            nxt = launch(*blocks[0])
-            for k, (t0, t1) in enumerate(blocks):
-                prep = nxt
-                main.wait_stream(side)
-                for t in prep.values():
-                    if t is not None:
-                        t.record_stream(main)
-                if k + 1 < len(blocks):
-                    nxt = launch(*blocks[k + 1])           # enqueued before this block's fused pass: runs beside it
-                o, i = self.stats_block(x0f, (t1 - t0) * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep)
-                outs.append(o)
-                idxs.append(i)
-            out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
-            res = {k: out[j].view(n_t, b) for j, k in enumerate(STAT_KEYS)}
-            res["argmin"] = (torch.cat(idxs) if len(idxs) > 1 else idxs[0]).view(n_t, b)
-            return res
-        for t0 in range(0, n_t, t_per_block):
-            t1 = min(n_t, t0 + t_per_block)
-            nb = t1 - t0
-            screen = screen_on and float(temp_host[t0:t1].min()) < min(self._screen_t_fail, self._screen_t_retry)
-            asc = not screen or bool(temp_host[t0] <= temp_host[t1 - 1])
-            wide = screen and float(temp_host[t0:t1].max()) > 8.0 * float(temp_host[t0:t1].min())
-            ph = getattr(self.backend, "phase", None)
-            if ph is None:
-                import contextlib
-                ph = lambda _n: contextlib.nullcontext()  # noqa: E731
+        ph = getattr(self.backend, "phase", None)
+        if ph is None:
+            import contextlib
+            ph = lambda _n: contextlib.nullcontext()  # noqa: E731
+        for k0 in range(0, n_mine, t_per_block):
+            k1 = min(n_mine, k0 + t_per_block)
+            nb = k1 - k0
+            tb = temp_mine[k0:k1]
+            screen = screen_on and float(temp_host[k0:k1].min()) < min(self._screen_t_fail, self._screen_t_retry)
+            asc = not screen or bool(temp_host[k0] <= temp_host[k1 - 1])
+            wide = screen and float(temp_host[k0:k1].max()) > 8.0 * float(temp_host[k0:k1].min())
+            t_rows = tb.repeat_interleave(b)
             if fused:
                 with ph("noise+prepare"):
-                    gen = self._cuda_generator(dev)
-                    step_off = self._randn_offset_step(tuple(x0.shape), dev)
-                    base = gen.get_offset()
-                    prep = self._fused_prepare(gen.initial_seed(), base, step_off, x0f, temp[t0:t1], x0_absmax)
-                    gen.set_offset(base + nb * step_off)
-                o, i = self.stats_block(x0f, nb * b, temp[t0:t1].repeat_interleave(b), aux=aux, prep=prep, screen=screen,
-                                        ascending=asc, wide=wide)
-                outs.append(o)
-                idxs.append(i)
-                continue
-            with ph("noise"):
-                noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
-                for i in range(nb):
-                    if draw is None:
-                        # same generator calls as torch.randn(*x0.shape, device=dev), written in place
-                        torch.randn(*x0.shape, device=dev, out=noise[i].view(x0.shape))
-                    else:
-                        noise[i].copy_(draw(t0 + i).reshape(b, -1))
-            if self.world > 1 and self.cfg.sync_noise:
-                import torch.distributed as dist
-                dist.broadcast(noise, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
-                               group=self.group)
-            t_rows = temp[t0:t1].repeat_interleave(b)
-            o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux,
-                                    screen=screen, ascending=asc, wide=wide)
+                    prep = self._fused_prepare(gen.initial_seed(), base + (qr + k0 * qw) * step_off, qw * step_off, x0f, tb,
+                                               x0_absmax)
+                o, i = self.stats_block(x0f, nb * b, t_rows, aux=aux, prep=prep, screen=screen, ascending=asc, wide=wide)
+            else:
+                with ph("noise"):
+                    noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
+                    for i in range(nb):
+                        draw_into(noise[i], qr + (k0 + i) * qw)
+                o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux,
+                                        screen=screen, ascending=asc, wide=wide)
             outs.append(o)
             idxs.append(i)
-        out = torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
-        res = {k: out[j].view(n_t, b) for j, k in enumerate(STAT_KEYS)}
-        res["argmin"] = (torch.cat(idxs) if len(idxs) > 1 else idxs[0]).view(n_t, b)
+        if draw is None:                          # leave the generator where a single-GPU run would
+            if on_cuda:
+                gen.set_offset(base + n_t * step_off)
+            else:
+                while drawn < n_t:
+                    torch.randn(*x0.shape)
+                    drawn += 1
+        if n_mine > 0:
+            out = (torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]).view(len(STAT_KEYS), n_mine, b)
+            arg = (torch.cat(idxs) if len(idxs) > 1 else idxs[0]).view(n_mine, b)
+        else:
+            out = torch.empty(len(STAT_KEYS), 0, b, dtype=torch.float32, device=dev)
+            arg = torch.empty(0, b, dtype=torch.int64, device=dev)
+        if qw > 1:
+            out, arg = self._gather_temperatures(out, arg, n_t)
+        res = {k: out[j] for j, k in enumerate(STAT_KEYS)}
+        res["argmin"] = arg
         return res
 
-    # -- sharded runs: every rank draws and prepares 1/world of the query rows -----------------------
+    def _gather_temperatures(self, out: Tensor, arg: Tensor, n_t: int):
+        """(8, n_mine, B) statistics and (n_mine, B) arg-mins of this rank's temperatures -> those of the whole schedule,
+        on every rank of the query group (one all-gather of each; ranks are padded to the same number of temperatures)."""
+        import torch.distributed as dist
+        qw = self.q_world
+        n_max = (n_t + qw - 1) // qw
+        b = out.shape[2]
+        k = out.shape[0]
+        send = torch.zeros(k + 2, n_max, b, dtype=torch.float32, device=out.device)
+        send[:k, :out.shape[1]] = out
+        send[k:, :arg.shape[0]] = arg.contiguous().view(torch.int32).view(arg.shape[0], b, 2).permute(2, 0, 1).view(torch.float32)
+        recv = torch.empty((qw,) + tuple(send.shape), dtype=torch.float32, device=out.device)
+        dist.all_gather_into_tensor(recv.view(qw * (k + 2), n_max, b), send, group=self.query_group)
+        full = torch.empty(k, n_t, b, dtype=torch.float32, device=out.device)
+        full_arg = torch.empty(n_t, b, dtype=torch.int64, device=out.device)
+        for j in range(qw):
+            cnt = len(range(j, n_t, qw))
+            full[:, j::qw] = recv[j, :k, :cnt]
+            halves = recv[j, k:, :cnt].view(torch.int32).permute(1, 2, 0).contiguous()       # (cnt, b, 2)
+            full_arg[j::qw] = halves.view(torch.int64).view(cnt, b)
+        return full, full_arg
+
+    # -- the reference's RNG stream ---------------------------------------------------------------------
     _RANDN_OFFSETS: dict = {}
 
     @staticmethod
@@ -660,24 +755,21 @@ class PosteriorEngine:
             PosteriorEngine._RANDN_OFFSETS[key] = step
         return step
 
-    _SIDE_STREAMS: dict = {}
-
-    @staticmethod
-    def _side_stream(dev: torch.device):
-        key = str(dev)
-        if key not in PosteriorEngine._SIDE_STREAMS:
-            PosteriorEngine._SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
-        return PosteriorEngine._SIDE_STREAMS[key]
-
     def _sync_generator(self, dev: torch.device) -> None:
-        """Give every rank rank 0's CUDA generator state (seed and offset), so that each can draw its slice of the
-        one noise stream a single-GPU run would draw."""
+        """Give every rank of the grid rank 0's generator state (seed and offset), so that each can draw its part of the
+        one noise stream a single-GPU run would draw: first along the dataset group, then along the query group."""
         if not self.cfg.sync_noise:
             return
         import torch.distributed as dist
-        state = torch.cuda.get_rng_state(dev).to(dev)
-        dist.broadcast(state, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
-        torch.cuda.set_rng_state(state.cpu(), dev)
+        cuda = dev.type == "cuda"
+        state = (torch.cuda.get_rng_state(dev) if cuda else torch.get_rng_state()).to(dev)
+        for grp in (self.group, self.query_group):
+            if grp is not None and dist.get_world_size(grp) > 1:
+                dist.broadcast(state, src=dist.get_global_rank(grp, 0), group=grp)
+        if cuda:
+            torch.cuda.set_rng_state(state.cpu(), dev)
+        else:
+            torch.set_rng_state(state.cpu())
 
     @staticmethod
     def _cuda_generator(dev: torch.device):
@@ -717,58 +809,19 @@ class PosteriorEngine:
         return self.backend.noised_rows_philox(seed, offset, step, x0f, temps.sqrt().contiguous(), x0_absmax=x0_absmax,
                                                want_x=not tensor, want_split=tensor)
 
-    def _prefetch_group(self):
-        """A communicator of its own for the operand exchange of the sliced path: on the engine's group it would queue
-        in front of the (tiny, latency-critical) merge all-gather of the block being computed."""
-        if getattr(self, "_pf_group", None) is None:
-            import torch.distributed as dist
-            ranks = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
-            self._pf_group = dist.new_group(ranks=ranks)
-        return self._pf_group
-
-    def _sliced_prepare(self, x0: Tensor, x0f: Tensor, temps: Tensor, dev: torch.device, fused: bool = False,
-                        x0_absmax=None) -> dict:
-        """Operands of the rows (t, b), t in ``temps``: this rank draws the noise of its ceil(nb/world) temperatures
-        by positioning the generator at the offset those calls have in the full stream (torch.randn per temperature,
-        utils/stats.py:74, :273), prepares them, and the ranks all-gather the prepared operands.  The generator ends
-        where a single-GPU run would leave it."""
-        import torch.distributed as dist
-        rank = dist.get_rank(self.group)
-        nb, b = temps.shape[0], x0f.shape[0]
-        k = (nb + self.world - 1) // self.world
-        lo, hi = min(nb, rank * k), min(nb, (rank + 1) * k)
-        gen = self._cuda_generator(dev)
-        step = self._randn_offset_step(tuple(x0.shape), dev)
-        base = gen.get_offset()
-        my_t = torch.ones(k, dtype=torch.float32, device=dev)
-        my_t[:hi - lo] = temps[lo:hi]
-        if fused:
-            local = self._fused_prepare(gen.initial_seed(), base + lo * step, step, x0f, my_t, x0_absmax)
-        else:
-            noise = torch.zeros(k, b, self.ds.d, dtype=torch.float32, device=dev)
-            for j in range(lo, hi):
-                gen.set_offset(base + j * step)
-                torch.randn(*x0.shape, device=dev, out=noise[j - lo].view(x0.shape))
-            local = self._prepare(x0f, k * b, noise.view(k * b, -1), my_t.repeat_interleave(b).sqrt(), None,
-                                  self.precision(), False)
-            del noise
-        gen.set_offset(base + nb * step)
-        out = {}
-        for key, t in local.items():
-            if t is None:
-                out[key] = None
-                continue
-            full = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            dist.all_gather_into_tensor(full, t.contiguous(), group=self._prefetch_group())
-            out[key] = full[:nb * b]
-        return out
-
     # -- posterior mean ---------------------------------------------------------------------------
     def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None,
-                       values: Optional[Tensor] = None) -> Tensor:
+                       values: Optional[Tensor] = None, temp_bounds: Optional[tuple] = None) -> Tensor:
         """x0_hat[r] = sum_j p_rj y_j with p ~ exp(-||x_r*post_r - y_j||^2 / (2 T_r)).  Returns (M, d).
-        ``values`` (N, dv) replaces y_j in the weighted sum (posterior mean of arbitrary per-point vectors)."""
+        ``values`` (N, dv) replaces y_j in the weighted sum (posterior mean of arbitrary per-point vectors).
+
+        Nothing in here waits for the device: which rows are delta posteriors, which row tiles a screening stage left
+        unproven and which tiles have to be contracted are tile lists whose lengths stay in device memory
+        (pdm_stats_args.n_row_tiles_dev and the *_tiles entry points), so a sampling loop enqueues step after step.
+        ``temp_bounds`` = (lowest, highest) temperature of the call as host floats (the sampler knows them); without it
+        an engine with screening on reads the two numbers back once per call."""
         dev = self.backend.device
+        be = self.backend
         ds = self.ds
         xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
         m = xf.shape[0]
@@ -783,86 +836,80 @@ class PosteriorEngine:
             if values.shape[0] != ds.n:
                 raise PdmError("values must have one row per dataset row")
             if tensor:
-                vscale = pow2_scale_for(float(self.backend.absmax(values).item()))
-                vt = self.backend.transpose_split(values, vscale) + (vscale,)
-        out = torch.empty(m, ds.d if values is None else values.shape[1], dtype=torch.float32, device=dev)
+                vscale = pow2_scale_for(float(be.absmax(values).item()))
+                vt = be.transpose_split(values, vscale) + (vscale,)
+        src = ds.y if values is None else values
+        out = torch.empty(m, src.shape[1], dtype=torch.float32, device=dev)
         step = max(128, min(m, self.cfg.max_energy_bytes // (ds.n * 8)))
-        ph = getattr(self.backend, "phase", None)
+        rpt = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)          # the fused kernel's row tile
+        tile_ops = tensor and hasattr(be, "delta_tile_list")                             # device-side tile lists available
+        ph = getattr(be, "phase", None)
         if ph is None:
             import contextlib
             ph = lambda _n: contextlib.nullcontext()      # noqa: E731
+        screen_on = self.screening_usable() and tile_ops and m > 0
+        if screen_on:
+            self._pm_poll()
+            if temp_bounds is None:
+                temp_bounds = tuple(float(v) for v in torch.stack([temp_rows.min(), temp_rows.max()]).cpu())
         for r0 in range(0, m, step):
             r1 = min(m, r0 + step)
             rows = r1 - r0
+            tiles = (rows + rpt - 1) // rpt
             inv_temp = (1.0 / temp_rows[r0:r1]).contiguous()
+            out_blk = out[r0:r1]
             with ph("prepare"):
                 prep = self._prepare(xf[r0:r1], rows, None, None, None if post is None else post[r0:r1], precision, False)
-            if self.screening_usable():
-                # Certified delta posteriors (the low-noise steps of a sampling trajectory): when the one-product pass proves
-                # every row of the block a delta, the mean is a gather of nearest training points -- no full-precision
-                # distances, no energy tile.  A failed attempt at temperature T is repeated below T/2, a success at T moves
-                # the mark up to 1.5 T (the mark persists across calls: one dataset, one boundary).
-                t_lo, t_hi = (float(v) for v in torch.stack([temp_rows[r0:r1].min(), temp_rows[r0:r1].max()]).cpu())
-                if t_hi < self._pm_screen_t:
-                    with ph("screen"):
-                        flags, arg1, _, n_listed, _, left8 = self._screen_cascade(prep, rows, inv_temp, t_hi < self._pm_f8_t)
-                        proven = int(n_listed.item()) == 0
-                    if left8 is not None:                      # same kind of mark for the E4M3 first stage
-                        self._pm_f8_t = 0.5 * t_lo if left8 > 0.75 else (
-                            max(self._pm_f8_t, 1.5 * t_hi) if math.isfinite(self._pm_f8_t) else self._pm_f8_t)
-                    self.screen_report["pm_rows_screened"] = self.screen_report.get("pm_rows_screened", 0) + rows
-                    if proven:
-                        self._pm_screen_t = max(self._pm_screen_t, 1.5 * t_hi) if math.isfinite(self._pm_screen_t) else self._pm_screen_t
-                        self.screen_report["pm_rows_certified"] = self.screen_report.get("pm_rows_certified", 0) + rows
-                        src = ds.y if values is None else values
-                        local = arg1 - ds.index_offset
-                        own = (local >= 0) & (local < ds.n)
-                        out[r0:r1].copy_(src.index_select(0, local.clamp(0, ds.n - 1)) * own[:, None].to(src.dtype))
-                        continue
-                    self._pm_screen_t = 0.5 * t_lo
+            # Certified delta posteriors (the low-noise steps of a sampling trajectory): the one-product passes prove rows to
+            # be deltas; only the row tiles with an unproven row get full-precision distances at all.  The marks move on the
+            # counts of EARLIER calls (a failed attempt at temperature T is repeated below T/2, a success moves the mark up
+            # to 1.5 T; they persist across calls: one dataset, one boundary).
+            listed = None                    # (tile list, device-side length) of the full-precision pass; None = every tile
+            flags_s = arg_s = None
+            if screen_on and temp_bounds[1] < self._pm_screen_t:
+                with ph("screen"):
+                    flags_s, arg_s, tl, nl, _, nl8 = self._screen_cascade_async(prep, rows, inv_temp, temp_bounds[1] < self._pm_f8_t)
+                    listed = (tl, nl)
+                    self._pm_report(nl, nl8, tiles, rows, temp_bounds[0], temp_bounds[1])
             with ph("prepare"):
                 energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
             with ph("fused+energy"):
-                parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0)
+                kw = {} if listed is None else dict(row_tiles=listed[0], n_row_tiles=tiles, n_row_tiles_dev=listed[1])
+                parts = self._local_partials(prep, rows, inv_temp, None, precision, energy_out=energy, energy_mult=1.0, **kw)
             with ph("merge"):
                 st, amin = self._merge(parts, inv_temp)
+            if flags_s is not None:
+                y_hi, y_lo = ds.split()                   # proven rows: l = 1, arg-min of the screening passes
+                be.screen_finalize(flags_s, arg_s, ds.d, (prep["hi"], prep["lo"], prep["inv_scale"]), prep["norms"],
+                                   (y_hi, None if precision == "f16x2" else y_lo), 1.0 / ds.scale, ds.y_norm, None,
+                                   ds.index_offset, ds.n, ds.n_total, st, amin)
             e_min, l = st[_cabi.OUT_E_MIN], st[_cabi.OUT_L]
-            out_blk, sel = out[r0:r1], None
-            if self.cfg.delta_shortcut:
-                # Rows whose posterior is a delta to fp32 resolution (every other weight sums to <= 2^-23): the mean IS
-                # the nearest training point -- a gather (on the shard that owns it) instead of weights + contraction.
+            # Rows whose posterior is a delta to fp32 resolution (every other weight sums to <= 2^-23): the mean IS the
+            # nearest training point -- a gather (on the shard that owns it) instead of weights + second contraction.
+            dflags = todo = None
+            if (self.cfg.delta_shortcut or flags_s is not None) and hasattr(be, "delta_tile_list"):
                 with ph("delta rows"):
-                    delta = (l - 1.0) <= 2.0 ** -23
-                    n_delta = int(delta.sum().item())
-                    if n_delta > 0:
-                        src = ds.y if values is None else values
-                        local = amin - ds.index_offset
-                        own = delta & (local >= 0) & (local < ds.n)
-                        picked = src.index_select(0, local.clamp(0, ds.n - 1)) * own[:, None].to(src.dtype)
-                        if n_delta == rows:
-                            out_blk.copy_(picked)
-                            continue
-                        sel = (~delta).nonzero().flatten()
-                        out_blk.copy_(picked * delta[:, None].to(src.dtype))
-                        energy, e_min, l, inv_temp = (energy.index_select(0, sel), e_min.index_select(0, sel).contiguous(),
-                                                      l.index_select(0, sel).contiguous(), inv_temp.index_select(0, sel).contiguous())
-            target = out_blk if sel is None else torch.empty(sel.shape[0], out.shape[1], dtype=torch.float32, device=dev)
+                    dflags, tl2, nl2 = be.delta_tile_list(l, rpt)
+                    todo = (tl2, nl2)
             if tensor:
                 with ph("weights"):
-                    p_hi, p_lo = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=True)
+                    tkw = {} if todo is None else dict(tiles=(todo[0], rpt, tiles, todo[1]))
+                    p_hi, p_lo = be.weights_from_energy(energy, e_min, l, inv_temp, split=True, **tkw)
                 with ph("gemm2"):
                     yt_hi, yt_lo, yscale = vt if vt is not None else (ds.transposed_split() + (ds.scale,))
                     if vt is None and precision == "f16x2":
                         yt_lo = None                      # lattice dataset: weights_hi.Y + weights_lo.Y is all there is
-                    self.backend.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=target,
-                                            cta_group=self.cfg.cta_group)
+                    tkw = {} if todo is None else dict(tiles=(todo[0], tiles, todo[1]))
+                    be.split_gemm(p_hi, p_lo, yt_hi, yt_lo, ds.n, (1.0 / 16384.0) / yscale, out=out_blk,
+                                  cta_group=self.cfg.cta_group, **tkw)
             else:
                 with ph("weights"):
-                    p = self.backend.weights_from_energy(energy, e_min, l, inv_temp, split=False)
+                    p = be.weights_from_energy(energy, e_min, l, inv_temp, split=False)
                 with ph("gemm2"):
-                    self.backend.weighted_mean_exact(p, ds.y if values is None else values, out=target)
-            if sel is not None:
-                out_blk.index_copy_(0, sel, target)
+                    be.weighted_mean_exact(p, src, out=out_blk)
+            if dflags is not None:
+                with ph("delta rows"):
+                    be.gather_rows(src, amin, ds.index_offset, dflags, out_blk)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out, group=self.group)

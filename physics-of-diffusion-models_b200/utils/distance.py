@@ -7,6 +7,8 @@ The arithmetic runs in the CUDA library (pdm_b200); there is no PyTorch or CPU f
 """
 from __future__ import annotations
 
+import weakref
+from collections import OrderedDict
 from typing import Optional
 
 import torch
@@ -43,8 +45,28 @@ def norm_sqr(x: Tensor) -> Tensor:
     return _be().row_norms(_to_engine(x)).to(x.device)
 
 
+_DATASETS: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def _dataset_for(ref: Tensor) -> EmpiricalDataset:
+    """The prepared form of ``ref`` (row norms, operand split) is kept for the last few tensors seen, keyed by storage
+    address / shape / version and tied to the tensor by a weak reference: loops that call compute_pw_dist_sqr(x, y)
+    against the same y (the k-NN searches of the scripts) prepare it once."""
+    key = (ref.data_ptr(), tuple(ref.shape), ref.dtype, str(ref.device), ref._version)
+    hit = _DATASETS.get(key)
+    if hit is not None and hit[0]() is ref:
+        _DATASETS.move_to_end(key)
+        return hit[1]
+    ds = EmpiricalDataset(ref, backend=_be())
+    _DATASETS[key] = (weakref.ref(ref), ds)
+    for k in [k for k, (r, _) in _DATASETS.items() if r() is None]:
+        del _DATASETS[k]
+    while len(_DATASETS) > 2:
+        _DATASETS.popitem(last=False)
+    return ds
+
+
 def compute_pw_dist_sqr(x: Tensor, y: Optional[Tensor] = None) -> Tensor:
     """Dense pairwise squared distances (utils/distance.py:13-21)."""
     ref = x if y is None else y
-    ds = EmpiricalDataset(ref, backend=_be())
-    return PosteriorEngine(ds).pairwise_sqdist(x).to(x.device)
+    return PosteriorEngine(_dataset_for(ref)).pairwise_sqdist(x).to(x.device)

@@ -29,56 +29,96 @@ from torch.utils.data import DataLoader
 from tqdm import tqdm
 
 from pdm_b200 import EmpiricalDataset, PosteriorEngine
-from pdm_b200.engine import default_backend, detect_lattice_scale
+from pdm_b200.engine import LATTICE_INT_MAX, LATTICE_RATIO_MAX, default_backend, lattice_candidates
+from pdm_b200.sharding import ShardGrid, make_grid
 
 _ENGINES: dict[int, tuple] = {}
+_GRID = None
 
 
-def _sharding_group():
-    """Row-shard the dataset over torch.distributed's default group when PDM_SHARD_DATASET=1."""
+def _grid():
+    """The node's GPUs as dataset shards x query groups (pdm_b200/sharding.py) when PDM_SHARD_DATASET=1 and
+    torch.distributed is initialised; PDM_DATA_SHARDS picks the number of dataset shards (default 2)."""
+    global _GRID
     if os.environ.get("PDM_SHARD_DATASET", "0") != "1":
-        return None, 0, 1
+        return ShardGrid()
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return None, 0, 1
-    return dist.group.WORLD, dist.get_rank(), dist.get_world_size()
+        return ShardGrid()
+    if _GRID is None or _GRID[0] != dist.get_world_size():
+        _GRID = (dist.get_world_size(), make_grid(int(os.environ.get("PDM_DATA_SHARDS", "0"))))
+    return _GRID[1]
+
+
+def _all_reduce(t: Tensor, op: str, group) -> Tensor:
+    import torch.distributed as dist
+    dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op], group=group)
+    return t
+
+
+def _sharded_lattice_scale(backend, shard: Tensor, absmax: float, group) -> float:
+    """detect_lattice_scale for a row-sharded dataset: every rank tests its own rows, the verdict is the worst shard's."""
+    if not hasattr(backend, "lattice_residual"):
+        return 0.0
+    for s in lattice_candidates(absmax):
+        rv = backend.lattice_residual(shard, s)
+        rv = _all_reduce(rv.clone(), "max", group)
+        ratio, vmax = rv.tolist()
+        if ratio <= LATTICE_RATIO_MAX and vmax <= LATTICE_INT_MAX:
+            return s
+    return 0.0
 
 
 def _engine_for(dataloader: DataLoader) -> PosteriorEngine:
-    """One resident dataset (and engine) per DataLoader object."""
+    """One resident dataset (and engine) per DataLoader object.  With a grid only this rank's rows are uploaded."""
     key = id(dataloader)
     hit = _ENGINES.get(key)
     if hit is not None and hit[0]() is dataloader:
         return hit[1]
     backend = default_backend()
-    chunks = [batch[0].to(backend.device, non_blocking=True) for batch in dataloader]
-    data = torch.cat(chunks, dim=0)
-    group, rank, world = _sharding_group()
-    n_total = data.shape[0]
-    if world > 1:
-        per = (n_total + world - 1) // world
-        lo, hi = rank * per, min(n_total, (rank + 1) * per)
-        flat = data.reshape(n_total, -1).to(torch.float32).contiguous()
-        amax = float(backend.absmax(flat).item())
-        lattice = detect_lattice_scale(backend, flat, amax)      # every rank must agree on the operand scale
-        ds = EmpiricalDataset(data[lo:hi], backend=backend, index_offset=lo, n_total=n_total, global_absmax=amax,
+    grid = _grid()
+    if grid.data_shards > 1:
+        n_total = len(dataloader.dataset)
+        lo, hi = grid.rows(n_total)
+        chunks, seen = [], 0
+        for batch in dataloader:
+            x = batch[0]
+            a, b = max(lo, seen), min(hi, seen + len(x))
+            if a < b:
+                chunks.append(x[a - seen:b - seen].to(backend.device, non_blocking=True))
+            seen += len(x)
+        if seen != n_total:
+            raise RuntimeError(f"the DataLoader yielded {seen} rows, its dataset holds {n_total}: a row-sharded engine "
+                               "needs a loader that visits every row once (no drop_last / sampler subsets)")
+        shard = torch.cat(chunks, dim=0)
+        flat = shard.reshape(shard.shape[0], -1).to(torch.float32).contiguous()
+        amax = float(_all_reduce(backend.absmax(flat).clone(), "max", grid.data_group).item())
+        lattice = _sharded_lattice_scale(backend, flat, amax, grid.data_group)   # every rank must agree on the operand scale
+        ds = EmpiricalDataset(shard, backend=backend, index_offset=lo, n_total=n_total, global_absmax=amax,
                               lattice_scale=lattice)
-        ds.full_moments_source = data          # Tr Sigma_0 is a whole-dataset quantity
     else:
-        ds = EmpiricalDataset(data, backend=backend)
-    eng = PosteriorEngine(ds, group=group)
+        ds = EmpiricalDataset(torch.cat([batch[0].to(backend.device, non_blocking=True) for batch in dataloader], dim=0),
+                              backend=backend)
+    eng = PosteriorEngine(ds, group=grid.data_group, query_group=grid.query_group)
     _ENGINES[key] = (weakref.ref(dataloader, lambda _r, k=key: _ENGINES.pop(k, None)), eng)
     return eng
 
 
 def _dataset_summary(eng: PosteriorEngine) -> tuple[float, float, float]:
-    """(Tr Sigma_0, min, max) of the whole dataset, computed once (utils/stats.py:39, 66, 176)."""
+    """(Tr Sigma_0, min, max) of the whole dataset, computed once (utils/stats.py:39, 66, 176).  Row-sharded: the
+    shards' column sums / sums of squares are added and their extrema combined (two small all-reduces)."""
     cached = getattr(eng, "_summary", None)
     if cached is None:
-        src = getattr(eng.ds, "full_moments_source", None)
-        ds = eng.ds if src is None else EmpiricalDataset(src, backend=eng.backend)
-        lo, hi = ds.value_range()
-        cached = (ds.tr_sigma0(), lo, hi)
+        ds = eng.ds
+        if eng.world > 1:
+            s, s2, mm = ds.moments()
+            s, s2 = _all_reduce(s.clone(), "sum", eng.group), _all_reduce(s2.clone(), "sum", eng.group)
+            ext = _all_reduce(torch.stack([-mm[0], mm[1]]), "max", eng.group)
+            n = float(ds.n_total)
+            cached = (float(((s2 - s * s / n) / (n - 1.0)).sum().item()), -float(ext[0].item()), float(ext[1].item()))
+        else:
+            lo, hi = ds.value_range()
+            cached = (ds.tr_sigma0(), lo, hi)
         eng._summary = cached
     return cached
 
@@ -91,34 +131,36 @@ def _k_smallest(eng: PosteriorEngine, mat: Tensor, k: int) -> Tensor:
 
 
 def _knn_sigma_reg_sq(eng: PosteriorEngine, knn_k: int, sigma_reg_scale: float) -> Tensor:
-    """d_k^2 * scale / D with d_k the distance to the k-th neighbour, self excluded
-    (utils/stats.py:137-146, where sklearn's kneighbors(k+1) runs on the CPU).  With a row-sharded dataset every
-    rank searches its own shard for all N points and the per-shard candidates are merged (all-gather of k+1
-    distances per point and shard)."""
+    """d_k^2 * scale / D with d_k the distance to the k-th neighbour, self excluded, for every point of the dataset
+    (utils/stats.py:137-146, where sklearn's kneighbors(k+1) runs on the CPU).  Row-sharded dataset: the shards take
+    turns as the query set -- the owner broadcasts a chunk of its rows, every rank searches its own shard, the k+1
+    candidates per shard are all-gathered and merged -- so no rank ever holds more than its shard plus one chunk."""
     ds = eng.ds
-    queries = ds.y
-    if eng.world > 1:
-        src = getattr(ds, "full_moments_source", None)
-        if src is None:
-            raise NotImplementedError("adaptive k-NN regularisation with a sharded dataset needs the full dataset as queries")
-        queries = src.reshape(src.shape[0], -1).to(device=ds.y.device, dtype=torch.float32)
-    n_q = queries.shape[0]
     kk = min(knn_k + 1, ds.n_total)
     k_local = min(kk, ds.n)
-    out = torch.empty(n_q, dtype=torch.float32, device=ds.y.device)
-    step = max(1, min(n_q, (1 << 30) // (4 * ds.n)))
-    for r0 in range(0, n_q, step):
-        d2 = eng.pairwise_sqdist(queries[r0:r0 + step])
-        cand = _k_smallest(eng, d2, k_local)
-        if eng.world > 1:
-            import torch.distributed as dist
+    dev = ds.y.device
+    out = torch.empty(ds.n_total, dtype=torch.float32, device=dev)
+    step = max(1, (1 << 30) // (4 * max(1, ds.n)))
+    if eng.world == 1:
+        for r0 in range(0, ds.n, step):
+            out[r0:r0 + step] = _k_smallest(eng, eng.pairwise_sqdist(ds.y[r0:r0 + step]), kk)[:, -1].clamp_(min=0)
+        return out * sigma_reg_scale / float(ds.d)
+    import torch.distributed as dist
+    rank = dist.get_rank(eng.group)
+    per = (ds.n_total + eng.world - 1) // eng.world
+    for owner in range(eng.world):
+        o_lo, o_hi = min(ds.n_total, owner * per), min(ds.n_total, (owner + 1) * per)
+        for r0 in range(o_lo, o_hi, step):
+            r1 = min(o_hi, r0 + step)
+            q = ds.y[r0 - o_lo:r1 - o_lo].contiguous() if owner == rank else torch.empty(r1 - r0, ds.d, dtype=torch.float32, device=dev)
+            dist.broadcast(q, src=dist.get_global_rank(eng.group, owner), group=eng.group)
+            cand = _k_smallest(eng, eng.pairwise_sqdist(q), k_local)
             if k_local < kk:
-                cand = torch.cat([cand, torch.full((cand.shape[0], kk - k_local), float("inf"), device=cand.device)], dim=1)
-            allc = torch.empty(eng.world * cand.shape[0], kk, dtype=cand.dtype, device=cand.device)   # rank-major
+                cand = torch.cat([cand, torch.full((cand.shape[0], kk - k_local), float("inf"), device=dev)], dim=1)
+            allc = torch.empty(eng.world * cand.shape[0], kk, dtype=cand.dtype, device=dev)   # rank-major
             dist.all_gather_into_tensor(allc, cand.contiguous(), group=eng.group)
             allc = allc.view(eng.world, cand.shape[0], kk).permute(1, 0, 2).reshape(cand.shape[0], -1).contiguous()
-            cand = _k_smallest(eng, allc, kk)
-        out[r0:r0 + step] = cand[:, -1].clamp_(min=0)
+            out[r0:r1] = _k_smallest(eng, allc, kk)[:, -1].clamp_(min=0)
     return out * sigma_reg_scale / float(ds.d)
 
 

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pdm_b200.h but not exported"
         assert n in _cabi.SIGNATURES, f"{n} has no ctypes signature in pdm_b200/_cabi.py"
-    assert lib.pdm_abi_version() == 3
+    assert lib.pdm_abi_version() == 4
 
 
 def test_stats_args_layout_matches_c(lib):

@@ -1,0 +1,545 @@
+"""GPU parity AT THE CONFIGURATIONS BASELINE.json NAMES, against the CPU oracle (fp32 restatement of the reference
+plus its fp64 re-evaluation as arbiter) -- not against the repo's own exact kernel.
+
+  C1   anisotropic GMM, N = 10 000, d = 64, 100 temperatures logspace(-4, 4), B = 1024 (scripts/reproduce_high_dim.py:18-46,
+       config/high_dim_exp.yaml:2-4): the WHOLE configuration through utils.compute_stats_batch and
+       utils.compute_metric_stats_batch, and row by row through the engine (every statistic, arg-min included).
+  C2   CIFAR-10 shape, N = 50 000, d = 3072: 64 queries x 12 temperatures of the 1000-step linear-beta schedule chosen across
+       the transition band (uniform data and a clustered variant): e_min, log_l, mean_e, mean_e2, var_e, entropy, arg-min,
+       and the ideal denoiser Scheduler.true_posterior_mean_x0 at the same noise levels.
+  NN   the nearest / second-nearest neighbour flow of scripts/analyze_cifar_nn.py:37-47 at its own size (5000, 3072) on the
+       tensor path: indices bit-exact wherever the reference's fp32 and fp64 evaluations agree.
+  MU   utils.metric_utils at D >= 64 (tensor path) with fp64 arbitration and a tolerance derived from the per-sample error.
+  OL   the outer loops compute_stats / compute_metric_stats / compute_thermo_stats against the golden run of the
+       unmodified reference (tests/golden/outer_loops.npz), fed the reference's own CPU noise draws.
+
+Tolerance contract as in tests/test_gpu_kernels.py:  |ours - ref64| <= max(1e-4 |ref64| + atol, 2 |ref32 - ref64|, floor)
+with floor = 8 * 2^-24 (|x|^2 + max|y|^2) on an energy (divided by T on the min-shifted exponents): the a-priori round-off of
+ANY fp32 evaluation of |x|^2 - 2 x.y + |y|^2.  Every test also reports (-s / -rA) which rows the floor, rather than the
+1e-4 relative bound, is the binding tolerance for -- those rows are only constrained to fp32 round-off, not to 1e-4.
+"""
+import math
+
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+from conftest import load_golden
+from oracle import posterior as orc
+from oracle import synthetic as syn
+from test_gpu_kernels import arbitrated_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend(cuda_device):
+    from pdm_b200.backend import CudaBackend
+    return CudaBackend(cuda_device)
+
+
+class _Replay:
+    """Noise hook that feeds the engine the CPU draws of the reference's RNG order, batch after batch."""
+
+    def __init__(self, eps_per_batch):
+        self.eps, self.batch = eps_per_batch, -1
+
+    def __call__(self, i, shape, dev):
+        if i == 0:
+            self.batch += 1
+        return self.eps[self.batch][i].reshape(shape).to(dev)
+
+
+@pytest.fixture()
+def replay(cuda_device):
+    from pdm_b200 import PosteriorEngine
+    import utils.stats as ustats
+    ustats._ENGINES.clear()
+
+    def install(eps_per_batch):
+        hook = _Replay(eps_per_batch)
+        PosteriorEngine.noise_hook = staticmethod(hook)
+        return hook
+    yield install
+    PosteriorEngine.noise_hook = None
+    ustats._ENGINES.clear()
+
+
+def _floors(xq, data, temp_rows):
+    xn = (xq.double().reshape(len(xq), -1) ** 2).sum(1)
+    yn = (data.double().reshape(len(data), -1) ** 2).sum(1).max()
+    f_e = 8 * 2.0 ** -24 * (xn + yn)
+    return f_e, f_e / temp_rows.double()
+
+
+def _oracle_rows(xq, data, temp_rows, aux=None, chunk=2048):
+    """fp32 and fp64 oracle statistics of explicit query rows (evaluated in chunks of rows: C1 has 102 400 of them)."""
+    res = {}
+    flat = data.reshape(len(data), -1)
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        y = flat.to(dt)
+        acc = {}
+        for r0 in range(0, len(xq), chunk):
+            e = 0.5 * orc.pairwise_sqdist(xq[r0:r0 + chunk].to(dt), y)
+            st = orc.boltzmann_rows(e, temp_rows[r0:r0 + chunk].to(dt)[:, None], aux=None if aux is None else aux.to(dt))
+            two = torch.topk(e, min(2, e.shape[1]), dim=1, largest=False).values
+            st["gap"] = (two[:, -1] - two[:, 0]) if e.shape[1] > 1 else torch.full_like(two[:, 0], float("inf"))
+            del st["weights"], e
+            for k, v in st.items():
+                acc.setdefault(k, []).append(v)
+        st = {k: torch.cat(v) for k, v in acc.items()}
+        st["entropy"] = st["log_l"] + st["mean_e"] - math.log(len(data))
+        res[name] = st
+    res["floor_E"], res["floor_e"] = _floors(xq, data, temp_rows)
+    return res
+
+
+def _report_binding(name, ref, temp_rows, rtol=1e-4, atol=1e-5):
+    """Which rows are constrained by the 1e-4 relative bound and which only by the fp32 round-off floor."""
+    r64 = ref["f64"]
+    rel = rtol * (r64["log_l"].abs() + r64["mean_e"].abs()).double() + atol
+    floor_binds = ref["floor_e"] > rel
+    t = temp_rows.double()
+    if floor_binds.any():
+        t_hi = t[floor_binds].max().item()
+        print(f"[parity {name}] fp32 round-off floor is the binding tolerance for {int(floor_binds.sum())} of {len(t)} rows "
+              f"(all rows with T <= {t_hi:.3g}); the remaining {int((~floor_binds).sum())} rows are held to 1e-4 relative")
+    else:
+        print(f"[parity {name}] every one of the {len(t)} rows is held to 1e-4 relative")
+
+
+def _report_errors(what, ours, ref32, ref64, rtol=1e-4, atol=1e-5):
+    """Achieved accuracy, independent of the floor: our error and the reference's own fp32 error against fp64, and the share
+    of entries that meet the bare 1e-4 relative bound."""
+    ours, ref32, ref64 = ours.detach().double().cpu(), ref32.detach().double().cpu(), ref64.detach().double().cpu()
+    e_ours, e_ref = (ours - ref64).abs(), (ref32 - ref64).abs()
+    bare = rtol * ref64.abs() + atol
+    print(f"[parity {what}] max|ours-f64| {e_ours.max().item():.2e} (rms {e_ours.pow(2).mean().sqrt().item():.2e}); reference's own "
+          f"max|f32-f64| {e_ref.max().item():.2e} (rms {e_ref.pow(2).mean().sqrt().item():.2e}); within bare 1e-4: ours "
+          f"{100 * (e_ours <= bare).double().mean().item():.2f} %, reference fp32 {100 * (e_ref <= bare).double().mean().item():.2f} %")
+
+
+def _check_argmin(ours, ref, xq, data, what):
+    """Nearest-neighbour index: identical to the fp64 oracle's wherever fp32 can resolve it at all -- the gap between the two
+    smallest fp64 energies exceeds 2 * floor_E, twice the round-off of an fp32 energy -- and otherwise one of the near-ties
+    (its fp64 energy within 2 * floor_E of the minimum).  (Agreement of the reference's own fp32 and fp64 evaluations is not a
+    usable criterion at high temperature: with |x|^2 ~ d T the ulp of an energy exceeds the gaps, the fp32 reference itself
+    picks among the near-ties by chance, and its errors are not ours.)"""
+    r32, r64 = ref["f32"], ref["f64"]
+    ours = ours.cpu()
+    same = ours == r64["argmin"]
+    resolvable = r64["gap"] > 2 * ref["floor_E"]
+    assert bool(same[resolvable].all()), f"{what}: arg-min differs from fp64 on {int((~same[resolvable]).sum())} resolvable rows"
+    bad = ~same
+    if bad.any():
+        flat = data.reshape(len(data), -1)
+        e_ours = 0.5 * ((xq[bad].double().reshape(int(bad.sum()), -1) - flat[ours[bad]].double()) ** 2).sum(1)
+        excess = e_ours - r64["e_min"][bad]
+        assert bool((excess <= 2 * ref["floor_E"][bad]).all()), f"{what}: arg-min is not a near-tie (excess {excess.max().item():.3e})"
+    print(f"[parity {what}] arg-min identical to fp64 on {int(same.sum())} of {len(same)} rows: all {int(resolvable.sum())} rows whose "
+          f"gap fp32 can resolve, and {int((same & ~resolvable).sum())} of the {int((~resolvable).sum())} near-ties; the reference's own "
+          f"fp32 arg-min differs from fp64 on {int((r32['argmin'] != r64['argmin']).sum())} rows")
+
+
+def _check_rows(st, ref, what, aux=False, xq=None, data=None):
+    r32, r64 = ref["f32"], ref["f64"]
+    for k in ("e_min", "log_l", "mean_e", "var_e", "entropy"):
+        _report_errors(f"{what} {k}", st[k], r32[k], r64[k])
+    _check_argmin(st["argmin"], ref, xq, data, what)
+    fE, fe = ref["floor_E"], ref["floor_e"]
+    fe2 = fe * (1 + 2 * r64["mean_e"].double())
+    arbitrated_close(st["e_min"], r32["e_min"], r64["e_min"], atol=1e-5, what=what + " e_min", floor=fE)
+    arbitrated_close(st["log_l"], r32["log_l"], r64["log_l"], atol=1e-5, what=what + " log_l", floor=fe)
+    arbitrated_close(st["mean_e"], r32["mean_e"], r64["mean_e"], atol=1e-5, what=what + " mean_e", floor=fe)
+    arbitrated_close(st["mean_e2"], r32["mean_e2"], r64["mean_e2"], atol=1e-5, what=what + " mean_e2", floor=fe2)
+    arbitrated_close(st["var_e"], r32["var_e"], r64["var_e"], atol=2e-5, what=what + " var_e", floor=fe2)
+    arbitrated_close(st["entropy"], r32["entropy"], r64["entropy"], atol=2e-5, what=what + " entropy", floor=2 * fe)
+    if aux:
+        arbitrated_close(st["aux_mean"], r32["aux_mean"], r64["aux_mean"], atol=1e-7, what=what + " aux_mean")
+
+
+# ------------------------------------------------------------------------------------------------
+# C1: the whole configuration
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c1():
+    data = syn.anisotropic_gmm(64, 5, 10_000, 42)
+    temp = torch.logspace(-4, 4, 100)
+    x0 = data[:1024].clone()
+    torch.manual_seed(4242)
+    eps = orc.draw_noise(x0.shape, len(temp))
+    xt = eps * temp.sqrt()[:, None, None] + x0                           # randn * sqrt(T) + x0, utils/stats.py:74, :273
+    return {"data": data, "temp": temp, "x0": x0, "eps": eps, "xt": xt}
+
+
+@pytest.fixture(scope="module")
+def c1_ref(c1):
+    """One oracle pass (fp32 + fp64) over all 102 400 rows of C1, with the k-NN regulariser as the aux vector."""
+    n_t, b = c1["xt"].shape[:2]
+    sig = orc.knn_sigma_reg_sq(c1["data"], 5, 1.0)
+    ref = _oracle_rows(c1["xt"].reshape(n_t * b, -1), c1["data"], c1["temp"].repeat_interleave(b), aux=sig)
+    ref["sigma_reg_sq"] = sig
+    return ref
+
+
+def test_c1_whole_compute_stats_batch(c1, c1_ref, replay):
+    import utils
+    replay([c1["eps"]])
+    loader = DataLoader(TensorDataset(c1["data"]), batch_size=100, shuffle=False)       # the stock dataloader_batch_size
+    ent = utils.compute_stats_batch(loader, c1["x0"], c1["temp"])["entropy"]
+    assert ent.shape == (100, 1024) and ent.device.type == "cpu"
+    n_t, b = ent.shape
+    ref32 = orc.entropy_batch(c1["xt"], c1["data"], c1["temp"])          # the reference's op order, utils/stats.py:282-289
+    ref64 = c1_ref["f64"]["entropy"].view(n_t, b)
+    fe = c1_ref["floor_e"].view(n_t, b)
+    arbitrated_close(ent, ref32, ref64, atol=2e-5, floor=2 * fe, what="C1 entropy (compute_stats_batch)")
+    # the curve the scripts save: mean over the queries
+    arbitrated_close(ent.mean(1), ref32.mean(1), ref64.mean(1), atol=2e-5, floor=2 * fe.mean(1), what="C1 entropy curve")
+    _report_errors("C1 entropy via utils.compute_stats_batch", ent.reshape(-1), ref32.reshape(-1), ref64.reshape(-1))
+
+
+def test_c1_whole_every_statistic(c1, c1_ref, backend):
+    """All 102 400 rows of C1 through the engine (the precision the drop-in picks for d = 64): every statistic, the aux
+    accumulator and the arg-min against the oracle."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine
+    eng = PosteriorEngine(EmpiricalDataset(c1["data"], backend=backend))
+    n_t, b = c1["xt"].shape[:2]
+    xq = c1["xt"].reshape(n_t * b, -1)
+    t_rows = c1["temp"].repeat_interleave(b)
+    st = {k: v.cpu() for k, v in eng.stats(xq, t_rows, aux=c1_ref["sigma_reg_sq"].to(backend.device)).items()}
+    _report_binding("C1", c1_ref, t_rows)
+    _check_rows(st, c1_ref, f"C1 rows ({eng.precision()})", aux=True, xq=xq, data=c1["data"])
+
+
+def test_c1_whole_metric_stats_batch(c1, c1_ref, replay, capsys):
+    import utils
+    loader = DataLoader(TensorDataset(c1["data"]), batch_size=100, shuffle=False)
+    n_t, b = c1["xt"].shape[:2]
+    fe = c1_ref["floor_e"].view(n_t, b)
+    floor = (fe * (1 + 2 * c1_ref["f64"]["mean_e"].view(n_t, b).double())).mean(1)
+
+    def metric_of(rows, tag):                       # utils/stats.py:90-111 from the oracle's per-row statistics
+        var = rows["var_e"].view(n_t, b)
+        t = c1["temp"].to(var.dtype)[:, None]
+        if tag == "global":
+            var = torch.maximum(var, orc.gaussian_cluster_metric(torch.tensor(1e-3, dtype=var.dtype), t))
+        elif tag == "knn":
+            var = torch.maximum(var, orc.gaussian_cluster_metric(rows["aux_mean"].view(n_t, b), t))
+        return var.mean(1)
+
+    for tag, kw in (("plain", {}), ("global", {"regularize": True}),
+                    ("knn", {"regularize": True, "adaptive_knn": True, "knn_k": 5, "sigma_reg_scale": 1.0})):
+        replay([c1["eps"]])
+        got = utils.compute_metric_stats_batch(loader, c1["x0"], c1["temp"], **kw)["metric_values"]
+        assert got.shape == (n_t,) and got.device.type == "cpu"
+        arbitrated_close(got, metric_of(c1_ref["f32"], tag), metric_of(c1_ref["f64"], tag), atol=2e-5, floor=floor,
+                         what=f"C1 metric {tag}")
+    assert "Tr(Sigma0)=" in capsys.readouterr().out
+    # the regulariser itself: k-NN on the GPU against the brute-force fp64 search
+    from utils.stats import _engine_for, _knn_sigma_reg_sq
+    torch.testing.assert_close(_knn_sigma_reg_sq(_engine_for(loader), 5, 1.0).cpu(), c1_ref["sigma_reg_sq"], rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# C2: N = 50 000, d = 3072, temperatures of the 1000-step DDPM schedule across the transition band
+# ------------------------------------------------------------------------------------------------
+def _pick_temps(targets):
+    temps = syn.ddpm_temperatures(1000)
+    idx = sorted({int((temps.log() - math.log(t)).abs().argmin()) for t in targets})
+    return torch.tensor(idx), temps[idx]
+
+
+C2_CASES = {
+    # delta posteriors to fp32 resolution up to T ~ 13; log l leaves 0 around T ~ 25 and saturates above T ~ 1000
+    "uniform": (lambda: syn.uniform_images(50_000, (3, 32, 32), 0),
+                (1e-4, 1.0, 10.0, 20.0, 30.0, 40.0, 60.0, 100.0, 150.0, 300.0, 1000.0, 2.478e4)),
+    # 500 clusters of 100 points, spread 0.05: members separate around T ~ 0.1, clusters around T ~ 100
+    "clustered": (lambda: syn.clustered_images(50_000, (3, 32, 32), 500, 0.05, 1),
+                  (1e-4, 1e-3, 1e-2, 3e-2, 0.1, 0.3, 1.0, 10.0, 60.0, 150.0, 400.0, 2.478e4)),
+}
+
+
+@pytest.fixture(scope="module", params=sorted(C2_CASES))
+def c2(request):
+    make, targets = C2_CASES[request.param]
+    data = make()
+    idx, temps = _pick_temps(targets)
+    b = 64
+    x0 = data[:b].clone()
+    eps = torch.randn(len(temps), b, 3, 32, 32, generator=syn.gen(77))
+    return {"name": request.param, "data": data, "idx": idx, "temps": temps, "x0": x0, "eps": eps}
+
+
+def test_c2_statistics_full_size(c2, backend):
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    data, temps, b = c2["data"], c2["temps"], c2["x0"].shape[0]
+    xt = (c2["eps"] * temps.sqrt()[:, None, None, None, None] + c2["x0"]).reshape(len(temps) * b, -1)
+    t_rows = temps.repeat_interleave(b)
+    ref = _oracle_rows(xt, data, t_rows)
+    _report_binding(f"C2 {c2['name']}", ref, t_rows)
+    spread = ref["f64"]["log_l"].view(len(temps), b).mean(1)
+    print(f"[parity C2 {c2['name']}] T = {[round(float(t), 4) for t in temps]}\n"
+          f"             mean log l = {[round(float(v), 3) for v in spread]}  (0 = delta, {math.log(len(data)):.2f} = uniform)")
+    assert spread[0] < 1e-3 and spread[-1] > 0.9 * math.log(len(data))          # the picks straddle the transition
+    assert ((spread > 0.05) & (spread < 0.9 * math.log(len(data)))).sum() >= 3  # and several sit inside it
+    ds = EmpiricalDataset(data, backend=backend)
+    eng = PosteriorEngine(ds, EngineConfig(screen=False))
+    assert eng.precision() == "f16x3"
+    st = {k: v.cpu() for k, v in eng.stats(xt, t_rows).items()}
+    _check_rows(st, ref, f"C2 {c2['name']} explicit rows", xq=xt, data=data)
+    # the same rows through the reference-facing noise path (noise replayed), plain and with certified delta posteriors
+    from pdm_b200 import PosteriorEngine as PE
+    PE.noise_hook = staticmethod(lambda i, shape, dev: c2["eps"][i].reshape(shape).to(dev))
+    try:
+        for screen in (False, True):
+            eng = PosteriorEngine(ds, EngineConfig(screen=screen))
+            ns = eng.noised_stats(c2["x0"], temps)
+            st = {k: v.reshape(-1).cpu() for k, v in ns.items()}
+            _check_rows(st, ref, f"C2 {c2['name']} noised_stats screen={screen}", xq=xt, data=data)
+            if screen:
+                assert eng.screen_report["rows_certified"] >= b, eng.screen_report       # the low-noise rows were proven
+    finally:
+        PE.noise_hook = None
+    del ds
+    torch.cuda.empty_cache()
+
+
+def test_c2_ideal_denoiser_full_size(c2, cuda_device):
+    """Scheduler.true_posterior_mean_x0 (diffusion/scheduler/scheduler.py:58-69) at N = 50 000, d = 3072 for the noise
+    levels of the transition band, against the oracle's fp32 restatement and its fp64 re-evaluation."""
+    import diffusion.scheduler.scheduler as sched
+    from diffusion.scheduler import LinearBetaScheduler
+    sched._DENOISER_ENGINES.clear()
+    data, b = c2["data"], c2["x0"].shape[0]
+    sch = LinearBetaScheduler(1e-4, 2.478e4)
+    tau_all = torch.linspace(0, 1, 1001)[1:]
+    data_dev = data.to(cuda_device)
+    worst = 0.0
+    for k, i in enumerate(c2["idx"].tolist()):
+        tau = tau_all[i].view(1)
+        ab = torch.sigmoid(-orc.linear_beta_log_temp(tau, 1e-4, 2.478e4))
+        xt = ab.sqrt() * c2["x0"] + (1 - ab).sqrt() * c2["eps"][k]
+        got = sch.true_posterior_mean_x0(xt.to(cuda_device), tau.to(cuda_device), data_dev)
+        assert got.shape == xt.shape and got.dtype == torch.float32 and got.device.type == "cuda"
+        ref32 = orc.posterior_mean_x0(xt, ab, data)
+        ref64 = orc.posterior_mean_x0(xt, ab, data, dtype=torch.float64)
+        arbitrated_close(got, ref32, ref64, atol=5e-5, what=f"C2 {c2['name']} x0_hat at tau index {i}")
+        worst = max(worst, (got.cpu().double() - ref64).abs().max().item())
+    print(f"[parity C2 {c2['name']}] ideal denoiser: worst |x0_hat - fp64| over {len(c2['idx'])} noise levels = {worst:.2e}")
+    sched._DENOISER_ENGINES.clear()
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# nearest-neighbour flow of scripts/analyze_cifar_nn.py:37-47 at (5000, 3072), tensor path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["uniform", "pixels"])
+def test_nn_indices_bit_exact_at_5000x3072(cuda_device, kind):
+    import utils
+    if kind == "uniform":
+        pts = syn.uniform_images(5000, (3, 32, 32), 12)
+    else:                                                    # ToTensor + Normalize(0.5, 0.5) of 8-bit pixels (utils/data.py:43-52)
+        px = torch.randint(0, 256, (5000, 3, 32, 32), generator=syn.gen(13), dtype=torch.uint8)
+        pts = (px.float() / 255 - 0.5) / 0.5
+    d = utils.compute_pw_dist_sqr(pts.to(cuda_device))       # self-distances, as the script calls it
+    assert d.shape == (5000, 5000) and d.device.type == "cuda"
+    d32 = orc.pairwise_sqdist(pts)
+    d64 = orc.pairwise_sqdist(pts.double())
+    yn = (pts.double().reshape(5000, -1) ** 2).sum(1)
+    floor = 8 * 2.0 ** -24 * (yn[:, None] + yn[None, :])
+    arbitrated_close(d, d32, d64, atol=2e-5, floor=floor, what=f"{kind} dense squared distances")
+    refs = []
+    for m in (d32.clone(), d64.clone(), d.clone()):
+        m.fill_diagonal_(1e10)
+        nn1, i1 = m.min(dim=1)
+        m.scatter_(1, i1.unsqueeze(1), 1e10)
+        nn2, i2 = m.min(dim=1)
+        refs.append((i1.cpu(), i2.cpu()))
+    (a1, a2), (b1, b2), (g1, g2) = refs
+    agree1, agree2 = a1 == b1, (a1 == b1) & (a2 == b2)
+    assert agree1.float().mean() > 0.99
+    assert torch.equal(g1[agree1], b1[agree1]) and torch.equal(g2[agree2], b2[agree2])
+
+
+# ------------------------------------------------------------------------------------------------
+# utils.metric_utils at D >= 64 (tensor path), fp64 arbitration
+# ------------------------------------------------------------------------------------------------
+class _ReplayDraws:
+    def __init__(self, mod, idx, eps):
+        self.mod, self.idx, self.eps = mod, idx, eps
+
+    def __enter__(self):
+        self.ri, self.rn = torch.randint, torch.randn
+        self.mod.torch.randint = lambda *a, **k: self.idx.to(k.get("device", "cpu"))
+        self.mod.torch.randn = lambda *a, **k: self.eps.to(k.get("device", "cpu"))
+
+    def __exit__(self, *exc):
+        self.mod.torch.randint, self.mod.torch.randn = self.ri, self.rn
+
+
+def _var_tol(ref64_scores, delta_rms, rtol=1e-4):
+    """|Var(s + delta) - Var(s)| <= 2 std(s) rms(delta) + rms(delta)^2 for a per-sample perturbation delta."""
+    sd = ref64_scores.double().std(dim=0)
+    return 2 * sd * delta_rms + delta_rms ** 2 + rtol * ref64_scores.double().var(dim=0)
+
+
+@pytest.mark.parametrize("dim,sigma_sq", [(64, 1e-3), (64, 0.3), (128, 0.05)])
+def test_metric_utils_tensor_path_fp64_arbitrated(cuda_device, dim, sigma_sq):
+    """compute_metric_scalar / compute_metric_matrix / compute_rescaled_metric_matrix (utils/metric_utils.py:4-216) with
+    K = 2000 prior samples in D >= 64 dimensions: the engine takes the tensor path.  The estimators are D/2 - Var_y(score):
+    a per-sample score error delta moves the variance by at most 2 std rms(delta) + rms(delta)^2, and delta itself is
+    bounded by the fp32 round-off floor of an energy over T (scalar case) -- that, 1e-4 relative, or twice the reference's
+    own fp32-vs-fp64 gap, whichever is largest, is the tolerance."""
+    import utils
+    import utils.metric_utils as mu
+    g = syn.gen(1000 + dim)
+    k, n_y = 2000, 512
+    x = torch.randn(k, dim, generator=g) * torch.linspace(0.5, 1.5, dim)
+    idx = torch.randint(0, k, (n_y,), generator=g)
+    eps = torch.randn(n_y, dim, generator=g)
+    xd = x.to(cuda_device)
+    # scalar
+    with _ReplayDraws(mu, idx, eps):
+        got = utils.compute_metric_scalar(math.log(sigma_sq), xd, n_y)
+    assert got.device.type == "cuda"
+    s2 = torch.exp(torch.tensor(math.log(sigma_sq)))
+    y = x[idx] + torch.sqrt(s2) * eps
+    ref32 = orc.metric_scalar_from_samples(y, x, s2)
+    ref64 = orc.metric_scalar_from_samples(y.double(), x.double(), s2.double())
+    f_e, _ = _floors(y, x, torch.ones(n_y))
+    delta_rms = (f_e / sigma_sq).pow(2).mean().sqrt()
+    w = torch.softmax(-0.5 * orc.pairwise_sqdist(y.double(), x.double()) / sigma_sq, dim=1)
+    scores64 = (w * (-0.5 * dim + 0.5 * orc.pairwise_sqdist(y.double(), x.double()) / sigma_sq)).sum(1)
+    tol = max(_var_tol(scores64[:, None], delta_rms).item(), 2 * abs(ref32.double().item() - ref64.item()))
+    err = abs(got.double().item() - ref64.item())
+    print(f"[parity metric_utils D={dim} sigma^2={sigma_sq}] scalar: ours {got.item():.6f} ref64 {ref64.item():.6f} "
+          f"ref32 {ref32.item():.6f} tol {tol:.2e}")
+    assert err <= tol, (err, tol)
+    # diagonal metric + rescaled metric
+    sig = torch.full((dim,), sigma_sq) * torch.linspace(0.7, 1.4, dim)
+    lam = torch.diag(sig.log())
+    with _ReplayDraws(mu, idx, eps):
+        got_m = utils.compute_metric_matrix(lam.to(cuda_device), xd, n_y)
+    with _ReplayDraws(mu, idx, eps):
+        got_r = utils.compute_rescaled_metric_matrix(sig.to(cuda_device), xd, n_y)
+    # the reference's own y draw for the matrix case goes through eigh(Lambda); replay it on the CPU in fp32
+    evals, evecs = torch.linalg.eigh(lam)
+    sqrt_sigma = evecs @ torch.diag(torch.sqrt(torch.exp(evals))) @ evecs.t()
+    y_m = x[idx] + (sqrt_sigma @ eps.t()).t()
+    sig_m = torch.diag(evecs @ torch.diag(torch.exp(evals)) @ evecs.t())
+    y_r = x[idx] + torch.sqrt(sig) * eps
+    for name, got_v, yv, sv, fn in (("matrix", got_m, y_m, sig_m, orc.metric_matrix_from_samples),
+                                    ("rescaled", got_r, y_r, sig, orc.rescaled_metric_from_samples)):
+        r32 = fn(yv, x, sv)
+        r64 = fn(yv.double(), x.double(), sv.double())
+        # per-sample, per-dimension score error: the weights move by (energy floor in whitened coordinates) and the
+        # second moment <(y_i - x_i)^2> carries 2^-22 |x_i|^2 of split round-off, both over Sigma_ii (Sigma_ii^2 rescaled)
+        w_floor, _ = _floors(yv / sv.sqrt(), x / sv.sqrt(), torch.ones(n_y))
+        _, m2 = orc.diag_marginal_scores(yv.double()[:128], x.double(), sv.double())
+        scale = (0.5 / sv if name == "matrix" else 0.5 / sv ** 2).double()
+        delta = scale * (m2.mean(0) * w_floor.mean() + 2.0 ** -21 * (x.double() ** 2).max(0).values)
+        scores = (-0.5 + 0.5 * m2 / sv.double()) if name == "matrix" else (-0.5 / sv.double() + 0.5 * m2 / sv.double() ** 2)
+        tol = torch.maximum(_var_tol(scores, delta), 2 * (r32.double() - r64).abs())
+        if name == "rescaled":
+            tol = tol * (4 * sv ** 2 / (torch.var(x, dim=0) + 2 * sv)).double()
+        err = (got_v.cpu().double() - r64).abs()
+        print(f"[parity metric_utils D={dim} sigma^2={sigma_sq}] {name}: worst err {err.max().item():.2e}, "
+              f"worst err/tol {(err / tol).max().item():.2f}, |ref32-ref64| {(r32.double() - r64).abs().max().item():.2e}")
+        assert (err <= tol).all(), f"{name}: {(err / tol).max().item():.2f} x tolerance"
+
+
+# ------------------------------------------------------------------------------------------------
+# outer loops against the golden run of the unmodified reference
+# ------------------------------------------------------------------------------------------------
+def _outer_batches(data):
+    i = 0
+    while True:
+        yield (data[(i * 20) % 120:(i * 20) % 120 + 20],)
+        i += 1
+
+
+def _draw_outer(seed, shape, n_t, n_batches, mode, leading_loader_pass=False):
+    torch.manual_seed(seed)
+    if leading_loader_pass:
+        orc._dataloader_seed_draw()
+    return [orc.draw_noise(shape, n_t, loader_iters=mode) for _ in range(n_batches)]
+
+
+def test_outer_loops_on_gpu_match_reference_golden(replay):
+    """compute_stats (utils/stats.py:295-311), compute_metric_stats (:116-183) and the legacy-schema extension
+    compute_thermo_stats on the GPU against outputs of the UNMODIFIED reference, fed the reference's CPU noise draws
+    (randn per temperature interleaved with its DataLoader passes)."""
+    import utils
+    g = load_golden("outer_loops.npz")
+    data, temp, seed = g["data"], g["temp"], int(g["seed"])
+    n_t, shape = len(temp), (20,) + tuple(data.shape[1:])
+    loader = DataLoader(TensorDataset(data), batch_size=50, shuffle=False)
+    flat = data.reshape(len(data), -1)
+
+    def xt_of(eps_list):
+        gen = _outer_batches(data)
+        return [e * temp.sqrt().view(-1, 1, 1, 1, 1) + next(gen)[0] for e in eps_list]
+
+    def floor_of(xts):
+        fl = []
+        for xt in xts:
+            _, fe = _floors(xt.reshape(n_t * 20, -1), flat, temp.repeat_interleave(20))
+            fl.append(fe.view(n_t, 20))
+        return torch.cat(fl, dim=1)
+
+    def mean_e_of(xts):
+        return torch.cat([torch.stack([orc.boltzmann_rows(0.5 * orc.pairwise_sqdist(x[i].double(), flat.double()),
+                                                          temp[i].double())["mean_e"] for i in range(n_t)]) for x in xts], dim=1)
+
+    # compute_stats: 3 batches of 20, one DataLoader pass after every draw
+    eps = _draw_outer(seed, shape, n_t, 3, "per_temp")
+    replay(eps)
+    st = utils.compute_stats(loader, _outer_batches(data), temp, 60)
+    assert set(st) == {"entropy", "temp"} and st["entropy"].device.type == "cpu"
+    xts = xt_of(eps)
+    ref64 = torch.cat([orc.entropy_batch(x, flat, temp, dtype=torch.float64) for x in xts], dim=1).mean(1)
+    arbitrated_close(st["entropy"], g["entropy"], ref64, atol=2e-5, floor=2 * floor_of(xts).mean(1), what="compute_stats entropy")
+    # compute_metric_stats: one pass before each batch's draws
+    eps = _draw_outer(seed, shape, n_t, 3, "once_before")
+    replay(eps)
+    mt = utils.compute_metric_stats(loader, _outer_batches(data), temp, 60)
+    assert set(mt) == {"temp", "metric", "log_temp", "dataset_tr_sigma0"}
+    xts = xt_of(eps)
+    ref64 = torch.stack([orc.metric_batch(x, flat, temp, dtype=torch.float64) for x in xts], dim=1).double().mean(1)
+    me64 = mean_e_of(xts)
+    arbitrated_close(mt["metric"], g["metric"], ref64, atol=2e-5, floor=(floor_of(xts) * (1 + 2 * me64)).mean(1),
+                     what="compute_metric_stats metric")
+    torch.testing.assert_close(mt["dataset_tr_sigma0"], g["metric_tr"].float(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(mt["log_temp"], g["metric_log_temp"])
+    # ... with the adaptive k-NN regulariser: a DataLoader pass for the k-NN search first (:130-133)
+    eps = _draw_outer(seed, shape, n_t, 2, "once_before", leading_loader_pass=True)
+    replay(eps)
+    mk = utils.compute_metric_stats(loader, _outer_batches(data), temp, 40, regularize=True, adaptive_knn=True, knn_k=3,
+                                    sigma_reg_scale=0.5)
+    xts = xt_of(eps)
+    sig = orc.knn_sigma_reg_sq(data, 3, 0.5)
+    ref64 = torch.stack([orc.metric_batch(x, flat, temp, dtype=torch.float64, regularize=True, sigma_reg_sq_per_point=sig)
+                         for x in xts], dim=1).double().mean(1)
+    me64 = mean_e_of(xts)
+    arbitrated_close(mk["metric"], g["metric_knn"], ref64, atol=2e-5, floor=(floor_of(xts) * (1 + 2 * me64)).mean(1),
+                     what="compute_metric_stats metric (k-NN regulariser)")
+    # legacy notebook schema (analyze_stats.ipynb:73-80): log_Z, U, var_H ... of the same pass, against the fp64 oracle
+    eps = _draw_outer(seed, shape, n_t, 3, "none")
+    replay(eps)
+    th = utils.compute_thermo_stats(loader, _outer_batches(data), temp, 60)
+    assert {"temp", "log_Z", "U", "full_U", "var_H", "entropy", "heat_capacity", "free_energy"} <= set(th)
+    xts = xt_of(eps)
+    rows = [orc.boltzmann_rows(0.5 * orc.pairwise_sqdist(x.reshape(n_t * 20, -1).double(), flat.double()),
+                               temp.double().repeat_interleave(20)[:, None]) for x in xts]
+    t64 = temp.double()
+    cat = lambda k: torch.cat([r[k].view(n_t, 20) for r in rows], dim=1)         # noqa: E731
+    fl = floor_of(xts)
+    log_z = (cat("log_l") - math.log(len(data))).mean(1)
+    u = (cat("mean_e") * t64[:, None]).mean(1)
+    var_h = (cat("var_e") * t64[:, None] ** 2).mean(1)
+    for key, want, floor in (("log_Z", log_z, fl.mean(1)), ("U", u, (fl * t64[:, None]).mean(1)),
+                             ("full_U", u + cat("e_min").mean(1), 2 * (fl * t64[:, None]).mean(1)),
+                             ("var_H", var_h, (fl * (1 + 2 * cat("mean_e")) * t64[:, None] ** 2).mean(1)),
+                             ("heat_capacity", cat("var_e").mean(1), (fl * (1 + 2 * cat("mean_e"))).mean(1)),
+                             ("entropy", (cat("log_l") + cat("mean_e") - math.log(len(data))).mean(1), 2 * fl.mean(1))):
+        arbitrated_close(th[key], want.float(), want, atol=2e-5, floor=floor, what=f"compute_thermo_stats {key}")

@@ -41,7 +41,8 @@ class SplitFakeBackend(FakeBackend):
         return r
 
     def posterior_stats(self, *, precision, M, N, d, q_norm, y_norm, inv_temp, q_split=None, y_split=None,
-                        y_inv_scale=1.0, y_aux=None, index_offset=0, n_splits=0, row_tiles=None, n_row_tiles=0, **kw):
+                        y_inv_scale=1.0, y_aux=None, index_offset=0, n_splits=0, row_tiles=None, n_row_tiles=0,
+                        n_row_tiles_dev=None, **kw):
         if precision == "exact":
             return super().posterior_stats(precision=precision, M=M, N=N, d=d, q_norm=q_norm, y_norm=y_norm,
                                            inv_temp=inv_temp, y_aux=y_aux, index_offset=index_offset, n_splits=n_splits, **kw)
@@ -55,9 +56,13 @@ class SplitFakeBackend(FakeBackend):
         y = (yv * y_inv_scale).float()
         self.calls.append(f"stats:{precision}:{'list' if row_tiles is not None else 'all'}")
         parts = super().posterior_stats(precision="exact", M=M, N=N, d=d, q_norm=q_norm, y_norm=y_norm, inv_temp=inv_temp,
-                                        q=q, y=y, y_aux=y_aux, index_offset=index_offset, n_splits=n_splits)
+                                        q=q, y=y, y_aux=y_aux, index_offset=index_offset, n_splits=n_splits,
+                                        energy_out=kw.get("energy_out"), energy_mult=kw.get("energy_mult", 1.0))
         if row_tiles is not None:
             keep = torch.zeros(M, dtype=torch.bool)
+            if n_row_tiles_dev is not None:                 # ABI v4: the list's length lives "on the device"
+                n_row_tiles = min(int(n_row_tiles), int(n_row_tiles_dev[0]))
+                self.calls.append(f"tiles:{precision}:{n_row_tiles}")
             for t in row_tiles[:n_row_tiles].tolist():
                 keep[t * self.row_tile:(t + 1) * self.row_tile] = True
             parts[~keep] = float("nan")                    # rows outside the list are never written by the kernel
@@ -81,6 +86,61 @@ class SplitFakeBackend(FakeBackend):
         tile_list = torch.zeros(max(1, tiles), dtype=torch.int32)
         tile_list[:len(listed)] = torch.tensor(listed, dtype=torch.int32)
         return tile_list, torch.tensor([len(listed)], dtype=torch.int32)
+
+    # ---- ABI v4: tile lists whose length stays on the device (sync-free posterior mean) ----
+    def _listed_rows(self, m, tiles):
+        tl, rpt, n_max, n_dev = tiles
+        n = min(int(n_max), int(n_dev[0])) if n_dev is not None else int(n_max)
+        keep = torch.zeros(m, dtype=torch.bool)
+        for t in tl[:n].tolist():
+            keep[t * rpt:(t + 1) * rpt] = True
+        return keep, n
+
+    def delta_tile_list(self, l, rows_per_tile):
+        flags = ((l - 1.0) <= 2.0 ** -23).to(torch.uint8)
+        tl, n = self.screen_tile_list(flags, rows_per_tile)
+        return flags, tl, n
+
+    def screen_merge_stage(self, tile_list, n_listed, max_tiles, rows_per_tile, flags_b, arg_b, flags, arg):
+        keep, _ = self._listed_rows(flags.numel(), (tile_list, rows_per_tile, max_tiles, n_listed))
+        take = keep & (flags == 0)
+        flags[take] = flags_b[take]
+        arg[take] = arg_b[take]
+
+    def gather_rows(self, src, idx, index_offset, flags, out):
+        sel = torch.ones(idx.numel(), dtype=torch.bool) if flags is None else flags != 0
+        j = idx - index_offset
+        own = (j >= 0) & (j < src.shape[0])
+        picked = src[j.clamp(0, src.shape[0] - 1)] * own[:, None].to(src.dtype)
+        out[sel] = picked[sel]
+        return out
+
+    def transpose_split(self, y, scale):
+        hi, lo = _split16(y.t().contiguous(), torch.tensor(float(scale)))
+        return hi, lo
+
+    def weights_from_energy(self, energy, e_min, l, inv_temp, *, split, tiles=None):
+        p = super().weights_from_energy(energy, e_min, l, inv_temp, split=False)
+        if tiles is not None:
+            keep, n = self._listed_rows(energy.shape[0], tiles)
+            self.calls.append(f"weights:{n}")
+            p[~keep] = float("nan")                         # rows outside the list are never written
+        if not split:
+            return p
+        return _split16(p, torch.tensor(16384.0))
+
+    def split_gemm(self, a_hi, a_lo, b_hi, b_lo, k, scale, out=None, accumulate=False, cta_group=0, tiles=None):
+        a = a_hi.double() + a_lo.double()
+        b = b_hi.double() + (b_lo.double() if b_lo is not None else 0.0)
+        r = (torch.nan_to_num(a) @ b.t() * scale).float()
+        if out is None:
+            out = torch.zeros_like(r)
+        keep = torch.ones(a.shape[0], dtype=torch.bool)
+        if tiles is not None:
+            keep, n = self._listed_rows(a.shape[0], (tiles[0], self.row_tile, tiles[1], tiles[2]))
+            self.calls.append(f"gemm2:{n}")
+        out[keep] = r[keep] if not accumulate else out[keep] + r[keep]
+        return out
 
     def screen_temperatures(self, q_norm, inv_temp, y_norm_max, g, e_star, kappa):
         delta = kappa * 2.0 ** -10 * q_norm.sqrt() * y_norm_max.sqrt() + 2.4e-7 * (q_norm + y_norm_max)
@@ -291,8 +351,9 @@ def test_e4m3_cascade_is_sound_and_falls_through_to_the_fp16_stage():
 
 
 def test_posterior_mean_of_a_fully_proven_block_is_a_gather():
-    """Low-noise ideal-denoiser call: every row certified -> x0_hat = the nearest training points, no energy tile, no
-    weights, no second contraction (the test double has none: reaching them would raise)."""
+    """Low-noise ideal-denoiser call: every row certified -> x0_hat = the nearest training points.  The path never reads a
+    count back (ABI v4: tile lists with device-side lengths), so the full-precision pass, the weights and the second
+    contraction are still ENQUEUED -- over empty tile lists."""
     data, _ = _setup(n=300, d=64, b=8)
     g = syn.gen(77)
     idx = torch.tensor([1, 7, 50, 120, 299, 200, 10, 11])         # none of them the duplicated point 5 / 37
@@ -305,5 +366,24 @@ def test_posterior_mean_of_a_fully_proven_block_is_a_gather():
         assert torch.equal(got, data[idx])
         want = orc.posterior_mean_x0(xt, ab, data, dtype=torch.float64)
         assert (got.double() - want).abs().max() < 1e-6
+        eng._pm_poll(wait=True)                                   # the counts arrive behind the call (lagged feedback)
         assert eng.screen_report["pm_rows_certified"] == len(idx)
         assert ("stats:f8x1:all" in be.calls) == f8
+        assert "tiles:f16x3:0" in be.calls and "weights:0" in be.calls and "gemm2:0" in be.calls
+
+
+def test_posterior_mean_mixed_block_contracts_only_the_listed_tiles():
+    """Rows of both kinds in one call: proven rows are gathered, the tile with the near-tie row goes through the
+    full-precision pass, the weights and the second contraction -- and nothing else does."""
+    data, _ = _setup(n=300, d=64, b=8)
+    g = syn.gen(78)
+    idx = torch.tensor([1, 7, 50, 120, 299, 200, 10, 11, 5, 60, 61, 62, 63, 64, 65, 66])     # row 8 sits on the duplicate 5 / 37
+    be = SplitFakeBackend()
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=be), EngineConfig(precision="f16x3", screen=True, screen_f8=False))
+    ab = torch.tensor(0.9999)
+    xt = ab.sqrt() * data[idx] + (1 - ab).sqrt() * torch.randn(len(idx), 64, generator=g)
+    got = eng.posterior_mean(xt, ((1 - ab) / ab).expand(len(idx)), post=ab.rsqrt().expand(len(idx)))
+    want = orc.posterior_mean_x0(xt, ab, data, dtype=torch.float64)
+    assert (got.double() - want).abs().max() < 1e-5
+    assert torch.equal(got[:8], data[idx[:8]])                     # first tile: every row proven
+    assert "tiles:f16x3:1" in be.calls and "weights:1" in be.calls and "gemm2:1" in be.calls

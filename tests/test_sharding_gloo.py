@@ -1,6 +1,8 @@
-"""World-size-2 gloo run of the sharded path on the CPU (test double of the backend): every rank holds half of
-the dataset rows, sees all queries, reduces its own partial records, all-gathers one record per row and
-merges.  The result must equal the unsharded one (the merge is pure math)."""
+"""gloo runs of the sharded path on the CPU (test double of the backend) over the 2-D grid of pdm_b200/sharding.py:
+dataset shards x query groups.  Within a dataset group every rank holds a slice of the dataset rows, reduces its own
+partial records, all-gathers one record per row and merges; within a query group the temperatures of the schedule are
+dealt round-robin and the results all-gathered.  Whatever the layout, the result must equal the unsharded one on the
+same noise stream (the merge is pure math)."""
 import os
 import socket
 import sys
@@ -13,6 +15,8 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
+N, D, B = 101, 12, 9
+
 
 def _free_port():
     with socket.socket() as s:
@@ -20,7 +24,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _inputs():
+    g = torch.Generator().manual_seed(0)
+    data = torch.randn(N, D, generator=g)
+    x0 = data[:B].clone()
+    temp = torch.logspace(-2, 2, 7)                       # 7 temperatures: ragged against 2 and 4 query groups
+    aux = torch.rand(N, generator=g) + 0.1
+    xq = x0 + 0.3 * torch.randn(B, D, generator=torch.Generator().manual_seed(5))
+    up = torch.randn(B, D, generator=torch.Generator().manual_seed(6))
+    return data, x0, temp, aux, xq, up
+
+
+def _worker(rank, world, data_shards, port, out_dir):
     for p in (ROOT, os.path.join(ROOT, "physics-of-diffusion-models_b200"), HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -29,64 +44,86 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fake_backend import FakeBackend
     from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
-    g = torch.Generator().manual_seed(0)
-    n, d, b = 101, 12, 9
-    data = torch.randn(n, d, generator=g)
-    x0 = data[:b].clone()
-    temp = torch.logspace(-2, 2, 5)
-    per = (n + world - 1) // world
-    lo, hi = rank * per, min(n, (rank + 1) * per)
+    from pdm_b200.sharding import make_grid
+    data, x0, temp, aux, xq, up = _inputs()
+    grid = make_grid(data_shards)
+    assert grid.world == world and grid.data_shards == data_shards
+    lo, hi = grid.rows(N)
     be = FakeBackend()
-    ds = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=n)
-    eng = PosteriorEngine(ds, EngineConfig(precision="exact"), group=dist.group.WORLD)
-    torch.manual_seed(100 + rank)                     # ranks draw DIFFERENT noise: rank 0's is broadcast
+    ds = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=N)
+    eng = PosteriorEngine(ds, EngineConfig(precision="exact"), group=grid.data_group, query_group=grid.query_group)
+    torch.manual_seed(100 + rank)                     # ranks start on DIFFERENT streams: rank 0's state is adopted
     st = eng.noised_stats(x0, temp)
-    xq = x0 + 0.3 * torch.randn(b, d, generator=torch.Generator().manual_seed(5))
-    mean = eng.posterior_mean(xq, torch.full((b,), 0.5))
-    up = torch.randn(b, d, generator=torch.Generator().manual_seed(6))
-    gq, gt = eng.posterior_mean_backward(xq, torch.full((b,), 0.5), None, up)
-    # adaptive k-NN regulariser on the sharded dataset: every rank searches its shard, candidates are merged
+    after = torch.randn(3)                            # the generator is left where the single-process run leaves it
+    torch.manual_seed(100 + rank)
+    st_aux = eng.noised_stats(x0, temp, aux=aux)      # per-point aux vector over the WHOLE dataset: cut to the shard
+    res = {"entropy": st["entropy"], "argmin": st["argmin"], "var_e": st["var_e"], "after": after,
+           "aux_mean": st_aux["aux_mean"], "calls": be.calls}
+    if grid.query_groups == 1:                        # the denoiser path shards the dataset only
+        res["mean"] = eng.posterior_mean(xq, torch.full((B,), 0.5))
+        res["gq"], res["gt"] = eng.posterior_mean_backward(xq, torch.full((B,), 0.5), None, up)
+    # the reference-facing functions over the same grid: only this rank's rows are uploaded, Tr Sigma_0 / range from
+    # all-reduced column moments, k-NN regulariser with the shards taking turns as the query set
     import utils.stats as ustats
-    ds.full_moments_source = data
-    sig = ustats._knn_sigma_reg_sq(eng, 5, 1.0)
-    torch.save({"entropy": st["entropy"], "argmin": st["argmin"], "var_e": st["var_e"], "mean": mean, "sigma_reg_sq": sig,
-                "gq": gq, "gt": gt,
-                "calls": be.calls}, os.path.join(out_dir, f"rank{rank}.pt"))
+    from torch.utils.data import DataLoader, TensorDataset
+    os.environ["PDM_SHARD_DATASET"] = "1"
+    os.environ["PDM_DATA_SHARDS"] = str(data_shards)
+    ustats.default_backend = lambda: be
+    ustats._GRID = (world, grid)
+    loader = DataLoader(TensorDataset(data.view(N, 1, D, 1)), batch_size=17, shuffle=False)
+    e2 = ustats._engine_for(loader)
+    assert e2.ds.n == hi - lo and e2.ds.n_total == N and e2.ds.index_offset == lo
+    res["sigma_reg_sq"] = ustats._knn_sigma_reg_sq(e2, 5, 1.0)
+    res["summary"] = torch.tensor(ustats._dataset_summary(e2))
+    torch.manual_seed(100 + rank)
+    res["metric_knn"] = ustats.compute_metric_stats_batch(loader, x0.view(B, 1, D, 1), temp, regularize=True, adaptive_knn=True,
+                                                          knn_k=5)["metric_values"]
+    torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(180)
-def test_two_rank_sharded_equals_unsharded(tmp_path):
-    world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    r0 = torch.load(tmp_path / "rank0.pt")
-    r1 = torch.load(tmp_path / "rank1.pt")
-    for k in ("entropy", "argmin", "var_e", "mean", "sigma_reg_sq", "gq", "gt"):
-        assert torch.equal(r0[k], r1[k]), k                  # both ranks end with the same merged result
-    assert "reduce" in r0["calls"]
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,data_shards", [(2, 2), (2, 1), (4, 2)])
+def test_grid_equals_unsharded(tmp_path, world, data_shards, capsys):
+    mp.spawn(_worker, args=(world, data_shards, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ranks = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    r0 = ranks[0]
+    for r in ranks[1:]:
+        for k in r0:
+            if k != "calls":
+                assert torch.equal(r0[k], r[k]), k            # every rank ends with the same result
+    if data_shards > 1:
+        assert "reduce" in r0["calls"]
 
     sys.path.insert(0, HERE)
     from fake_backend import FakeBackend
     from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
-    g = torch.Generator().manual_seed(0)
-    n, d, b = 101, 12, 9
-    data = torch.randn(n, d, generator=g)
-    x0 = data[:b].clone()
-    temp = torch.logspace(-2, 2, 5)
+    from oracle import posterior as orc
+    data, x0, temp, aux, xq, up = _inputs()
     eng = PosteriorEngine(EmpiricalDataset(data, backend=FakeBackend()), EngineConfig(precision="exact"))
     torch.manual_seed(100)                                    # rank 0's stream
     st = eng.noised_stats(x0, temp)
+    assert torch.equal(torch.randn(3), r0["after"])
     assert torch.equal(st["argmin"], r0["argmin"])
     torch.testing.assert_close(st["entropy"], r0["entropy"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(st["var_e"], r0["var_e"], rtol=1e-4, atol=1e-5)
-    xq = x0 + 0.3 * torch.randn(b, d, generator=torch.Generator().manual_seed(5))
-    torch.testing.assert_close(eng.posterior_mean(xq, torch.full((b,), 0.5)), r0["mean"], rtol=1e-5, atol=1e-6)
-    up = torch.randn(b, d, generator=torch.Generator().manual_seed(6))
-    gq, gt = eng.posterior_mean_backward(xq, torch.full((b,), 0.5), None, up)     # backward pass: shards sum to the whole
-    torch.testing.assert_close(r0["gq"], gq, rtol=1e-3, atol=1e-4 * gq.abs().max().item())     # fp32 sums, other order
-    torch.testing.assert_close(r0["gt"], gt, rtol=1e-3, atol=1e-4 * gt.abs().max().item())
-    from oracle import posterior as orc
+    torch.manual_seed(100)
+    st_aux = eng.noised_stats(x0, temp, aux=aux)
+    torch.testing.assert_close(st_aux["aux_mean"], r0["aux_mean"], rtol=1e-5, atol=1e-6)
+    assert (st_aux["aux_mean"] - st_aux["aux_mean"].mean()).abs().max() > 1e-3      # the check is not vacuous
+    if "mean" in r0:
+        torch.testing.assert_close(eng.posterior_mean(xq, torch.full((B,), 0.5)), r0["mean"], rtol=1e-5, atol=1e-6)
+        gq, gt = eng.posterior_mean_backward(xq, torch.full((B,), 0.5), None, up)   # backward pass: shards sum to the whole
+        torch.testing.assert_close(r0["gq"], gq, rtol=1e-3, atol=1e-4 * gq.abs().max().item())     # fp32 sums, other order
+        torch.testing.assert_close(r0["gt"], gt, rtol=1e-3, atol=1e-4 * gt.abs().max().item())
     import utils.stats as ustats
     torch.testing.assert_close(r0["sigma_reg_sq"], ustats._knn_sigma_reg_sq(eng, 5, 1.0), rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(r0["sigma_reg_sq"], orc.knn_sigma_reg_sq(data, 5, 1.0), rtol=1e-4, atol=1e-6)
+    want = torch.tensor([orc.dataset_trace_sigma0(data), data.min().item(), data.max().item()])
+    torch.testing.assert_close(r0["summary"], want, rtol=1e-5, atol=1e-6)
+    # the regularised metric through the drop-in on the grid == the oracle on the same noise stream
+    torch.manual_seed(100)
+    xt = orc.draw_noised_queries(x0, temp)
+    ref = orc.metric_batch(xt, data, temp, regularize=True, sigma_reg_sq_per_point=orc.knn_sigma_reg_sq(data, 5, 1.0))
+    torch.testing.assert_close(r0["metric_knn"], ref, rtol=2e-3, atol=1e-5)

@@ -1,5 +1,7 @@
-"""2+ GPU check (torchrun): the row-sharded statistics path with rank-sliced noise generation against the unsharded
-engine on the same seed -- same RNG stream, same statistics, same arg-min, same generator position afterwards.
+"""2+ GPU check (torchrun): the statistics path over the 2-D grid of pdm_b200/sharding.py (dataset shards x query groups)
+against the unsharded engine on the same seed -- same RNG stream, same statistics, same arg-min, bit-identical E_min, same
+generator position afterwards -- for every factorisation of the world size, with and without certified delta posteriors, plus
+the query-sharded ideal-denoiser sampler against the one-GPU sampler.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded_gpu.py
 """
@@ -43,44 +45,70 @@ def main():
 
     ref, off_ref = run(full, 123)
     other = 123 if rank == 0 else 999 + rank                  # with sync_noise every rank must end up on rank 0's stream
-    # last entry: certified delta posteriors (EngineConfig.screen) on the sharded dataset
-    for slice_noise, sync, seed, screen in ((True, False, 123, False), (False, False, 123, False), (True, True, other, False),
-                                            (False, True, other, False), (False, True, other, True)):
-        cfg = EngineConfig(max_query_bytes=96 << 20)          # several blocks of temperatures
-        cfg.slice_noise, cfg.sync_noise, cfg.screen = slice_noise, sync, screen
-        shard = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=n, global_absmax=amax, lattice_scale=lat)
-        eng = PosteriorEngine(shard, cfg, group=dist.group.WORLD)
-        st, off = run(eng, seed)
-        if screen:
-            rep = eng.screen_report
-            if rank == 0:
-                print("screened sharded run:", rep)
-            if rep["rows_certified"] < 10 * b or rep["rows_unscreened"] == 0:
+    from pdm_b200.sharding import make_grid
+    shapes = [g for g in range(1, world + 1) if world % g == 0]
+    for data_shards in shapes:
+        grid = make_grid(data_shards)
+        lo, hi = grid.rows(n)
+        for sync, seed, screen in ((False, 123, False), (True, other, False), (True, other, True)):
+            cfg = EngineConfig(max_query_bytes=96 << 20)          # several blocks of temperatures
+            cfg.sync_noise, cfg.screen = sync, screen
+            shard = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=n, global_absmax=amax, lattice_scale=lat)
+            eng = PosteriorEngine(shard, cfg, group=grid.data_group, query_group=grid.query_group)
+            st, off = run(eng, seed)
+            tag = f"rank {rank} grid {grid.data_shards}x{grid.query_groups} sync={sync} screen={screen}"
+            if screen:
+                rep = eng.screen_report
+                if rank == 0:
+                    print("screened sharded run:", grid.describe(), rep)
+                if rep["rows_certified"] < 10 * b // grid.query_groups or rep["rows_unscreened"] == 0:
+                    ok = False
+                    print(f"{tag}: screening did not engage as expected: {rep}")
+            xn = (x0.reshape(b, -1).double() ** 2).sum(1)[None, :] + d * temps.double()[:, None]
+            floor = 8 * 2.0 ** -24 * (xn + (data.double() ** 2).sum(1).max()) / temps.double()[:, None]
+            for k in ("log_l", "mean_e", "entropy"):
+                err = (st[k].double() - ref[k].double()).abs()
+                tol = torch.maximum(2e-5 * ref[k].double().abs() + 2e-6, 0.25 * floor)
+                if (err > tol).any():
+                    ok = False
+                    print(f"{tag}: {k} mismatch, worst {err.max().item():.3e}")
+            if not torch.equal(st["argmin"], ref["argmin"]):
                 ok = False
-                print(f"rank {rank}: screening did not engage as expected: {rep}")
-        xn = (x0.reshape(b, -1).double() ** 2).sum(1)[None, :] + d * temps.double()[:, None]
-        floor = 8 * 2.0 ** -24 * (xn + (data.double() ** 2).sum(1).max()) / temps.double()[:, None]
-        for k in ("log_l", "mean_e", "entropy"):
-            err = (st[k].double() - ref[k].double()).abs()
-            tol = torch.maximum(2e-5 * ref[k].double().abs() + 2e-6, 0.25 * floor)
-            if (err > tol).any():
+                print(f"{tag}: argmin mismatch")
+            if screen:
+                # certified rows recompute E_min in fp64 from the operands: within the fp32 round-off floor of the full pass
+                err = (st["e_min"].double() - ref["e_min"].double()).abs()
+                if (err > floor * temps.double()[:, None]).any():
+                    ok = False
+                    print(f"{tag}: e_min off by {err.max().item():.3e}")
+            elif not torch.equal(st["e_min"], ref["e_min"]):
                 ok = False
-                print(f"rank {rank} slice={slice_noise} sync={sync}: {k} mismatch, worst {err.max().item():.3e}")
-        if not torch.equal(st["argmin"], ref["argmin"]):
-            ok = False
-            print(f"rank {rank} slice={slice_noise} sync={sync}: argmin mismatch")
-        if screen:
-            # certified rows recompute E_min in fp64 from the operands: within the fp32 round-off floor of the full pass
-            err = (st["e_min"].double() - ref["e_min"].double()).abs()
-            if (err > floor * temps.double()[:, None]).any():
+                print(f"{tag}: e_min not bit-identical")
+            if not (sync and rank != 0) and off != off_ref:
                 ok = False
-                print(f"rank {rank} screened: e_min off by {err.max().item():.3e}")
-        elif not torch.equal(st["e_min"], ref["e_min"]):
+                print(f"{tag}: generator offset {off} != {off_ref}")
+            # per-point aux vector over the WHOLE dataset (the k-NN regulariser): every shard must use its own rows
+            if not screen:
+                aux = torch.rand(n, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) + 0.1
+                torch.manual_seed(seed)
+                a_ref = full.noised_stats(x0, temps, aux=aux)["aux_mean"]
+                torch.manual_seed(seed)
+                a_got = eng.noised_stats(x0, temps, aux=aux)["aux_mean"]
+                if (a_got - a_ref).abs().max().item() > 1e-4:
+                    ok = False
+                    print(f"{tag}: aux_mean mismatch {(a_got - a_ref).abs().max().item():.3e}")
+    # query-sharded sampler (dataset replicated, trajectories split) == the one-GPU sampler on the same seed
+    from pdm_b200 import IdealSampler
+    small = data[:4000].view(4000, 3, 32, 32)
+    log_temp = torch.linspace(-4.0, 6.0, 12)
+    for step_type in ("ddim", "ddpm"):
+        torch.manual_seed(55)
+        one = IdealSampler(small, log_temp, step_type=step_type).batch_sample(50)["x"]
+        torch.manual_seed(55)
+        many = IdealSampler(small, log_temp, step_type=step_type, query_group=dist.group.WORLD).batch_sample(50)["x"]
+        if not torch.allclose(one, many, rtol=1e-5, atol=1e-5):
             ok = False
-            print(f"rank {rank} slice={slice_noise} sync={sync}: e_min not bit-identical")
-        if not (sync and rank != 0) and off != off_ref:
-            ok = False
-            print(f"rank {rank} slice={slice_noise} sync={sync}: generator offset {off} != {off_ref}")
+            print(f"rank {rank}: query-sharded {step_type} sampler differs by {(one - many).abs().max().item():.3e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
