@@ -199,7 +199,17 @@ typedef struct pdm_stats_args {
        pass without reading the count back (no host synchronisation inside a sampling step).  n_row_tiles is then the
        upper bound the schedule is planned for; a count of 0 makes the launch a no-op.                               */
     const int32_t* n_row_tiles_dev;
+    /* ABI v4: top-k epilogue (tensor path, no partials / aux): instead of the statistics, every (row, record) keeps the
+       PDM_TOPK_SLOTS smallest SQUARED DISTANCES ||x - y_j||^2 (op order of utils/distance.py:21) of its share of the dataset
+       in registers and writes them once: topk_val (records_per_row, M, PDM_TOPK_SLOTS) ascending, +inf = empty slot,
+       topk_idx the LOCAL dataset row of each (-1 = empty).  pdm_topk_merge combines the records.  Replaces the dense
+       N x chunk distance tile + pdm_topk_smallest_f32 of the k-NN searches (utils/stats.py:50-60, 137-146;
+       scripts/analyze_cifar_nn.py:37-47): nothing of size M x N reaches HBM.                                         */
+    float*   topk_val;
+    int32_t* topk_idx;
 } pdm_stats_args;
+
+#define PDM_TOPK_SLOTS 8
 
 /* Fills args->n_splits / m_group / cta_group when they are 0, sets args->records_per_row and reports the
  * size of `partials` in floats. */
@@ -358,6 +368,21 @@ int pdm_sampler_step_f32(const float* x0_hat, const float* xt, const float* nois
  * ------------------------------------------------------------------------------------------- */
 int pdm_topk_smallest_f32(const float* x, int64_t ldx, int64_t rows, int64_t n, int32_t k,
                           float* vals, int64_t* idx, pdm_stream_t stream);
+
+/* Merge of the top-k epilogue's records (see pdm_stats_args.topk_val): for every row the k <= PDM_TOPK_SLOTS smallest
+ * (value, global index = local + index_offset) pairs over all records, ascending, ties by lower index; out_val (M, k),
+ * out_idx (M, k) int64 (+inf / -1 when the dataset holds fewer than k rows). */
+int pdm_topk_merge(const float* topk_val, const int32_t* topk_idx, int64_t M, int64_t records, int64_t index_offset,
+                   int32_t k, float* out_val, int64_t* out_idx, pdm_stream_t stream);
+
+/* Exact re-evaluation of nearest-neighbour candidates: vals[r, q] = sum_k (x[r,k] - y[idx[r,q] - index_offset, k])^2 with
+ * fp64 accumulation for every candidate that lies in this shard, then each row's k <= 8 candidates are re-sorted (value,
+ * then index; empty slots idx < 0 last).  The selection itself runs on the norm expansion of utils/distance.py:21, whose fp32
+ * round-off is 2^-24 (||x||^2 + ||y||^2); sklearn's kneighbors, which utils/stats.py:50-60, 138-146 calls, works in
+ * float64 -- this step brings the k-NN regulariser sigma_reg^2 = d_k^2 * scale / D to that accuracy. */
+int pdm_refine_neighbours_f32(const float* x, int64_t ldx, int64_t M, int64_t d, const float* y, int64_t ldy,
+                              int64_t n_local, int64_t index_offset, int32_t k, float* vals, int64_t* idx,
+                              pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward pass of K8 (autograd through Scheduler.true_posterior_mean_x0, which

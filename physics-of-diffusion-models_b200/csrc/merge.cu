@@ -116,3 +116,60 @@ extern "C" int pdm_reduce_partials(const float* parts, int64_t M, int64_t n_oute
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// merge of the top-k epilogue's records: one warp per query row, k selection rounds over the records' candidates
+// (records x 8 (value, local index) pairs, L2-resident): round r takes the lexicographic minimum of (value, index)
+// strictly above the pair selected in round r-1 -- ascending values, ties by lower dataset index.
+// ------------------------------------------------------------------------------------------------
+namespace pdm {
+
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ val, const int32_t* __restrict__ idx, int64_t M,
+                                                         int64_t records, int64_t index_offset, int k,
+                                                         float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int64_t cands = records * PDM_TOPK_SLOTS;
+    float last_v = -INFINITY;
+    int last_i = -1;
+    for (int r = 0; r < k; ++r) {
+        float bv = INFINITY;
+        int bi = 0x7fffffff;
+        for (int64_t c = lane; c < cands; c += 32) {
+            const int64_t rec = c / PDM_TOPK_SLOTS, slot = c - rec * PDM_TOPK_SLOTS;
+            const int64_t at = (rec * M + row) * PDM_TOPK_SLOTS + slot;
+            const int i = __ldg(idx + at);
+            if (i < 0) continue;
+            const float v = __ldg(val + at);
+            const bool above = v > last_v || (v == last_v && i > last_i);
+            if (above && (v < bv || (v == bv && i < bi))) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        const bool found = bi != 0x7fffffff;
+        if (lane == 0) {
+            out_val[row * k + r] = found ? bv : INFINITY;
+            out_idx[row * k + r] = found ? (int64_t)bi + index_offset : -1;
+        }
+        if (!found) { bv = INFINITY; bi = 0x7fffffff; }
+        last_v = bv; last_i = bi;
+    }
+}
+
+}  // namespace pdm
+
+extern "C" int pdm_topk_merge(const float* topk_val, const int32_t* topk_idx, int64_t M, int64_t records, int64_t index_offset,
+                              int32_t k, float* out_val, int64_t* out_idx, pdm_stream_t stream) {
+    PDM_REQUIRE(topk_val && topk_idx && out_val && out_idx && M >= 0 && records >= 1 && k >= 1 && k <= PDM_TOPK_SLOTS,
+                "pdm_topk_merge: bad arguments (1 <= k <= %d)", PDM_TOPK_SLOTS);
+    if (M == 0) return PDM_OK;
+    pdm::topk_merge_kernel<<<(unsigned)pdm::ceil_div(M, 8), 256, 0, pdm::as_stream(stream)>>>(topk_val, topk_idx, M, records,
+                                                                                             index_offset, (int)k, out_val, out_idx);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}

@@ -475,6 +475,55 @@ __global__ void __launch_bounds__(256) topk_smallest_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Refinement of nearest-neighbour candidates: the selection works on ||x||^2 - 2 x.y + ||y||^2 (utils/distance.py:21),
+// whose fp32 round-off is 2^-24 (||x||^2 + ||y||^2) -- for tight clusters that is 1e-3 of the neighbour distance itself,
+// while sklearn's kneighbors (utils/stats.py:50-60, 138-146) works in float64.  So the k candidates of a row are
+// re-evaluated directly, sum_k (x_k - y_k)^2 with fp64 accumulation, and re-sorted (value, then index).  One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refine_neighbours_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int64_t d,
+                                                                const float* __restrict__ y, int64_t ldy, int64_t n_local,
+                                                                int64_t index_offset, int k, float* __restrict__ vals,
+                                                                int64_t* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* xr = x + row * ldx;
+    float v[8];
+    long long id[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = INFINITY; id[q] = -1; }
+    for (int q = 0; q < k; ++q) {
+        const long long g = idx[row * k + q];
+        const long long j = g - index_offset;
+        float val = vals[row * k + q];
+        if (g >= 0 && j >= 0 && j < n_local) {
+            const float* yr = y + j * ldy;
+            double acc = 0.0;
+            for (int64_t c = lane; c < d; c += 32) {
+                const float df = xr[c] - __ldg(yr + c);
+                acc += (double)df * (double)df;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            val = (float)acc;
+        }
+        // insertion into the sorted prefix (every lane holds the same copy)
+        int pos = q;
+        v[q] = val; id[q] = g;
+#pragma unroll
+        for (int t = 7; t > 0; --t) {
+            if (t <= pos && g >= 0 && (v[t] < v[t - 1] || (v[t] == v[t - 1] && id[t] < id[t - 1]) || id[t - 1] < 0)) {
+                const float tv = v[t]; v[t] = v[t - 1]; v[t - 1] = tv;
+                const long long ti = id[t]; id[t] = id[t - 1]; id[t - 1] = ti;
+            }
+        }
+    }
+    if (lane == 0) {
+        for (int q = 0; q < k; ++q) { vals[row * k + q] = v[q]; idx[row * k + q] = id[q]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // one reverse-diffusion update: out = c_x0 * x0_hat + c_xt * xt (+ c_noise * noise), the DDPM / DDIM step of
 // diffusion/ddpm_sampling.py:94-110 with the x0 / eps algebra of diffusion/ddpm/ddpm.py:17-20 folded into three
 // host-computed coefficients.  HBM-bound: 12-16 B per element.
@@ -652,6 +701,18 @@ extern "C" int pdm_topk_smallest_f32(const float* x, int64_t ldx, int64_t rows, 
     if (rows == 0) return PDM_OK;
     PDM_REQUIRE(rows < (1ll << 31), "pdm_topk_smallest_f32: too many rows for one launch");
     topk_smallest_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, ldx, n, (int)k, vals, idx);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_refine_neighbours_f32(const float* x, int64_t ldx, int64_t M, int64_t d, const float* y, int64_t ldy,
+                                         int64_t n_local, int64_t index_offset, int32_t k, float* vals, int64_t* idx,
+                                         pdm_stream_t stream) {
+    PDM_REQUIRE(x && y && vals && idx && M >= 0 && d > 0 && ldx >= d && ldy >= d && n_local > 0 && k >= 1 && k <= 8,
+                "pdm_refine_neighbours_f32: bad arguments (1 <= k <= 8)");
+    if (M == 0) return PDM_OK;
+    refine_neighbours_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, as_stream(stream)>>>(x, ldx, M, d, y, ldy, n_local, index_offset,
+                                                                                     (int)k, vals, idx);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

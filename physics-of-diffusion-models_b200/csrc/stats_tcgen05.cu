@@ -8,6 +8,9 @@
 //              per query row (online_stats.cuh); the M x N distance matrix never reaches HBM.
 //              Replaces utils/distance.py:13-21 + utils/stats.py:71-101, 271-289 + scheduler.py:64-68.
 //   EPI_STORE  out = scale * S, the posterior-mean contraction p @ data (scheduler.py:69).
+//   EPI_TOPK   the kTopK smallest squared distances per query row and their dataset indices, kept in registers and
+//              written once per (row, split, column half): k-NN searches (utils/stats.py:50-60, 137-146; the
+//              min / scatter / min flow of scripts/analyze_cifar_nn.py:37-47) without a dense distance tile in HBM.
 //
 // Per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only with cta_group::2), warp 2 = TMEM
 // allocator, warps 4-11 = epilogue (two warps per TMEM lane quarter; thread <-> TMEM lane <-> query row).
@@ -57,7 +60,8 @@ constexpr int kRegsEpilogue = 232;
 #define PDM_DRAIN_COLS 32                         // columns per tcgen05.ld of the accumulator drain (32 or 64)
 #endif
 
-enum { EPI_STATS = 0, EPI_STORE = 1 };
+enum { EPI_STATS = 0, EPI_STORE = 1, EPI_TOPK = 2 };
+constexpr int kTopK = 8;                         // slots of the top-k epilogue (k <= 8: the reference's k-NN uses k + 1 = 6)
 
 // Soft rendezvous of the TMA producers at the start of every round.  CTA groups that share a column split stream the
 // same dataset tiles; they start a round together and drift apart by a tile or two over its ~50 column tiles, which
@@ -112,6 +116,8 @@ struct GemmParams {
     float* partials; float* energy_out; int64_t lde; float energy_mult;
     // EPI_STORE
     float* out; int64_t ldo; float out_scale; int32_t accumulate;
+    // EPI_TOPK: (records, M, kTopK) squared distances ascending (+inf = empty slot) and LOCAL dataset row indices
+    float* topk_val; int32_t* topk_idx;
 };
 
 template <int CG, int TERMS>
@@ -316,7 +322,8 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             uint32_t chunk_iter = 0;
             unsigned long long st_tfull = 0, st_stats = 0; (void)st_tfull; (void)st_stats;
             // 128-bit stores of the dense outputs need 16-byte aligned rows
-            const bool out_vec = (EPI == EPI_STATS)
+            constexpr bool kDist = EPI == EPI_STATS || EPI == EPI_TOPK;     // the epilogue works on squared distances
+            const bool out_vec = kDist
                 ? (p.energy_out && (p.lde % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.energy_out) & 15) == 0))
                 : ((p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0));
             // |y_k| <= 4096 * y_inv_scale by construction of the split, so |y|^2 <= d_pad * (4096 y_inv_scale)^2
@@ -329,17 +336,23 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 float xn = 0.f, neg2inv = 0.f, c2 = -0.5f * kLog2e;
                 bool safe = true;          // (u - 2m) * c2 cannot overflow for this row: no per-element clamp
                 PackedState st;
-                if (EPI == EPI_STATS) {
+                float tk_v[kTopK];
+                int tk_i[kTopK];
+                if (EPI == EPI_TOPK) {
+#pragma unroll
+                    for (int q = 0; q < kTopK; ++q) { tk_v[q] = INFINITY; tk_i[q] = -1; }
+                }
+                if (kDist) {
                     if (row_ok) {
                         xn = p.q_norm[grow];
                         neg2inv = -2.f * p.q_inv_scale[grow] * p.y_inv_scale;
-                        if (p.inv_temp) {
+                        if (EPI == EPI_STATS && p.inv_temp) {
                             const float inv_t = p.inv_temp[grow];
                             c2 = -0.5f * kLog2e * inv_t;
                             safe = inv_t * (xn + yn_bound) < 1.0e29f;
                         }
                     }
-                    packed_init(st);
+                    if (EPI == EPI_STATS) packed_init(st);
                 }
                 for (int nt = sp; nt < p.n_tiles; nt += p.n_splits) {
                     float2 sums[CPT / 2];
@@ -388,7 +401,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     // |y|^2 of the chunk after the current one is loaded while the current one is processed
                     // (one chunk ahead only: the barrier below keeps ptxas from hoisting all of them)
                     float4 yn_next[CH / 4];
-                    if (EPI == EPI_STATS && nbase + CH <= p.ncols) {
+                    if (kDist && nbase + CH <= p.ncols) {
 #pragma unroll
                         for (int i = 0; i < CH / 4; ++i) yn_next[i] = __ldg(reinterpret_cast<const float4*>(p.y_norm + nbase) + i);
                     }
@@ -396,7 +409,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     for (int c0 = 0; c0 < CPT; c0 += CH) {
                         const int64_t col0 = nbase + c0;
                         float4 yn_cur[CH / 4];
-                        if (EPI == EPI_STATS) {
+                        if (kDist) {
 #pragma unroll
                             for (int i = 0; i < CH / 4; ++i) yn_cur[i] = yn_next[i];
                             asm volatile("" ::: "memory");
@@ -408,7 +421,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         }
                         if (col0 < p.ncols) {
                             const bool full_chunk = col0 + CH <= p.ncols;
-                            if (EPI == EPI_STATS) {
+                            if (kDist) {
                                 float2 u[NP], ax[NP];
                                 if (full_chunk) {
                                     const float2 n2 = splat2(neg2inv), xv = splat2(xn);
@@ -455,9 +468,34 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                                         }
                                     }
                                 }
-                                if (p.partials) {
+                                if (EPI == EPI_STATS && p.partials) {
                                     if (full_chunk && safe) packed_add_chunk<NP, AUX, false>(st, u, ax, p.index_offset + col0, c2);
                                     else packed_add_chunk<NP, AUX, true>(st, u, ax, p.index_offset + col0, c2);
+                                }
+                                if (EPI == EPI_TOPK) {
+                                    // Sorted insertion, rare after the first few tiles (k log(N/k) insertions per row in
+                                    // expectation): one chunk-minimum test guards the 32 compares.  Columns arrive in
+                                    // ascending order within a thread, so the strict '<' keeps the lower index on ties.
+                                    float cmin = fminf(u[0].x, u[0].y);
+#pragma unroll
+                                    for (int i = 1; i < NP; ++i) cmin = fminf(fminf(cmin, u[i].x), u[i].y);
+                                    if (cmin < tk_v[kTopK - 1]) {
+#pragma unroll
+                                        for (int i = 0; i < 2 * NP; ++i) {
+                                            const float v = (i & 1) ? u[i / 2].y : u[i / 2].x;
+                                            if (v < tk_v[kTopK - 1] && v < kBigE) {
+                                                tk_v[kTopK - 1] = v;
+                                                tk_i[kTopK - 1] = (int)(col0 + i);
+#pragma unroll
+                                                for (int q = kTopK - 1; q > 0; --q) {
+                                                    if (tk_v[q] < tk_v[q - 1]) {
+                                                        const float tv = tk_v[q]; tk_v[q] = tk_v[q - 1]; tk_v[q - 1] = tv;
+                                                        const int ti = tk_i[q]; tk_i[q] = tk_i[q - 1]; tk_i[q - 1] = ti;
+                                                    }
+                                                }
+                                            }
+                                        }
+                                    }
                                 }
                             } else if (row_ok) {
                                 float* o = p.out + grow * p.ldo + col0;
@@ -488,6 +526,15 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 // one partial record per (row, split, column half)
                 if (EPI == EPI_STATS && p.partials && row_ok)
                     packed_store(st, p.partials + ((int64_t)(2 * sp + half) * p.M + grow) * PDM_PART_STRIDE);   // record-major
+                if (EPI == EPI_TOPK && row_ok) {
+                    const int64_t rec = ((int64_t)(2 * sp + half) * p.M + grow) * kTopK;
+                    float4* tv4 = reinterpret_cast<float4*>(p.topk_val + rec);
+                    int4* ti4 = reinterpret_cast<int4*>(p.topk_idx + rec);
+                    tv4[0] = make_float4(tk_v[0], tk_v[1], tk_v[2], tk_v[3]);
+                    tv4[1] = make_float4(tk_v[4], tk_v[5], tk_v[6], tk_v[7]);
+                    ti4[0] = make_int4(tk_i[0], tk_i[1], tk_i[2], tk_i[3]);
+                    ti4[1] = make_int4(tk_i[4], tk_i[5], tk_i[6], tk_i[7]);
+                }
             }
 #ifdef PDM_STALL_STATS
             if (warp == kEpiWarp0 && lane == 0) { g_stall[blockIdx.x][3] = st_tfull; g_stall[blockIdx.x][5] = st_stats; }
@@ -739,6 +786,17 @@ int launch_tensor_stats(const pdm_stats_args& a, cudaStream_t stream) {
     p.q_norm = a.q_norm; p.q_inv_scale = a.q_inv_scale; p.inv_temp = a.inv_temp;
     p.y_norm = a.y_norm; p.y_aux = a.y_aux; p.y_inv_scale = a.y_inv_scale; p.index_offset = a.index_offset;
     p.partials = a.partials; p.energy_out = a.energy_out; p.lde = a.lde; p.energy_mult = a.energy_mult;
+    if (a.topk_val) {
+        PDM_REQUIRE(a.topk_idx && !f8 && terms >= 2 && !a.y_aux && !a.partials,
+                    "the top-k epilogue runs in f16x3 / f16x2, without partial records and without aux");
+        PDM_REQUIRE((reinterpret_cast<uintptr_t>(a.topk_val) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.topk_idx) & 15) == 0,
+                    "topk_val / topk_idx must be 16-byte aligned");
+        p.topk_val = a.topk_val; p.topk_idx = a.topk_idx;
+        if (cg == 2) return terms == 3 ? launch_variant<2, 3, EPI_TOPK, false>(maps, p, info.sm_count, stream)
+                                       : launch_variant<2, 2, EPI_TOPK, false>(maps, p, info.sm_count, stream);
+        return terms == 3 ? launch_variant<1, 3, EPI_TOPK, false>(maps, p, info.sm_count, stream)
+                          : launch_variant<1, 2, EPI_TOPK, false>(maps, p, info.sm_count, stream);
+    }
     if (f8) return cg == 2 ? launch_variant<2, 1, EPI_STATS, false, true>(maps, p, info.sm_count, stream)
                            : launch_variant<1, 1, EPI_STATS, false, true>(maps, p, info.sm_count, stream);
     if (a.y_aux) return dispatch<EPI_STATS, true>(cg, terms, maps, p, info.sm_count, stream);
@@ -790,7 +848,9 @@ extern "C" int pdm_posterior_stats(const pdm_stats_args* a, pdm_stream_t stream)
     PDM_REQUIRE(a, "pdm_posterior_stats: null args");
     PDM_REQUIRE(a->M >= 0 && a->N > 0 && a->d > 0, "pdm_posterior_stats: bad sizes");
     PDM_REQUIRE(a->q_norm && a->y_norm, "pdm_posterior_stats: q_norm / y_norm missing");
-    PDM_REQUIRE(a->partials || a->energy_out, "pdm_posterior_stats: no output requested");
+    PDM_REQUIRE(a->partials || a->energy_out || a->topk_val, "pdm_posterior_stats: no output requested");
+    PDM_REQUIRE(!a->topk_val || (a->precision == PDM_PREC_F16X3 || a->precision == PDM_PREC_F16X2),
+                "pdm_posterior_stats: the top-k epilogue needs the tensor path (f16x3 / f16x2)");
     PDM_REQUIRE(!a->partials || a->inv_temp, "pdm_posterior_stats: inv_temp missing");
     PDM_REQUIRE(!a->energy_out || a->lde >= a->N, "pdm_posterior_stats: lde < N");
     PDM_REQUIRE(a->n_splits >= 1, "pdm_posterior_stats: n_splits must be planned (>= 1)");

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PDM_B200_LIB") or os.path.join(PKG_ROOT, "lib", "libp
 PDM_OK = 0
 PREC_EXACT_F32, PREC_F16X3, PREC_F16X1, PREC_F16X2, PREC_F8X1 = 0, 1, 2, 3, 4
 PART_STRIDE = 8
+TOPK_SLOTS = 8
 OUT_E_MIN, OUT_LOG_L, OUT_MEAN_E, OUT_MEAN_E2, OUT_VAR_E, OUT_AUX_MEAN, OUT_ENTROPY, OUT_L = range(8)
 OUT_ROWS = 8
 
@@ -36,6 +37,7 @@ class StatsArgs(C.Structure):
         ("q_norm", C.c_void_p), ("y_norm", C.c_void_p), ("inv_temp", C.c_void_p), ("y_aux", C.c_void_p),
         ("partials", C.c_void_p), ("energy_out", C.c_void_p), ("lde", C.c_int64), ("energy_mult", C.c_float),
         ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int64), ("n_row_tiles_dev", C.c_void_p),
+        ("topk_val", C.c_void_p), ("topk_idx", C.c_void_p),
     ]
 
 
@@ -72,6 +74,8 @@ SIGNATURES = {
     "pdm_split_gemm_f16x3_tiles": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
     "pdm_delta_tile_list": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P]),
     "pdm_screen_merge_stage": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P]),
+    "pdm_topk_merge": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P]),
+    "pdm_refine_neighbours_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "pdm_gather_rows_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     "pdm_split_gemm_f16x3": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P]),
     "pdm_sampler_step_f32": (C.c_int, [_P, _P, _P, _F, _F, _F, _P, _I64, _P]),

@@ -213,7 +213,7 @@ class CudaBackend:
                         index_offset: int = 0, n_splits: int = 0, m_group: int = 0, cta_group: int = 0,
                         want_partials: bool = True, energy_out: Optional[Tensor] = None,
                         energy_mult: float = 1.0, row_tiles: Optional[Tensor] = None,
-                        n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None) -> Optional[Tensor]:
+                        n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None, topk: bool = False):
         """``row_tiles`` (int32, device) / ``n_row_tiles``: screened launch over the listed row tiles of
         128*cta_group rows only; records of the other rows are left as allocated (uninitialised).
         ``n_row_tiles_dev`` (one int32 on the device): the list's actual length, read by the kernel -- ``n_row_tiles`` is
@@ -244,6 +244,12 @@ class CudaBackend:
         check(self.lib.pdm_posterior_stats_plan(C.byref(a), self.device.index or 0, C.byref(nfloats)),
               "pdm_posterior_stats_plan")
         partials = None
+        if topk:
+            # top-k epilogue: per (record, row) the 8 smallest squared distances and their local dataset rows
+            tk_val = torch.empty(a.records_per_row, M, _cabi.TOPK_SLOTS, dtype=torch.float32, device=self.device)
+            tk_idx = torch.empty(a.records_per_row, M, _cabi.TOPK_SLOTS, dtype=torch.int32, device=self.device)
+            a.topk_val, a.topk_idx = tk_val.data_ptr(), tk_idx.data_ptr()
+            want_partials = False
         if want_partials:
             partials = torch.empty(a.records_per_row, M, _cabi.PART_STRIDE, dtype=torch.float32, device=self.device)
             a.partials = partials.data_ptr()
@@ -260,7 +266,19 @@ class CudaBackend:
         self.launches += 1
         self.last_plan = (a.n_splits, a.m_group, a.cta_group)
         del keep
+        if topk:
+            return tk_val, tk_idx
         return partials
+
+    def topk_merge(self, tk_val: Tensor, tk_idx: Tensor, index_offset: int, k: int):
+        """records of the top-k epilogue -> (values (M, k) ascending, global indices (M, k) int64)."""
+        records, m, _ = tk_val.shape
+        vals = torch.empty(m, k, dtype=torch.float32, device=self.device)
+        idx = torch.empty(m, k, dtype=torch.int64, device=self.device)
+        check(self.lib.pdm_topk_merge(tk_val.data_ptr(), tk_idx.data_ptr(), m, records, int(index_offset), int(k),
+                                      vals.data_ptr(), idx.data_ptr(), self._stream()), "pdm_topk_merge")
+        self.launches += 1
+        return vals, idx
 
     def merge(self, parts: Tensor, inv_temp: Tensor, n_total: int):
         """parts: (S, M, 8) record-major, as posterior_stats emits them, or (G, M, S, 8): G all-gathered shards of
@@ -455,6 +473,14 @@ class CudaBackend:
                                              self._stream()), "pdm_topk_smallest_f32")
         self.launches += 1
         return vals, idx
+
+    def refine_neighbours(self, x: Tensor, y: Tensor, index_offset: int, vals: Tensor, idx: Tensor) -> None:
+        """In place: exact squared distances (direct differences, fp64 accumulation) of the candidates, rows re-sorted."""
+        x, y = self._f32(x), self._f32(y)
+        check(self.lib.pdm_refine_neighbours_f32(x.data_ptr(), _ld(x), x.shape[0], x.shape[1], y.data_ptr(), _ld(y), y.shape[0],
+                                                 int(index_offset), vals.shape[1], vals.data_ptr(), idx.data_ptr(),
+                                                 self._stream()), "pdm_refine_neighbours_f32")
+        self.launches += 1
 
     def sampler_step(self, x0_hat: Tensor, xt: Tensor, noise: Optional[Tensor], c_x0: float, c_xt: float, c_noise: float,
                      out: Optional[Tensor] = None) -> Tensor:

@@ -811,7 +811,7 @@ class PosteriorEngine:
 
     # -- posterior mean ---------------------------------------------------------------------------
     def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None,
-                       values: Optional[Tensor] = None, temp_bounds: Optional[tuple] = None) -> Tensor:
+                       values: Optional[Tensor] = None, temp_bounds: Optional[tuple] = None, scatter: bool = False) -> Tensor:
         """x0_hat[r] = sum_j p_rj y_j with p ~ exp(-||x_r*post_r - y_j||^2 / (2 T_r)).  Returns (M, d).
         ``values`` (N, dv) replaces y_j in the weighted sum (posterior mean of arbitrary per-point vectors).
 
@@ -819,7 +819,11 @@ class PosteriorEngine:
         unproven and which tiles have to be contracted are tile lists whose lengths stay in device memory
         (pdm_stats_args.n_row_tiles_dev and the *_tiles entry points), so a sampling loop enqueues step after step.
         ``temp_bounds`` = (lowest, highest) temperature of the call as host floats (the sampler knows them); without it
-        an engine with screening on reads the two numbers back once per call."""
+        an engine with screening on reads the two numbers back once per call.
+        ``scatter`` (row-sharded dataset): the shards' partial sums are combined with a reduce-scatter instead of an
+        all-reduce and the call returns only this rank's slice of the rows, ceil(M / world) of them starting at
+        rank * ceil(M / world) (zero rows beyond M) -- a sampler whose ranks each own a slice of the trajectories moves
+        M d / world floats per rank instead of M d."""
         dev = self.backend.device
         be = self.backend
         ds = self.ds
@@ -839,7 +843,11 @@ class PosteriorEngine:
                 vscale = pow2_scale_for(float(be.absmax(values).item()))
                 vt = be.transpose_split(values, vscale) + (vscale,)
         src = ds.y if values is None else values
-        out = torch.empty(m, src.shape[1], dtype=torch.float32, device=dev)
+        per = (m + self.world - 1) // self.world
+        m_alloc = per * self.world if (scatter and self.world > 1) else m
+        out = torch.empty(m_alloc, src.shape[1], dtype=torch.float32, device=dev)
+        if m_alloc > m:
+            out[m:].zero_()
         step = max(128, min(m, self.cfg.max_energy_bytes // (ds.n * 8)))
         rpt = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)          # the fused kernel's row tile
         tile_ops = tensor and hasattr(be, "delta_tile_list")                             # device-side tile lists available
@@ -912,6 +920,10 @@ class PosteriorEngine:
                     be.gather_rows(src, amin, ds.index_offset, dflags, out_blk)
         if self.world > 1:
             import torch.distributed as dist
+            if scatter:
+                mine = torch.empty(per, out.shape[1], dtype=torch.float32, device=dev)
+                dist.reduce_scatter_tensor(mine, out, group=self.group)
+                return mine
             dist.all_reduce(out, group=self.group)
         return out
 
@@ -976,6 +988,57 @@ class PosteriorEngine:
         a = sums[:, 0].contiguous()
         dist.all_reduce(a, group=self.group)
         return self.backend.denoiser_backward_weights(energy, sdot, e_min, l, inv_temp, s_scale, a_in=a)
+
+    # -- nearest neighbours -----------------------------------------------------------------------------
+    TOPK_MAX = _cabi.TOPK_SLOTS
+
+    def nearest(self, x: Tensor, k: int, refine: bool = True):
+        """The k smallest squared distances ||x_b - y_j||^2 of every query to this dataset shard and the global indices of
+        those points: (values (M, k) ascending, indices (M, k) int64, ties by lower index; +inf / -1 beyond the shard's
+        size).  Tensor path, k <= 8: the top-k epilogue of the fused kernel -- nothing of size M x N reaches HBM.  Otherwise
+        (d < 64, k > 8): dense distance tiles + the selection kernel.  ``refine``: the selection runs on the norm expansion
+        of utils/distance.py:21 (fp32 round-off 2^-24 (|x|^2 + |y|^2)); the candidates -- all 8 slots, so that near-ties
+        misordered by that round-off are still among them -- are then re-evaluated directly in fp64 and re-sorted, which is
+        the accuracy of the float64 search sklearn runs for utils/stats.py:50-60, 138-146."""
+        dev = self.backend.device
+        be = self.backend
+        ds = self.ds
+        xf = _flat2d(x).to(device=dev, dtype=torch.float32).contiguous()
+        m = xf.shape[0]
+        precision = self.precision()
+        can_refine = refine and hasattr(be, "refine_neighbours")
+        if precision != "exact" and k <= self.TOPK_MAX and hasattr(be, "topk_merge"):
+            ks = self.TOPK_MAX if can_refine else k                     # candidates kept for the refinement
+            vals = torch.empty(m, ks, dtype=torch.float32, device=dev)
+            idx = torch.empty(m, ks, dtype=torch.int64, device=dev)
+            step = self.rows_per_block()
+            y_hi, y_lo = ds.split()
+            for r0 in range(0, m, step):
+                r1 = min(m, r0 + step)
+                prep = self._prepare(xf[r0:r1], r1 - r0, None, None, None, precision, False)
+                tv, ti = be.posterior_stats(precision=precision, M=r1 - r0, N=ds.n, d=ds.d, q_norm=prep["norms"], y_norm=ds.y_norm,
+                                            inv_temp=None, q_split=(prep["hi"], prep["lo"], prep["inv_scale"]),
+                                            y_split=(y_hi, None if precision == "f16x2" else y_lo), y_inv_scale=1.0 / ds.scale,
+                                            index_offset=ds.index_offset, n_splits=self.cfg.n_splits, m_group=self.cfg.m_group,
+                                            cta_group=self.cfg.cta_group, topk=True)
+                v, i = be.topk_merge(tv, ti, ds.index_offset, ks)
+                vals[r0:r1], idx[r0:r1] = v, i
+        else:
+            ks = min(max(k, self.TOPK_MAX) if (can_refine and k <= self.TOPK_MAX) else k, ds.n)
+            vals = torch.full((m, max(k, ks)), float("inf"), dtype=torch.float32, device=dev)
+            idx = torch.full((m, max(k, ks)), -1, dtype=torch.int64, device=dev)
+            step = max(1, (1 << 30) // (4 * max(1, ds.n)))
+            for r0 in range(0, m, step):
+                d2 = self.pairwise_sqdist(xf[r0:r0 + step])
+                if hasattr(be, "topk_smallest"):
+                    v, i = be.topk_smallest(d2, ks)
+                else:                                                     # CPU test double
+                    v, i = torch.topk(d2, ks, dim=1, largest=False)
+                vals[r0:r0 + step, :ks] = v
+                idx[r0:r0 + step, :ks] = i + ds.index_offset
+        if can_refine and vals.shape[1] <= self.TOPK_MAX and m > 0:
+            be.refine_neighbours(xf, ds.y, ds.index_offset, vals, idx)
+        return vals[:, :k].contiguous(), idx[:, :k].contiguous()
 
     # -- dense distances (callers of compute_pw_dist_sqr index / min / scatter the matrix) -----------
     def pairwise_sqdist(self, x: Tensor) -> Tensor:

@@ -56,10 +56,16 @@ class IdealSampler:
             raise ValueError(f"unknown step type: {step_type}")
         self.engine = engine if engine is not None else PosteriorEngine(
             EmpiricalDataset(train_data, backend=default_backend()), config)
-        if self.engine.world > 1:
-            raise ValueError("IdealSampler shards the trajectories, not the dataset: pass an engine over the whole dataset")
         self.backend = self.engine.backend
         self.step_type = step_type
+        # An engine over a row-sharded dataset (too large to replicate): the trajectories are split over the SAME group;
+        # every step all-gathers the current states (each shard has to see every query) and gets its own slice of the
+        # posterior means back from a reduce-scatter (mode 1).
+        self.dataset_sharded = self.engine.world > 1
+        if self.dataset_sharded:
+            if query_group is not None:
+                raise ValueError("an engine over a row-sharded dataset splits the trajectories over its own group")
+            query_group = self.engine.group
         self.query_group = query_group
         self.q_world, self.q_rank = 1, 0
         if query_group is not None:
@@ -96,7 +102,13 @@ class IdealSampler:
             abp = self.alpha_bar[idx - 1] if idx > 0 else 1.0         # clean_log_temp = -inf -> alpha_bar = 1
             last = idx == 0
             t = (1.0 - ab) / ab
-            x0_hat = self.engine.posterior_mean(flat, ones * t, post=ones * (1.0 / math.sqrt(ab)), temp_bounds=(t, t))
+            if self.dataset_sharded:
+                every = self._gather_rows(xt, batch_size, copy=False).view(batch_size, d)
+                x0_hat = self.engine.posterior_mean(every, torch.full((batch_size,), t, device=dev),
+                                                    post=torch.full((batch_size,), 1.0 / math.sqrt(ab), device=dev),
+                                                    temp_bounds=(t, t), scatter=True)[:rows]
+            else:
+                x0_hat = self.engine.posterior_mean(flat, ones * t, post=ones * (1.0 / math.sqrt(ab)), temp_bounds=(t, t))
             c_x0, c_xt, c_noise = step_coefficients(ab, abp, self.step_type)
             noise = None
             if self.step_type == "ddpm" and not last:                 # no draw on the last step (:107)

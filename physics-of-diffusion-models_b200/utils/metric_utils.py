@@ -8,8 +8,9 @@ expectation:
   * scalar case: the per-point lambda-score is -D/2 + E_k/T with E_k = |y - x_k|^2/2 and T = sigma^2, so
     its posterior mean is -D/2 + <e> + E_min/T, straight from the fused statistics pass;
   * diagonal case: whiten by 1/sqrt(Sigma_ii) (T = 1); the per-dimension score needs
-    sum_k w_k (y_i - x_ki)^2 = y_i^2 - 2 y_i <x_i> + <x_i^2>, i.e. the posterior mean of [x, x^2] -- one
-    pass of the posterior-mean contraction instead of the reference's (n_y, K, D) tensor (:131, :187).
+    sum_k w_k (y_i - x_ki)^2 = y_i^2 - 2 y_i <x_i> + <x_i^2>, i.e. the posterior mean of [x, x^2] (about the
+    samples' mean, x^2 as an fp32 pair) -- one pass of the posterior-mean contraction instead of the reference's
+    (n_y, K, D) tensor (:131, :187).
 """
 from __future__ import annotations
 
@@ -30,16 +31,26 @@ def _marginal_scalar_scores(y_samples: Tensor, x_samples: Tensor, sigma_sq: Tens
 
 
 def _diag_second_moments(y_samples: Tensor, x_samples: Tensor, sigma_diag: Tensor) -> Tensor:
-    """m2[b, i] = sum_k w[b, k] (y[b, i] - x[k, i])^2 with w the softmax of -1/2 sum_i (.)^2/Sigma_ii."""
+    """m2[b, i] = sum_k w[b, k] (y[b, i] - x[k, i])^2 with w the softmax of -1/2 sum_i (.)^2/Sigma_ii.
+
+    Expanded as y^2 - 2 y <x> + <x^2> the three terms cancel to the distance of y from its nearest samples -- at small
+    Sigma many orders below |x|^2 -- so the expansion is taken about the samples' mean, <x^2> is carried as an fp32 pair
+    (hi + lo = x^2 to 48 bits: a posterior that is a delta on one sample then reproduces (y - x)^2 exactly, the engine
+    gathers such rows) and the three terms are combined in float64."""
     s = torch.sqrt(sigma_diag)
     xw, yw = x_samples / s, y_samples / s                       # whitened coordinates, T = 1
     eng = PosteriorEngine(EmpiricalDataset(xw, backend=default_backend()))
     t = torch.ones(yw.shape[0])
-    values = torch.cat((x_samples, x_samples ** 2), dim=1)
-    mean = eng.posterior_mean(yw, t, values=values).to(x_samples.device)
+    mu = x_samples.mean(dim=0, keepdim=True)
+    xc, yc = (x_samples - mu).double(), (y_samples - mu).double()
+    sq = xc * xc
+    sq_hi = sq.float()
+    sq_lo = (sq - sq_hi.double()).float()
+    values = torch.cat((xc.float(), sq_hi, sq_lo), dim=1)
+    mean = eng.posterior_mean(yw, t, values=values).to(x_samples.device).double()
     d = x_samples.shape[1]
-    ex, ex2 = mean[:, :d], mean[:, d:]
-    return y_samples ** 2 - 2 * y_samples * ex + ex2
+    ex, ex2 = mean[:, :d], mean[:, d:2 * d] + mean[:, 2 * d:]
+    return (yc * yc - 2 * yc * ex + ex2).clamp_min(0).to(x_samples.dtype)
 
 
 def compute_metric_scalar(log_sigma_sq, x_samples, n_y_samples=10000):

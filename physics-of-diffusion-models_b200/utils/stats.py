@@ -142,8 +142,7 @@ def _knn_sigma_reg_sq(eng: PosteriorEngine, knn_k: int, sigma_reg_scale: float) 
     out = torch.empty(ds.n_total, dtype=torch.float32, device=dev)
     step = max(1, (1 << 30) // (4 * max(1, ds.n)))
     if eng.world == 1:
-        for r0 in range(0, ds.n, step):
-            out[r0:r0 + step] = _k_smallest(eng, eng.pairwise_sqdist(ds.y[r0:r0 + step]), kk)[:, -1].clamp_(min=0)
+        out = eng.nearest(ds.y, kk)[0][:, -1].clamp_(min=0)       # top-k epilogue of the fused pass: no N x N tile
         return out * sigma_reg_scale / float(ds.d)
     import torch.distributed as dist
     rank = dist.get_rank(eng.group)
@@ -154,9 +153,7 @@ def _knn_sigma_reg_sq(eng: PosteriorEngine, knn_k: int, sigma_reg_scale: float) 
             r1 = min(o_hi, r0 + step)
             q = ds.y[r0 - o_lo:r1 - o_lo].contiguous() if owner == rank else torch.empty(r1 - r0, ds.d, dtype=torch.float32, device=dev)
             dist.broadcast(q, src=dist.get_global_rank(eng.group, owner), group=eng.group)
-            cand = _k_smallest(eng, eng.pairwise_sqdist(q), k_local)
-            if k_local < kk:
-                cand = torch.cat([cand, torch.full((cand.shape[0], kk - k_local), float("inf"), device=dev)], dim=1)
+            cand = eng.nearest(q, kk)[0]                          # +inf beyond the shard's size
             allc = torch.empty(eng.world * cand.shape[0], kk, dtype=cand.dtype, device=dev)   # rank-major
             dist.all_gather_into_tensor(allc, cand.contiguous(), group=eng.group)
             allc = allc.view(eng.world, cand.shape[0], kk).permute(1, 0, 2).reshape(cand.shape[0], -1).contiguous()

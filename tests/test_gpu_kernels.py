@@ -488,6 +488,55 @@ def test_topk_smallest(backend):
     assert idx.cpu()[0].tolist() == [3, 0, 1] and vals.cpu()[0, 0] == 1.0      # +inf entries are still entries (index order)
 
 
+@pytest.mark.parametrize("kind,n,d,m,k", [("uniform", 5000, 3072, 300, 6), ("pixels", 3000, 1024, 200, 6), ("ragged", 777, 200, 131, 3),
+                                          ("tiny", 5, 64, 7, 8), ("offset", 1500, 512, 64, 8)])
+def test_topk_epilogue_of_the_fused_pass(backend, kind, n, d, m, k):
+    """PosteriorEngine.nearest on the tensor path: the k nearest dataset rows come out of the fused kernel's epilogue (registers
+    -> one record per (row, split, column half) -> pdm_topk_merge), no M x N distance tile.  Unrefined it must reproduce the
+    dense tile + pdm_topk_smallest_f32 bit for bit (same distances, same tie rule); refined (direct fp64 re-evaluation of the
+    8 candidates) it must match a brute-force fp64 search: indices wherever the gap is resolvable, values to 1e-6."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    g = syn.gen(300 + n)
+    if kind == "pixels":
+        data = (torch.randint(0, 256, (n, d), generator=g, dtype=torch.uint8).float() / 255 - 0.5) / 0.5
+    else:
+        data = torch.rand(n, d, generator=g) * 2 - 1
+    if n > 100:
+        data[n // 2] = data[17]                                      # an exact duplicate: ties resolve to the lower index
+    x = data[torch.randint(0, n, (m,), generator=g)] + 0.05 * torch.randn(m, d, generator=g)
+    x[0] = data[17 % n]                                              # a query ON the duplicated point
+    off = 4000 if kind == "offset" else 0
+    ds = EmpiricalDataset(data, backend=backend, index_offset=off, n_total=n + off)
+    eng = PosteriorEngine(ds, EngineConfig())
+    assert eng.precision() == ("f16x2" if kind == "pixels" else "f16x3")
+    launches = backend.launches
+    v_raw, i_raw = eng.nearest(x, k, refine=False)
+    assert backend.launches - launches <= 4                          # prepare, fused pass, merge: no dense tile, no selection pass
+    dense = eng.pairwise_sqdist(x)
+    kk = min(k, n)
+    v_sel, i_sel = backend.topk_smallest(dense, kk)
+    assert torch.equal(v_raw[:, :kk], v_sel) and torch.equal(i_raw[:, :kk], i_sel + off)
+    if kk < k:
+        assert bool((i_raw[:, kk:] == -1).all()) and bool(torch.isinf(v_raw[:, kk:]).all())
+    if n > 100:
+        assert i_raw[0, 0].item() == 17 + off and i_raw[0, 1].item() == n // 2 + off
+    v, i = eng.nearest(x, k)
+    d64 = torch.cdist(x.double(), data.double()).pow(2)
+    want_v, want_i = torch.sort(d64, dim=1, stable=True)
+    want_v, want_i = want_v[:, :kk], want_i[:, :kk]
+    torch.testing.assert_close(v.cpu()[:, :kk].double(), want_v, rtol=2e-6, atol=1e-9)
+    floor = 8 * 2.0 ** -24 * ((x.double() ** 2).sum(1, keepdim=True) + (data.double() ** 2).sum(1).max())
+    gaps_ok = torch.ones(m, kk, dtype=torch.bool)
+    srt = torch.sort(d64, dim=1).values[:, :min(n, 9)]
+    for q in range(kk):                                              # slot q is unambiguous when its neighbours in the sorted
+        lo_gap = srt[:, q] - srt[:, q - 1] if q > 0 else torch.full((m,), float("inf"), dtype=torch.float64)    # list are far
+        hi_gap = srt[:, q + 1] - srt[:, q] if q + 1 < srt.shape[1] else torch.full((m,), float("inf"), dtype=torch.float64)
+        gaps_ok[:, q] = (lo_gap > 1e-9) & (hi_gap > 1e-9)
+    # selection ran in fp32: candidates beyond slot 8 of the true order could only enter through a near-tie at the cut
+    sure = gaps_ok & (srt[:, min(n, 9) - 1:min(n, 9)] - srt[:, :kk] > 2 * floor if n >= 9 else torch.ones(m, kk, dtype=torch.bool))
+    assert torch.equal(i.cpu()[:, :kk][sure] - off, want_i[sure])
+
+
 @pytest.mark.parametrize("precision", ["exact", "f16x3"])
 def test_posterior_mean_delta_rows_shortcut(backend, precision):
     """Rows whose posterior is a delta to fp32 resolution are gathered instead of contracted: same result as the full

@@ -154,8 +154,10 @@ def _check_rows(st, ref, what, aux=False, xq=None, data=None):
     arbitrated_close(st["mean_e2"], r32["mean_e2"], r64["mean_e2"], atol=1e-5, what=what + " mean_e2", floor=fe2)
     arbitrated_close(st["var_e"], r32["var_e"], r64["var_e"], atol=2e-5, what=what + " var_e", floor=fe2)
     arbitrated_close(st["entropy"], r32["entropy"], r64["entropy"], atol=2e-5, what=what + " entropy", floor=2 * fe)
-    if aux:
-        arbitrated_close(st["aux_mean"], r32["aux_mean"], r64["aux_mean"], atol=1e-7, what=what + " aux_mean")
+    if aux:                             # <s> = sum_j p_j s_j: the weights move by the round-off of an exponent
+        _report_errors(f"{what} aux_mean", st["aux_mean"], r32["aux_mean"], r64["aux_mean"], atol=1e-7)
+        arbitrated_close(st["aux_mean"], r32["aux_mean"], r64["aux_mean"], atol=1e-7, what=what + " aux_mean",
+                         floor=fe * r64["aux_mean"].abs().max())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,7 +349,12 @@ def test_nn_indices_bit_exact_at_5000x3072(cuda_device, kind):
     d64 = orc.pairwise_sqdist(pts.double())
     yn = (pts.double().reshape(5000, -1) ** 2).sum(1)
     floor = 8 * 2.0 ** -24 * (yn[:, None] + yn[None, :])
-    arbitrated_close(d, d32, d64, atol=2e-5, floor=floor, what=f"{kind} dense squared distances")
+    # the script overwrites the diagonal (fill_diagonal_(1e10)); there x.x = |x|^2 is as large as a dot product gets and
+    # its 48 per-k-block partial sums each round at ulp(|x|^2): held to 2 floors, everything else to one
+    eye = torch.eye(5000, dtype=torch.bool)
+    _report_errors(f"{kind} dense squared distances (off-diagonal)", d.cpu()[~eye], d32[~eye], d64[~eye])
+    arbitrated_close(d.cpu()[~eye], d32[~eye], d64[~eye], atol=2e-5, floor=floor[~eye], what=f"{kind} dense squared distances")
+    arbitrated_close(d.cpu()[eye], d32[eye], d64[eye], atol=2e-5, floor=2 * floor[eye], what=f"{kind} self-distances")
     refs = []
     for m in (d32.clone(), d64.clone(), d.clone()):
         m.fill_diagonal_(1e10)
@@ -383,7 +390,7 @@ def _var_tol(ref64_scores, delta_rms, rtol=1e-4):
     return 2 * sd * delta_rms + delta_rms ** 2 + rtol * ref64_scores.double().var(dim=0)
 
 
-@pytest.mark.parametrize("dim,sigma_sq", [(64, 1e-3), (64, 0.3), (128, 0.05)])
+@pytest.mark.parametrize("dim,sigma_sq", [(64, 1e-5), (64, 1e-3), (64, 0.3), (128, 0.05)])
 def test_metric_utils_tensor_path_fp64_arbitrated(cuda_device, dim, sigma_sq):
     """compute_metric_scalar / compute_metric_matrix / compute_rescaled_metric_matrix (utils/metric_utils.py:4-216) with
     K = 2000 prior samples in D >= 64 dimensions: the engine takes the tensor path.  The estimators are D/2 - Var_y(score):

@@ -192,6 +192,7 @@ def test_screened_posterior_mean(backend):
         t_rows, post = ((1 - ab) / ab).expand(b), ab.rsqrt().expand(b)
         before = scr.screen_report.get("pm_rows_certified", 0)
         got = scr.posterior_mean(xt, t_rows, post=post).cpu()
+        scr._pm_poll(wait=True)              # the counts follow the call (no host read inside it): collect them
         plain = ref.posterior_mean(xt, t_rows, post=post).cpu()
         want = orc.posterior_mean_x0(xt, ab, data, dtype=torch.float64)
         assert (scr.screen_report.get("pm_rows_certified", 0) > before) == expect_certified, (alpha_bar, scr.screen_report)

@@ -61,6 +61,13 @@ def _worker(rank, world, data_shards, port, out_dir):
            "aux_mean": st_aux["aux_mean"], "calls": be.calls}
     if grid.query_groups == 1:                        # the denoiser path shards the dataset only
         res["mean"] = eng.posterior_mean(xq, torch.full((B,), 0.5))
+        if grid.data_shards > 1:                      # reduce-scatter form: every rank gets its slice of the rows
+            part = eng.posterior_mean(xq, torch.full((B,), 0.5), scatter=True)
+            per = (B + grid.data_shards - 1) // grid.data_shards
+            lo_r = grid.data_index * per
+            assert part.shape == (per, D)
+            assert torch.allclose(part[:max(0, min(B, lo_r + per) - lo_r)], res["mean"][lo_r:lo_r + per], rtol=1e-6, atol=1e-7)
+            assert bool((part[max(0, min(B, lo_r + per) - lo_r):] == 0).all())
         res["gq"], res["gt"] = eng.posterior_mean_backward(xq, torch.full((B,), 0.5), None, up)
     # the reference-facing functions over the same grid: only this rank's rows are uploaded, Tr Sigma_0 / range from
     # all-reduced column moments, k-NN regulariser with the shards taking turns as the query set
