@@ -358,6 +358,10 @@ int pdm_weighted_mean_exact_f32(const float* p, int64_t ldp, int64_t M, int64_t 
  * ------------------------------------------------------------------------------------------- */
 int pdm_sampler_step_f32(const float* x0_hat, const float* xt, const float* noise, float c_x0, float c_xt,
                          float c_noise, float* out, int64_t n, pdm_stream_t stream);
+/* Same with the three coefficients read from DEVICE memory (coef[0..2] = c_x0, c_xt, c_noise): a step captured once in a
+ * CUDA graph is replayed for every noise level of a trajectory, the host only rewrites five device scalars in between. */
+int pdm_sampler_step_dev_f32(const float* x0_hat, const float* xt, const float* noise, const float* coef,
+                             float* out, int64_t n, pdm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * k-NN selection on a dense distance tile (pdm_posterior_stats with energy_out, mult 2): the k smallest

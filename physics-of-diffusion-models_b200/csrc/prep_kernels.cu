@@ -532,7 +532,8 @@ __global__ void __launch_bounds__(256) refine_neighbours_kernel(const float* __r
 // not declared restrict, every thread reads its elements before it writes them.
 __global__ void __launch_bounds__(256) sampler_step_kernel(const float* __restrict__ x0_hat, const float* xt,
                                                            const float* __restrict__ noise, float c_x0, float c_xt, float c_noise,
-                                                           float* out, int64_t n, int vec) {
+                                                           float* out, int64_t n, int vec, const float* __restrict__ coef) {
+    if (coef) { c_x0 = __ldg(coef); c_xt = __ldg(coef + 1); c_noise = __ldg(coef + 2); }     // CUDA-graphed steps: device scalars
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
@@ -723,7 +724,18 @@ extern "C" int pdm_sampler_step_f32(const float* x0_hat, const float* xt, const 
     if (n == 0) return PDM_OK;
     const bool vec = aligned16(x0_hat) && aligned16(xt) && aligned16(out) && (!noise || aligned16(noise));
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 16);
-    sampler_step_kernel<<<grid, 256, 0, as_stream(stream)>>>(x0_hat, xt, noise, c_x0, c_xt, c_noise, out, n, vec ? 1 : 0);
+    sampler_step_kernel<<<grid, 256, 0, as_stream(stream)>>>(x0_hat, xt, noise, c_x0, c_xt, c_noise, out, n, vec ? 1 : 0, nullptr);
+    PDM_CUDA_CHECK(cudaGetLastError());
+    return PDM_OK;
+}
+
+extern "C" int pdm_sampler_step_dev_f32(const float* x0_hat, const float* xt, const float* noise, const float* coef,
+                                        float* out, int64_t n, pdm_stream_t stream) {
+    PDM_REQUIRE(x0_hat && xt && out && coef && n >= 0, "pdm_sampler_step_dev_f32: bad arguments");
+    if (n == 0) return PDM_OK;
+    const bool vec = aligned16(x0_hat) && aligned16(xt) && aligned16(out) && (!noise || aligned16(noise));
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 16);
+    sampler_step_kernel<<<grid, 256, 0, as_stream(stream)>>>(x0_hat, xt, noise, 0.f, 0.f, 0.f, out, n, vec ? 1 : 0, coef);
     PDM_CUDA_CHECK(cudaGetLastError());
     return PDM_OK;
 }

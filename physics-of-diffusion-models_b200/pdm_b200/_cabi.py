@@ -79,6 +79,7 @@ SIGNATURES = {
     "pdm_gather_rows_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P]),
     "pdm_split_gemm_f16x3": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _I64, _F, _P, _I64, _I32, _I32, _P]),
     "pdm_sampler_step_f32": (C.c_int, [_P, _P, _P, _F, _F, _F, _P, _I64, _P]),
+    "pdm_sampler_step_dev_f32": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
     "pdm_topk_smallest_f32": (C.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "pdm_denoiser_backward_weights": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "pdm_weighted_mean_exact_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I32, _P]),

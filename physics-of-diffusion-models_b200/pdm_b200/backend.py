@@ -213,11 +213,14 @@ class CudaBackend:
                         index_offset: int = 0, n_splits: int = 0, m_group: int = 0, cta_group: int = 0,
                         want_partials: bool = True, energy_out: Optional[Tensor] = None,
                         energy_mult: float = 1.0, row_tiles: Optional[Tensor] = None,
-                        n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None, topk: bool = False):
+                        n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None, topk: bool = False,
+                        plan_row_tiles: int = 0):
         """``row_tiles`` (int32, device) / ``n_row_tiles``: screened launch over the listed row tiles of
         128*cta_group rows only; records of the other rows are left as allocated (uninitialised).
         ``n_row_tiles_dev`` (one int32 on the device): the list's actual length, read by the kernel -- ``n_row_tiles`` is
-        then only the upper bound the schedule is planned for, and nothing is read back to the host."""
+        then only the upper bound, and nothing is read back to the host; ``plan_row_tiles`` is the length the schedule
+        (m_group x n_splits) is planned for when the caller has an estimate (any value is safe: the kernel walks the
+        device-side length whatever the plan)."""
         a = StatsArgs()
         a.precision = PRECISIONS[precision]
         a.n_splits, a.m_group, a.cta_group = n_splits, m_group, cta_group
@@ -241,8 +244,12 @@ class CudaBackend:
                 a.n_row_tiles_dev = n_row_tiles_dev.data_ptr()
                 keep.append(n_row_tiles_dev)
         nfloats = C.c_int64()
+        if row_tiles is not None and plan_row_tiles > 0:
+            a.n_row_tiles = max(1, min(int(plan_row_tiles), int(n_row_tiles)))
         check(self.lib.pdm_posterior_stats_plan(C.byref(a), self.device.index or 0, C.byref(nfloats)),
               "pdm_posterior_stats_plan")
+        if row_tiles is not None:
+            a.n_row_tiles = int(n_row_tiles)
         partials = None
         if topk:
             # top-k epilogue: per (record, row) the 8 smallest squared distances and their local dataset rows
@@ -483,13 +490,19 @@ class CudaBackend:
         self.launches += 1
 
     def sampler_step(self, x0_hat: Tensor, xt: Tensor, noise: Optional[Tensor], c_x0: float, c_xt: float, c_noise: float,
-                     out: Optional[Tensor] = None) -> Tensor:
-        """out = c_x0 * x0_hat + c_xt * xt (+ c_noise * noise); ``out`` may be ``xt``."""
+                     out: Optional[Tensor] = None, coef: Optional[Tensor] = None) -> Tensor:
+        """out = c_x0 * x0_hat + c_xt * xt (+ c_noise * noise); ``out`` may be ``xt``.  ``coef`` (3 floats on the device)
+        replaces the three host scalars (CUDA-graphed sampling steps)."""
         if out is None:
             out = torch.empty_like(xt)
         for t in (x0_hat, xt, out) + ((noise,) if noise is not None else ()):
             if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
                 raise PdmError("sampler_step needs contiguous float32 tensors on the engine's device")
+        if coef is not None:
+            check(self.lib.pdm_sampler_step_dev_f32(x0_hat.data_ptr(), xt.data_ptr(), _ptr(noise), coef.data_ptr(),
+                                                    out.data_ptr(), xt.numel(), self._stream()), "pdm_sampler_step_dev_f32")
+            self.launches += 1
+            return out
         check(self.lib.pdm_sampler_step_f32(x0_hat.data_ptr(), xt.data_ptr(), _ptr(noise), float(c_x0), float(c_xt),
                                             float(c_noise), out.data_ptr(), xt.numel(), self._stream()), "pdm_sampler_step_f32")
         self.launches += 1

@@ -199,11 +199,12 @@ class EngineConfig:
                                        # nearest training point directly (skips weights + second contraction for them)
     fused_noise: bool = True           # regenerate torch.randn's Philox stream inside the operand kernel (bit-identical,
                                        # verified once per device) instead of torch.randn + pdm_prepare_rows
-    screen: bool = False               # noised_stats: certified delta posteriors.  A one-product tensor pass with a rigorous
-                                       # error bound proves, row by row, that every other training point's weight is below
-                                       # exp(-screen_g) of the nearest one's; proven rows take the closed form and only the
-                                       # row tiles with an unproven row run the full-precision pass (include/pdm_b200.h,
-                                       # pdm_screen_*).  PDM_SCREEN=1 turns it on.
+    screen: bool = True                # certified delta posteriors (on by default since round 2: parity at the named
+                                       # configurations is pinned with it on, tests/test_gpu_named_configs.py).  A one-product
+                                       # tensor pass with a rigorous error bound proves, row by row, that every other training
+                                       # point's weight is below exp(-screen_g) of the nearest one's; proven rows take the closed
+                                       # form and only the row tiles with an unproven row run the full-precision pass
+                                       # (include/pdm_b200.h, pdm_screen_*).  PDM_SCREEN=0 turns it off.
     screen_f8: bool = True             # screening cascade: an E4M3 pass (twice the MMA rate) first, the fp16 one-product pass
                                        # only on the row tiles it leaves unproven (PDM_SCREEN_F8=0 turns the first stage off)
     screen_g: float = 0.0              # weight cut-off exponent; 0 = 17 + log N (everything dropped sums to < 2^-24)
@@ -252,6 +253,8 @@ class PosteriorEngine:
         self._pm_screen_t = math.inf       # posterior_mean: blocks whose temperatures are all below this mark are screened
         self._screen_t_retry = math.inf    # after a screened block that certified nothing: next attempt at T <= this
         self._pm_pending: list = []        # posterior_mean: screening counts in flight to the host (lagged feedback)
+        self._screen_prior = None          # noised_stats: lowest temperature at which a row stayed unproven (across calls)
+        self._screen_hint: dict = {}       # noised_stats: listed tiles of a block in the previous call (schedule hint)
         self._y_norm_max = None
         if group is not None:
             import torch.distributed as dist
@@ -302,7 +305,8 @@ class PosteriorEngine:
 
     def _local_partials(self, prep: dict, rows: int, inv_temp: Tensor, aux: Optional[Tensor], precision: str,
                         energy_out: Optional[Tensor] = None, energy_mult: float = 1.0, want_partials: bool = True,
-                        row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None):
+                        row_tiles: Optional[Tensor] = None, n_row_tiles: int = 0, n_row_tiles_dev: Optional[Tensor] = None,
+                        plan_row_tiles: int = 0):
         ds = self.ds
         kw = dict(precision=precision, M=rows, N=ds.n, d=ds.d, q_norm=prep["norms"], y_norm=ds.y_norm,
                   inv_temp=inv_temp, y_aux=aux, index_offset=ds.index_offset, n_splits=self.cfg.n_splits,
@@ -312,6 +316,8 @@ class PosteriorEngine:
             kw.update(row_tiles=row_tiles, n_row_tiles=n_row_tiles)
             if n_row_tiles_dev is not None:
                 kw.update(n_row_tiles_dev=n_row_tiles_dev)
+            if plan_row_tiles > 0:
+                kw.update(plan_row_tiles=plan_row_tiles)
         if precision == "exact":
             return self.backend.posterior_stats(q=prep["x"], y=ds.y, **kw)
         y_hi, y_lo = ds.split()
@@ -463,8 +469,23 @@ class PosteriorEngine:
             else:                                              # a failed attempt at temperature T is repeated below T/2
                 self._pm_screen_t = min(self._pm_screen_t, 0.5 * t_lo)
 
+    @staticmethod
+    def _open_boundary(open_rows: Tensor, t_rows: Tensor, per_temp: int) -> Tensor:
+        """Lowest temperature at which MOST rows stayed unproven (device scalar, +inf if none): the boundary of the
+        certifiable range.  Single rows that can never be certified -- a query next to duplicated or near-duplicate
+        training points fails at every temperature -- must not move it, so rows are grouped in runs of ``per_temp`` (one
+        temperature of a schedule; 1 = every row on its own) and a run counts as failed when more than half of it is open."""
+        n = open_rows.numel()
+        if per_temp <= 1 or n < per_temp:
+            frac, t_run = open_rows.to(torch.float32), t_rows
+        else:
+            runs = n // per_temp                                   # a ragged tail joins nothing: it is dropped
+            frac = open_rows[:runs * per_temp].view(runs, per_temp).to(torch.float32).mean(dim=1)
+            t_run = t_rows[:runs * per_temp].view(runs, per_temp)[:, 0]
+        return torch.where(frac > 0.5, t_run, torch.full_like(t_run, math.inf)).min()
+
     def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
-                        precision: str, ascending: bool = True, wide: bool = True):
+                        precision: str, ascending: bool = True, wide: bool = True, per_temp: int = 1):
         """One-product pass at the fictitious temperature -> certificate per row -> full-precision pass over the row
         tiles that hold an unproven row -> closed form for the proven rows.
 
@@ -501,8 +522,9 @@ class PosteriorEngine:
             flags[r0:r1] = f
             arg1[r0:r1] = a
             open_rows = f == 0
-            t_rows = temp_rows[r0:r1]
-            t_open = torch.where(open_rows, t_rows, torch.full_like(t_rows, math.inf)).min()
+            # rows r0.. start on a temperature boundary whenever the tile size divides per_temp (B = 1024 queries, 256-row
+            # tiles); otherwise the runs are shifted by a few rows, which a majority vote does not mind
+            t_open = self._open_boundary(open_rows, temp_rows[r0:r1], per_temp)
             n_l, t_open, n_open = (float(v) for v in torch.stack(
                 [nl[0].to(torch.float64), t_open.to(torch.float64), open_rows.sum().to(torch.float64)]).cpu())
             n_l, n_open = int(n_l), int(n_open)
@@ -514,7 +536,7 @@ class PosteriorEngine:
             rep["tiles_screened"] += tb - ta
             rep["tiles_full_pass"] += n_l
             self._screen_t_fail = min(self._screen_t_fail, t_open)
-            if n_open == r1 - r0:
+            if n_open == r1 - r0 and math.isfinite(t_open):
                 self._screen_t_retry = min(self._screen_t_retry, 0.25 * t_open)
             elif 2 * n_l <= tb - ta:
                 self._screen_t_retry = math.inf            # the certifiable range has been reached
@@ -558,9 +580,48 @@ class PosteriorEngine:
             out[_cabi.OUT_AUX_MEAN].copy_(-both[1])
         return out, argmin
 
+    def _screened_block_prior(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
+                              precision: str, screen_rows: tuple, plan_tiles: int = 0, per_temp: int = 1):
+        """The same pipeline once the certifiable temperature range is known from an earlier call on this dataset: rows
+        ``screen_rows`` = [r0, r1) (tile-aligned, the block's low-temperature end) go through the cascade in one go, the rest
+        is left to the full pass, and NOTHING is read back -- the list of row tiles with an unproven row and its length stay
+        on the device (pdm_stats_args.n_row_tiles_dev).  Returns (out, argmin, feedback) with feedback = device scalars
+        (listed tiles, lowest unproven temperature, unproven rows) that the caller reads once at the end of the call."""
+        be, ds = self.backend, self.ds
+        dev = be.device
+        rpt = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)
+        tiles = (rows + rpt - 1) // rpt
+        r0, r1 = screen_rows
+        flags = torch.zeros(rows, dtype=torch.uint8, device=dev)          # unscreened rows count as unproven: listed
+        arg1 = torch.zeros(rows, dtype=torch.int64, device=dev)
+        sub = {k: (v[r0:r1] if isinstance(v, Tensor) else v) for k, v in prep.items()}
+        f, a, _, _, _, nl8 = self._screen_cascade_async(sub, r1 - r0, inv_temp[r0:r1], self._screen_f8_live)
+        flags[r0:r1] = f
+        arg1[r0:r1] = a
+        tile_list, n_listed = be.screen_tile_list(flags, rpt)
+        parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=tiles,
+                                     n_row_tiles_dev=n_listed, plan_row_tiles=plan_tiles)
+        out, argmin = self._merge(parts, inv_temp)
+        y_hi, y_lo = ds.split()
+        be.screen_finalize(flags, arg1, ds.d, (prep["hi"], prep["lo"], prep["inv_scale"]), prep["norms"],
+                           (y_hi, None if precision == "f16x2" else y_lo), 1.0 / ds.scale, ds.y_norm, aux,
+                           ds.index_offset, ds.n, ds.n_total, out, argmin)
+        if self.world > 1:
+            import torch.distributed as dist
+            both = torch.stack([out[_cabi.OUT_E_MIN], -out[_cabi.OUT_AUX_MEAN]])
+            dist.all_reduce(both, op=dist.ReduceOp.MIN, group=self.group)
+            out[_cabi.OUT_E_MIN].copy_(both[0])
+            out[_cabi.OUT_AUX_MEAN].copy_(-both[1])
+        open_rows = f == 0
+        t_open = self._open_boundary(open_rows, temp_rows[r0:r1], per_temp)
+        feedback = torch.stack([n_listed[0].to(torch.float64), t_open.to(torch.float64), open_rows.sum().to(torch.float64),
+                                (nl8[0] if nl8 is not None else n_listed.new_full((1,), -1)[0]).to(torch.float64)])
+        return out, argmin, feedback
+
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
                     sigma: Optional[Tensor] = None, post: Optional[Tensor] = None, aux: Optional[Tensor] = None,
-                    prep: Optional[dict] = None, screen: bool = False, ascending: bool = True, wide: bool = True):
+                    prep: Optional[dict] = None, screen: bool = False, ascending: bool = True, wide: bool = True,
+                    per_temp: int = 1):
         """Statistics for ``rows`` query rows; returns (out (8, rows), argmin (rows,)) device tensors.
         Query row r is  (noise[r]*sigma[r] + src[r % len(src)]) * post[r]  (noise/post optional); ``prep`` passes
         already prepared operands (rank-sliced preparation of a sharded run) instead."""
@@ -575,7 +636,8 @@ class PosteriorEngine:
                 prep = self._prepare(src, rows, noise, sigma, post, precision, want_x=False)
         if screen and self.screening_usable():
             with ph("fused"):
-                return self._screened_block(prep, rows, temp_rows.to(torch.float32), inv_temp, aux, precision, ascending, wide)
+                return self._screened_block(prep, rows, temp_rows.to(torch.float32), inv_temp, aux, precision, ascending, wide,
+                                            per_temp)
         self.screen_report["rows_unscreened"] += rows
         with ph("fused"):
             parts = self._local_partials(prep, rows, inv_temp, aux, precision)
@@ -670,6 +732,12 @@ class PosteriorEngine:
         self._screen_t_fail = math.inf
         self._screen_t_retry = math.inf
         self._screen_f8_live = True
+        # From the second call on the certifiable range is known (one dataset, one boundary: the lowest temperature at
+        # which a row stayed unproven, remembered across calls): a block screens its rows below 1.5x that mark in one go
+        # and leaves the rest, without probing and without reading anything back until the end of the call.
+        prior = self._screen_prior if (screen_on and hasattr(self.backend, "screen_merge_stage")) else None
+        rpt = getattr(self.backend, "row_tile", None) or 128 * (self.cfg.cta_group or 2)
+        pending = []                              # (feedback scalars on the device, rows screened, tiles screened, block key)
         ph = getattr(self.backend, "phase", None)
         if ph is None:
             import contextlib
@@ -682,20 +750,53 @@ class PosteriorEngine:
             asc = not screen or bool(temp_host[k0] <= temp_host[k1 - 1])
             wide = screen and float(temp_host[k0:k1].max()) > 8.0 * float(temp_host[k0:k1].min())
             t_rows = tb.repeat_interleave(b)
+            th = temp_host[k0:k1] if screen_on else None
+            monotone = screen_on and (bool((th[1:] >= th[:-1]).all()) or bool((th[1:] <= th[:-1]).all()))
+            if prior is not None and monotone:
+                # temperatures of the block at or below the cut sit at one end of it
+                below = int((th <= 1.5 * prior).sum())
+                span = None
+                if below > 0:
+                    if bool(th[0] <= th[-1]):
+                        span = (0, min(nb * b, -(-below * b // rpt) * rpt))
+                    else:
+                        span = ((nb - below) * b // rpt * rpt, nb * b)
+                if span is not None and span[1] - span[0] >= min(rpt, nb * b):
+                    with ph("noise+prepare" if fused else "noise"):
+                        if fused:
+                            prep = self._fused_prepare(gen.initial_seed(), base + (qr + k0 * qw) * step_off, qw * step_off, x0f,
+                                                       tb, x0_absmax)
+                        else:
+                            noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
+                            for i in range(nb):
+                                draw_into(noise[i], qr + (k0 + i) * qw)
+                            prep = self._prepare(x0f, nb * b, noise.view(nb * b, -1), t_rows.sqrt(), None, self.precision(), False)
+                    with ph("fused"):
+                        key = (n_t, b, k0)
+                        o, i, fb = self._screened_block_prior(prep, nb * b, t_rows, (1.0 / t_rows).contiguous(), aux,
+                                                              self.precision(), span, self._screen_hint.get(key, 0), per_temp=b)
+                    pending.append((fb, span[1] - span[0], (span[1] - span[0] + rpt - 1) // rpt, key, nb * b))
+                    outs.append(o)
+                    idxs.append(i)
+                    continue
+                screen = False                    # nothing of this block lies in the certifiable range
             if fused:
                 with ph("noise+prepare"):
                     prep = self._fused_prepare(gen.initial_seed(), base + (qr + k0 * qw) * step_off, qw * step_off, x0f, tb,
                                                x0_absmax)
-                o, i = self.stats_block(x0f, nb * b, t_rows, aux=aux, prep=prep, screen=screen, ascending=asc, wide=wide)
+                o, i = self.stats_block(x0f, nb * b, t_rows, aux=aux, prep=prep, screen=screen, ascending=asc, wide=wide,
+                                        per_temp=b)
             else:
                 with ph("noise"):
                     noise = torch.empty(nb, b, self.ds.d, dtype=torch.float32, device=dev)
                     for i in range(nb):
                         draw_into(noise[i], qr + (k0 + i) * qw)
                 o, i = self.stats_block(x0f, nb * b, t_rows, noise=noise.view(nb * b, -1), sigma=t_rows.sqrt(), aux=aux,
-                                        screen=screen, ascending=asc, wide=wide)
+                                        screen=screen, ascending=asc, wide=wide, per_temp=b)
             outs.append(o)
             idxs.append(i)
+        if screen_on:
+            self._screen_feedback(pending, float(temp_host.max()) if n_mine > 0 else math.inf, rpt)
         if draw is None:                          # leave the generator where a single-GPU run would
             if on_cuda:
                 gen.set_offset(base + n_t * step_off)
@@ -714,6 +815,33 @@ class PosteriorEngine:
         res = {k: out[j] for j, k in enumerate(STAT_KEYS)}
         res["argmin"] = arg
         return res
+
+    def _screen_feedback(self, pending: list, t_max: float, rpt: int) -> None:
+        """End of a noised_stats call: read the screening counts of its blocks (one copy for all of them) and move the
+        remembered boundary: the lowest temperature at which a row stayed unproven; if every screened row was proven the
+        mark moves up by the factor the next call will try."""
+        rep = self.screen_report
+        if pending:
+            vals = torch.stack([p[0] for p in pending]).cpu()
+            t_fail = math.inf
+            for (_, rows_s, tiles_s, key, rows_blk), v in zip(pending, vals.tolist()):
+                n_l, t_open, n_open, n8 = int(v[0]), float(v[1]), int(v[2]), int(v[3])
+                unscreened_tiles = (rows_blk - rows_s + rpt - 1) // rpt
+                rep["rows_screened"] += rows_s
+                rep["rows_certified"] += rows_s - n_open
+                rep["rows_unscreened"] += rows_blk - rows_s
+                rep["tiles_screened"] += tiles_s
+                rep["tiles_full_pass"] += max(0, n_l - unscreened_tiles)
+                if n8 >= 0:
+                    rep["f8_tiles_screened"] = rep.get("f8_tiles_screened", 0) + tiles_s
+                    rep["f8_tiles_left"] = rep.get("f8_tiles_left", 0) + n8
+                self._screen_hint[key] = n_l + 2              # schedule hint for the same block of the next call
+                t_fail = min(t_fail, t_open)
+            self._screen_prior = t_fail if math.isfinite(t_fail) else min(1.5 * self._screen_prior, 2.0 * t_max)
+        elif self._screen_prior is None and math.isfinite(self._screen_t_fail):
+            self._screen_prior = self._screen_t_fail          # first call: the probing found the boundary
+        elif self._screen_prior is None and self.screen_report["rows_screened"] > 0 and not math.isfinite(self._screen_t_fail):
+            self._screen_prior = 2.0 * t_max                  # everything proven: screen the whole schedule next time
 
     def _gather_temperatures(self, out: Tensor, arg: Tensor, n_t: int):
         """(8, n_mine, B) statistics and (n_mine, B) arg-mins of this rank's temperatures -> those of the whole schedule,
@@ -811,7 +939,8 @@ class PosteriorEngine:
 
     # -- posterior mean ---------------------------------------------------------------------------
     def posterior_mean(self, x: Tensor, temp_rows: Tensor, post: Optional[Tensor] = None,
-                       values: Optional[Tensor] = None, temp_bounds: Optional[tuple] = None, scatter: bool = False) -> Tensor:
+                       values: Optional[Tensor] = None, temp_bounds: Optional[tuple] = None, scatter: bool = False,
+                       frozen: Optional[tuple] = None) -> Tensor:
         """x0_hat[r] = sum_j p_rj y_j with p ~ exp(-||x_r*post_r - y_j||^2 / (2 T_r)).  Returns (M, d).
         ``values`` (N, dv) replaces y_j in the weighted sum (posterior mean of arbitrary per-point vectors).
 
@@ -823,7 +952,9 @@ class PosteriorEngine:
         ``scatter`` (row-sharded dataset): the shards' partial sums are combined with a reduce-scatter instead of an
         all-reduce and the call returns only this rank's slice of the rows, ceil(M / world) of them starting at
         rank * ceil(M / world) (zero rows beyond M) -- a sampler whose ranks each own a slice of the trajectories moves
-        M d / world floats per rank instead of M d."""
+        M d / world floats per rank instead of M d.
+        ``frozen`` = (screen?, E4M3 stage?, pinned int32[2] buffer): the screening decisions are the caller's and the counts
+        are copied to the caller's buffer -- the form a CUDA-graph capture of a sampling step needs (IdealSampler)."""
         dev = self.backend.device
         be = self.backend
         ds = self.ds
@@ -856,7 +987,7 @@ class PosteriorEngine:
             import contextlib
             ph = lambda _n: contextlib.nullcontext()      # noqa: E731
         screen_on = self.screening_usable() and tile_ops and m > 0
-        if screen_on:
+        if screen_on and frozen is None:
             self._pm_poll()
             if temp_bounds is None:
                 temp_bounds = tuple(float(v) for v in torch.stack([temp_rows.min(), temp_rows.max()]).cpu())
@@ -874,11 +1005,17 @@ class PosteriorEngine:
             # to 1.5 T; they persist across calls: one dataset, one boundary).
             listed = None                    # (tile list, device-side length) of the full-precision pass; None = every tile
             flags_s = arg_s = None
-            if screen_on and temp_bounds[1] < self._pm_screen_t:
+            attempt = screen_on and (frozen[0] if frozen is not None else temp_bounds[1] < self._pm_screen_t)
+            if attempt:
                 with ph("screen"):
-                    flags_s, arg_s, tl, nl, _, nl8 = self._screen_cascade_async(prep, rows, inv_temp, temp_bounds[1] < self._pm_f8_t)
+                    use_f8 = frozen[1] if frozen is not None else temp_bounds[1] < self._pm_f8_t
+                    flags_s, arg_s, tl, nl, _, nl8 = self._screen_cascade_async(prep, rows, inv_temp, use_f8)
                     listed = (tl, nl)
-                    self._pm_report(nl, nl8, tiles, rows, temp_bounds[0], temp_bounds[1])
+                    if frozen is None:
+                        self._pm_report(nl, nl8, tiles, rows, temp_bounds[0], temp_bounds[1])
+                    else:
+                        frozen[2].copy_(torch.cat([nl.reshape(1), nl8.reshape(1) if nl8 is not None else nl.new_full((1,), -1)]),
+                                        non_blocking=True)
             with ph("prepare"):
                 energy = torch.empty(rows, ds.n, dtype=torch.float32, device=dev)
             with ph("fused+energy"):

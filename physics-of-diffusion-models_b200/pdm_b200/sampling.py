@@ -13,6 +13,7 @@ value.  The RNG stream is the reference's: ``torch.randn`` for the initial state
 from __future__ import annotations
 
 import math
+import os
 from typing import Iterable, Optional
 
 import torch
@@ -47,13 +48,24 @@ class IdealSampler:
     from the last entry down and finishes at the clean state (log_temp = -inf, alpha_bar = 1)."""
 
     def __init__(self, train_data: Tensor, log_temp: Tensor | Iterable[float], step_type: str = "ddim",
-                 engine: Optional[PosteriorEngine] = None, config: Optional[EngineConfig] = None, query_group=None):
+                 engine: Optional[PosteriorEngine] = None, config: Optional[EngineConfig] = None, query_group=None,
+                 use_graphs: Optional[bool] = None):
         """``query_group``: torch.distributed group whose ranks share the work of every batch (mode 2:
         the dataset -- 0.6 GB at CIFAR-10 shape -- is replicated, each rank owns a contiguous slice of the trajectories,
         no collective inside the loop; the samples are all-gathered once at the end).  Every rank draws the whole batch's
         noise and keeps its rows, so the result is the one-GPU result for the same seed, whatever the number of ranks."""
         if step_type not in ("ddpm", "ddim"):
             raise ValueError(f"unknown step type: {step_type}")
+        # CUDA graphs (PDM_SAMPLER_GRAPHS=0 turns them off): a step never reads anything back from the device, so it is
+        # captured once per (batch slice, screening mode) and replayed with five device scalars rewritten in between --
+        # the ~60 launches and allocations of a step cost the host one graph launch (the low-noise steps of a trajectory
+        # split over 8 GPUs are otherwise bound by the host, not the GPU).
+        if use_graphs is None:
+            use_graphs = os.environ.get("PDM_SAMPLER_GRAPHS", "1") != "0"
+        self.use_graphs = bool(use_graphs)
+        self._graphs: dict = {}
+        self._graph_seen: dict = {}
+        self.graph_replays = 0
         self.engine = engine if engine is not None else PosteriorEngine(
             EmpiricalDataset(train_data, backend=default_backend()), config)
         self.backend = self.engine.backend
@@ -80,6 +92,86 @@ class IdealSampler:
         per = (batch_size + self.q_world - 1) // self.q_world
         return min(batch_size, self.q_rank * per), min(batch_size, (self.q_rank + 1) * per)
 
+    # ---- one reverse-diffusion step ----------------------------------------------------------------------------------
+    def _step_eager(self, flat: Tensor, batch_size: int, lo: int, hi: int, ab: float, abp: float, last: bool) -> None:
+        dev, d, rows = self.backend.device, self.engine.ds.d, hi - lo
+        t = (1.0 - ab) / ab
+        if self.dataset_sharded:
+            every = self._gather_rows(flat.view(rows, *self.obj_size), batch_size, copy=False).view(batch_size, d)
+            x0_hat = self.engine.posterior_mean(every, torch.full((batch_size,), t, device=dev),
+                                                post=torch.full((batch_size,), 1.0 / math.sqrt(ab), device=dev),
+                                                temp_bounds=(t, t), scatter=True)[:rows]
+        else:
+            ones = torch.ones(rows, dtype=torch.float32, device=dev)
+            x0_hat = self.engine.posterior_mean(flat, ones * t, post=ones * (1.0 / math.sqrt(ab)), temp_bounds=(t, t))
+        c_x0, c_xt, c_noise = step_coefficients(ab, abp, self.step_type)
+        noise = None
+        if self.step_type == "ddpm" and not last:                 # no draw on the last step (ddpm_sampling.py:107)
+            noise = torch.randn(batch_size, *self.obj_size, device=dev)       # = randn_like(xt) of the whole batch
+            noise = noise.view(batch_size, d)[lo:hi].contiguous()
+        self.backend.sampler_step(x0_hat, flat, noise, c_x0, c_xt, c_noise if noise is not None else 0.0, out=flat)
+
+    def _graph_mode(self, t: float) -> tuple:
+        """(screen?, E4M3 stage?) exactly as PosteriorEngine.posterior_mean would decide them from its marks."""
+        eng = self.engine
+        eng._pm_poll()
+        if not eng.screening_usable():
+            return (False, False)
+        return (t < eng._pm_screen_t, t < eng._pm_f8_t)
+
+    def _step_graphed(self, flat: Tensor, batch_size: int, lo: int, hi: int, ab: float, abp: float, last: bool,
+                      scal_row: Tensor) -> bool:
+        """Replay (or capture, the second time a configuration is met -- the first time runs eagerly and doubles as the
+        warm-up of every lazy initialisation) the CUDA graph of one step.  False: this step has to run eagerly."""
+        dev, d, rows = self.backend.device, self.engine.ds.d, hi - lo
+        t = (1.0 - ab) / ab
+        has_noise = self.step_type == "ddpm" and not last
+        mode = self._graph_mode(t)
+        key = (flat.data_ptr(), rows, batch_size, lo, mode, has_noise)
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if seen == 0:
+            return False
+        entry = self._graphs.get(key)
+        if entry is None:
+            scal = torch.empty(5, dtype=torch.float32, device=dev)
+            counts = torch.zeros(2, dtype=torch.int32).pin_memory()
+            scal.copy_(scal_row)
+            eng = self.engine
+
+            def body():
+                temp_rows = scal[0:1].expand(rows)
+                post = scal[1:2].expand(rows)
+                x0_hat = eng.posterior_mean(flat, temp_rows, post=post, temp_bounds=(t, t), frozen=(mode[0], mode[1], counts))
+                noise = None
+                if has_noise:
+                    noise = torch.randn(batch_size, *self.obj_size, device=dev).view(batch_size, d)[lo:hi].contiguous()
+                self.backend.sampler_step(x0_hat, flat, noise, 0.0, 0.0, 0.0, out=flat, coef=scal[2:5])
+
+            graph = torch.cuda.CUDAGraph()
+            try:
+                torch.cuda.synchronize(dev)
+                with torch.cuda.graph(graph):
+                    body()
+            except Exception as exc:                     # noqa: BLE001  (capture is an optimisation: fall back, say so once)
+                import warnings
+                warnings.warn(f"pdm_b200.IdealSampler: CUDA-graph capture failed ({type(exc).__name__}: {exc}); "
+                              "sampling continues without graphs")
+                self.use_graphs = False
+                return False
+            entry = (graph, scal, counts)
+            self._graphs[key] = entry
+        graph, scal, counts = entry
+        scal.copy_(scal_row, non_blocking=True)           # pinned row of the trajectory's table: a true async copy
+        graph.replay()
+        self.graph_replays += 1
+        if mode[0]:                                       # screening counts of this step -> the engine's lagged feedback
+            ev = torch.cuda.Event()
+            ev.record()
+            rpt = getattr(self.backend, "row_tile", None) or 128 * (self.engine.cfg.cta_group or 2)
+            self.engine._pm_pending.append((ev, counts, (rows + rpt - 1) // rpt, rows, t, t))
+        return True
+
     @torch.no_grad()
     def batch_sample(self, batch_size: int, track_states: bool = False, x_init: Optional[Tensor] = None) -> dict[str, Tensor]:
         """``x_init``: start from this state (shape (batch_size, *obj_size), at the noise level of the last entry of the
@@ -90,35 +182,41 @@ class IdealSampler:
         drawn = x_init is None
         if drawn:
             x_init = torch.randn(batch_size, *self.obj_size, device=dev)       # ddpm_sampling.py:114
-        xt = x_init.to(device=dev, dtype=torch.float32)[lo:hi]
-        if not drawn or self.q_world > 1:
-            xt = xt.clone()                                                   # the loop updates its state in place
         rows = hi - lo
+        graphs = self.use_graphs and dev.type == "cuda" and not self.dataset_sharded and rows > 0
+        if graphs:
+            # the graphs are tied to the address of the state they update: one persistent state buffer per slice shape
+            xt = self._graphs.get(("state", rows))
+            if xt is None:
+                xt = torch.empty(rows, *self.obj_size, dtype=torch.float32, device=dev)
+                self._graphs[("state", rows)] = xt
+            xt.copy_(x_init.to(device=dev, dtype=torch.float32)[lo:hi])
+        else:
+            xt = x_init.to(device=dev, dtype=torch.float32)[lo:hi]
+            if not drawn or self.q_world > 1:
+                xt = xt.clone()                                               # the loop updates its state in place
         states = [] if track_states else None
         flat = xt.view(rows, d)
-        ones = torch.ones(rows, dtype=torch.float32, device=dev)
+        table = None
+        if graphs:                                        # (t, 1/sqrt(ab), c_x0, c_xt, c_noise) of every step, pinned
+            rows_t = []
+            for idx in range(len(self.alpha_bar)):
+                ab = self.alpha_bar[idx]
+                abp = self.alpha_bar[idx - 1] if idx > 0 else 1.0
+                c = step_coefficients(ab, abp, self.step_type)
+                rows_t.append([(1.0 - ab) / ab, 1.0 / math.sqrt(ab), c[0], c[1],
+                               c[2] if (self.step_type == "ddpm" and idx > 0) else 0.0])
+            table = torch.tensor(rows_t, dtype=torch.float32).pin_memory()
+            self._scal_table = table                      # alive until the copies out of it have run
         for idx in range(len(self.alpha_bar) - 1, -1, -1):
             ab = self.alpha_bar[idx]
             abp = self.alpha_bar[idx - 1] if idx > 0 else 1.0         # clean_log_temp = -inf -> alpha_bar = 1
             last = idx == 0
-            t = (1.0 - ab) / ab
-            if self.dataset_sharded:
-                every = self._gather_rows(xt, batch_size, copy=False).view(batch_size, d)
-                x0_hat = self.engine.posterior_mean(every, torch.full((batch_size,), t, device=dev),
-                                                    post=torch.full((batch_size,), 1.0 / math.sqrt(ab), device=dev),
-                                                    temp_bounds=(t, t), scatter=True)[:rows]
-            else:
-                x0_hat = self.engine.posterior_mean(flat, ones * t, post=ones * (1.0 / math.sqrt(ab)), temp_bounds=(t, t))
-            c_x0, c_xt, c_noise = step_coefficients(ab, abp, self.step_type)
-            noise = None
-            if self.step_type == "ddpm" and not last:                 # no draw on the last step (:107)
-                noise = torch.randn(batch_size, *self.obj_size, device=dev)       # = randn_like(xt) of the whole batch
-                noise = noise.view(batch_size, d)[lo:hi]
-            self.backend.sampler_step(x0_hat, flat, noise.contiguous() if noise is not None else None, c_x0, c_xt,
-                                      c_noise if noise is not None else 0.0, out=flat)
+            if not (graphs and self.use_graphs and self._step_graphed(flat, batch_size, lo, hi, ab, abp, last, table[idx])):
+                self._step_eager(flat, batch_size, lo, hi, ab, abp, last)
             if states is not None:
                 states.append(self._gather_rows(xt, batch_size, copy=True))
-        res = {"x": self._gather_rows(xt, batch_size, copy=False)}
+        res = {"x": self._gather_rows(xt, batch_size, copy=graphs)}
         if states is not None:
             res["states"] = torch.stack(states[::-1])
         return res

@@ -316,6 +316,14 @@ def test_ideal_sampler_on_gpu(cuda_device, step_type):
     assert sampler.engine.precision() == "f16x2"
     torch.manual_seed(21)
     got = sampler.batch_sample(64)["x"]
+    # CUDA graphs: a step configuration met for the second time is captured and replayed from then on; same trajectory
+    # as the eager loop (the screening decisions may fall on different steps, both forms are inside the parity tolerance)
+    assert sampler.use_graphs and sampler.graph_replays > 0, sampler.graph_replays
+    torch.manual_seed(21)
+    again = sampler.batch_sample(64)["x"]                               # all replays now
+    torch.manual_seed(21)
+    eager = IdealSampler(data, log_temp, step_type=step_type, use_graphs=False).batch_sample(64)["x"]
+    assert (got - eager).abs().max().item() <= 1e-4 and (again - eager).abs().max().item() <= 1e-4
     model = DDPMTrue(sch, "x0", data)
     torch.manual_seed(21)
     with torch.no_grad():

@@ -215,6 +215,40 @@ def test_screened_schedule_equals_unscreened_and_policy_stops():
     assert (r_s["l"][:4, 5] >= 1.9).all() and (r_s["argmin"][:4, 5] == 5).all()
 
 
+def test_repeated_calls_remember_the_certifiable_range():
+    """Second and later calls on the same dataset: the boundary found by the first call's probing is remembered, every block
+    screens its rows below 1.5x that mark in ONE cascade with the tile list and its length left on the device (no probing, no
+    read-back inside the call) -- same results, and a query sitting on a duplicated training point (never certifiable, at any
+    temperature) does not drag the boundary down."""
+    data, x0 = _setup()
+    temp = torch.tensor([1e-4, 1e-3, 1e-2, 0.05, 0.2, 0.5, 1.0, 3.0, 10.0, 100.0, 1e3, 1e4])
+    be = SplitFakeBackend()
+    cfg = EngineConfig(precision="f16x3", screen=True, screen_f8=False)
+    cfg.max_query_bytes = 4 * x0.shape[0] * data.shape[1] * 12            # blocks of four temperatures
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=be), cfg)
+    noise = torch.randn(len(temp), x0.shape[0], data.shape[1], generator=syn.gen(9))
+    first = eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+    prior = eng._screen_prior
+    assert prior is not None and prior > 0.04, prior                      # NOT 1e-4, where the duplicate's query already fails
+    n_probe = len(be.calls)
+    second = eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+    calls = be.calls[n_probe:]
+    assert any(c.startswith("tiles:f16x3:") for c in calls)               # device-side list lengths: the sync-free path
+    assert calls.count("stats:f16x1:all") <= 3                            # one cascade per block that reaches below the mark
+    for k in ("log_l", "mean_e", "var_e", "entropy", "l"):
+        assert torch.isfinite(second[k]).all(), k
+        assert torch.allclose(second[k], first[k], rtol=1e-5, atol=1e-6), k
+    assert torch.equal(second["argmin"], first["argmin"])
+    assert (second["l"][:4, 5] >= 1.9).all()                              # the duplicate's query still goes through the full pass
+    plain = PosteriorEngine(EmpiricalDataset(data, backend=SplitFakeBackend()), EngineConfig(precision="f16x3", screen=False))
+    ref = plain.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+    for k in ("log_l", "mean_e", "var_e", "entropy"):
+        assert torch.allclose(second[k], ref[k], rtol=1e-4, atol=2e-6), k
+    # a descending schedule takes the same path (the certifiable rows sit at the END of a block)
+    third = eng.noised_stats(x0, temp.flip(0), noise_fn=lambda i: noise[len(temp) - 1 - i])
+    assert torch.allclose(third["entropy"].flip(0), ref["entropy"], rtol=1e-4, atol=2e-6)
+
+
 def test_certificate_is_sound_in_fp64():
     """Every certified row: all other points' weights are below exp(-g) in exact arithmetic."""
     data, x0 = _setup(n=600, d=128, b=16, seed=4)

@@ -34,7 +34,7 @@ def main():
     lo, hi = rank * per, min(n, (rank + 1) * per)
     amax = float(data.abs().max().item())
     lat = detect_lattice_scale(be, data, amax)
-    full = PosteriorEngine(EmpiricalDataset(data, backend=be), EngineConfig(max_query_bytes=96 << 20))
+    full = PosteriorEngine(EmpiricalDataset(data, backend=be), EngineConfig(max_query_bytes=96 << 20, screen=False))
     gen = PosteriorEngine._cuda_generator(dev)
     ok = True
 
