@@ -470,18 +470,23 @@ class PosteriorEngine:
                 self._pm_screen_t = min(self._pm_screen_t, 0.5 * t_lo)
 
     @staticmethod
+    def _open_runs(open_rows: Tensor, t_rows: Tensor, per_temp: int):
+        """(fraction of unproven rows, temperature) per run of ``per_temp`` rows (one temperature of a schedule; 1 = every row
+        on its own; a ragged tail joins nothing and is dropped)."""
+        n = open_rows.numel()
+        if per_temp <= 1 or n < per_temp:
+            return open_rows.to(torch.float32), t_rows
+        runs = n // per_temp
+        frac = open_rows[:runs * per_temp].view(runs, per_temp).to(torch.float32).mean(dim=1)
+        return frac, t_rows[:runs * per_temp].view(runs, per_temp)[:, 0]
+
+    @staticmethod
     def _open_boundary(open_rows: Tensor, t_rows: Tensor, per_temp: int) -> Tensor:
         """Lowest temperature at which MOST rows stayed unproven (device scalar, +inf if none): the boundary of the
         certifiable range.  Single rows that can never be certified -- a query next to duplicated or near-duplicate
-        training points fails at every temperature -- must not move it, so rows are grouped in runs of ``per_temp`` (one
-        temperature of a schedule; 1 = every row on its own) and a run counts as failed when more than half of it is open."""
-        n = open_rows.numel()
-        if per_temp <= 1 or n < per_temp:
-            frac, t_run = open_rows.to(torch.float32), t_rows
-        else:
-            runs = n // per_temp                                   # a ragged tail joins nothing: it is dropped
-            frac = open_rows[:runs * per_temp].view(runs, per_temp).to(torch.float32).mean(dim=1)
-            t_run = t_rows[:runs * per_temp].view(runs, per_temp)[:, 0]
+        training points fails at every temperature -- must not move it, so a temperature counts as failed only when more
+        than half of its rows are open."""
+        frac, t_run = PosteriorEngine._open_runs(open_rows, t_rows, per_temp)
         return torch.where(frac > 0.5, t_run, torch.full_like(t_run, math.inf)).min()
 
     def _screened_block(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
@@ -613,9 +618,12 @@ class PosteriorEngine:
             out[_cabi.OUT_E_MIN].copy_(both[0])
             out[_cabi.OUT_AUX_MEAN].copy_(-both[1])
         open_rows = f == 0
-        t_open = self._open_boundary(open_rows, temp_rows[r0:r1], per_temp)
+        frac, t_run = self._open_runs(open_rows, temp_rows[r0:r1], per_temp)
+        t_open = torch.where(frac > 0.5, t_run, torch.full_like(t_run, math.inf)).min()
+        top = t_run.argmax()                                   # the highest screened temperature and how it fared
         feedback = torch.stack([n_listed[0].to(torch.float64), t_open.to(torch.float64), open_rows.sum().to(torch.float64),
-                                (nl8[0] if nl8 is not None else n_listed.new_full((1,), -1)[0]).to(torch.float64)])
+                                (nl8[0] if nl8 is not None else n_listed.new_full((1,), -1)[0]).to(torch.float64),
+                                t_run[top].to(torch.float64), frac[top].to(torch.float64)])
         return out, argmin, feedback
 
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
@@ -733,7 +741,7 @@ class PosteriorEngine:
         self._screen_t_retry = math.inf
         self._screen_f8_live = True
         # From the second call on the certifiable range is known (one dataset, one boundary: the lowest temperature at
-        # which a row stayed unproven, remembered across calls): a block screens its rows below 1.5x that mark in one go
+        # which most rows stayed unproven, remembered across calls): a block screens its rows below that mark in one go
         # and leaves the rest, without probing and without reading anything back until the end of the call.
         prior = self._screen_prior if (screen_on and hasattr(self.backend, "screen_merge_stage")) else None
         rpt = getattr(self.backend, "row_tile", None) or 128 * (self.cfg.cta_group or 2)
@@ -754,7 +762,7 @@ class PosteriorEngine:
             monotone = screen_on and (bool((th[1:] >= th[:-1]).all()) or bool((th[1:] <= th[:-1]).all()))
             if prior is not None and monotone:
                 # temperatures of the block at or below the cut sit at one end of it
-                below = int((th <= 1.5 * prior).sum())
+                below = int((th < prior).sum())
                 span = None
                 if below > 0:
                     if bool(th[0] <= th[-1]):
@@ -823,7 +831,7 @@ class PosteriorEngine:
         rep = self.screen_report
         if pending:
             vals = torch.stack([p[0] for p in pending]).cpu()
-            t_fail = math.inf
+            t_fail, t_top, top_open = math.inf, 0.0, 1.0
             for (_, rows_s, tiles_s, key, rows_blk), v in zip(pending, vals.tolist()):
                 n_l, t_open, n_open, n8 = int(v[0]), float(v[1]), int(v[2]), int(v[3])
                 unscreened_tiles = (rows_blk - rows_s + rpt - 1) // rpt
@@ -837,7 +845,14 @@ class PosteriorEngine:
                     rep["f8_tiles_left"] = rep.get("f8_tiles_left", 0) + n8
                 self._screen_hint[key] = n_l + 2              # schedule hint for the same block of the next call
                 t_fail = min(t_fail, t_open)
-            self._screen_prior = t_fail if math.isfinite(t_fail) else min(1.5 * self._screen_prior, 2.0 * t_max)
+                if v[4] > t_top:
+                    t_top, top_open = float(v[4]), float(v[5])
+            # a temperature failed by majority: the mark moves there (strictly below it is screened next time); nothing
+            # failed and the highest screened temperature was proven almost entirely: try 1.25x further next time
+            if math.isfinite(t_fail):
+                self._screen_prior = t_fail
+            elif top_open < 0.2:
+                self._screen_prior = max(self._screen_prior, min(1.25 * t_top, 2.0 * t_max))
         elif self._screen_prior is None and math.isfinite(self._screen_t_fail):
             self._screen_prior = self._screen_t_fail          # first call: the probing found the boundary
         elif self._screen_prior is None and self.screen_report["rows_screened"] > 0 and not math.isfinite(self._screen_t_fail):

@@ -72,15 +72,23 @@ def _floors(xq, data, temp_rows):
     return f_e, f_e / temp_rows.double()
 
 
-def _oracle_rows(xq, data, temp_rows, aux=None, chunk=2048):
-    """fp32 and fp64 oracle statistics of explicit query rows (evaluated in chunks of rows: C1 has 102 400 of them)."""
+def _oracle_rows(xq, data, temp_rows, aux=None, chunk=2048, data_chunk=None):
+    """fp32 and fp64 oracle statistics of explicit query rows (evaluated in chunks of rows: C1 has 102 400 of them; and, for
+    the 7 - 10 GB datasets of C3 / C4, with the distance matrix assembled from chunks of dataset rows -- the chunking the
+    reference's DataLoader applies, utils/stats.py:276-280 -- so that the fp64 copy of the dataset never exists whole)."""
     res = {}
     flat = data.reshape(len(data), -1)
     for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
-        y = flat.to(dt)
+        y = flat.to(dt) if data_chunk is None else None
         acc = {}
         for r0 in range(0, len(xq), chunk):
-            e = 0.5 * orc.pairwise_sqdist(xq[r0:r0 + chunk].to(dt), y)
+            if y is not None:
+                e = 0.5 * orc.pairwise_sqdist(xq[r0:r0 + chunk].to(dt), y)
+            else:
+                q = xq[r0:r0 + chunk].to(dt)
+                e = torch.empty(q.shape[0], len(flat), dtype=dt)
+                for j0 in range(0, len(flat), data_chunk):
+                    e[:, j0:j0 + data_chunk] = 0.5 * orc.pairwise_sqdist(q, flat[j0:j0 + data_chunk].to(dt))
             st = orc.boltzmann_rows(e, temp_rows[r0:r0 + chunk].to(dt)[:, None], aux=None if aux is None else aux.to(dt))
             two = torch.topk(e, min(2, e.shape[1]), dim=1, largest=False).values
             st["gap"] = (two[:, -1] - two[:, 0]) if e.shape[1] > 1 else torch.full_like(two[:, 0], float("inf"))
@@ -329,6 +337,50 @@ def test_c2_ideal_denoiser_full_size(c2, cuda_device):
         worst = max(worst, (got.cpu().double() - ref64).abs().max().item())
     print(f"[parity C2 {c2['name']}] ideal denoiser: worst |x0_hat - fp64| over {len(c2['idx'])} noise levels = {worst:.2e}")
     sched._DENOISER_ENGINES.clear()
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# C3 (hypersphere, N = 100 000, d = 16 384) and C4 (CelebA-64 shape, N = 200 000, d = 12 288) at FULL size against the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_c3_c4_full_size_rows_against_oracle(backend, name):
+    """The 6.5 / 9.8 GB datasets of BASELINE.json's configs[2] and [3], whole, on one GPU: 24 queries x 8 temperatures of the
+    configuration's own grid (200 x logspace(-4, 4), reproduce_high_dim.py:150; 100 x logspace(-4, 8),
+    compute_cifar10_metric.py:24-26) through noised_stats with the noise replayed, plain and with certified delta
+    posteriors, every statistic and the arg-min against the oracle in fp32 and fp64."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    if name == "C3":
+        data = syn.hypersphere(16384, 100_000, 5)                   # sample_on_hypersphere, utils/synthetic_datasets.py:14-17
+        temps = torch.logspace(-4, 4, 200)[[0, 100, 150, 165, 172, 180, 190, 199]]
+    else:
+        data = torch.rand(200_000, 12288, generator=syn.gen(6)) * 2 - 1
+        temps = torch.logspace(-4, 8, 100)[[0, 33, 48, 52, 56, 60, 66, 99]]
+    b = 24
+    x0 = data[:b].clone()
+    eps = torch.randn(len(temps), b, data.shape[1], generator=syn.gen(78))
+    xt = (eps * temps.sqrt()[:, None, None] + x0).reshape(len(temps) * b, -1)
+    t_rows = temps.repeat_interleave(b)
+    ref = _oracle_rows(xt, data, t_rows, data_chunk=20_000)
+    _report_binding(name, ref, t_rows)
+    spread = ref["f64"]["log_l"].view(len(temps), b).mean(1)
+    print(f"[parity {name}] T = {[float(f'{t:.3g}') for t in temps]}\n"
+          f"             mean log l = {[round(float(v), 3) for v in spread]}  (0 = delta, {math.log(len(data)):.2f} = uniform)")
+    # (C3's own grid ends at T = 1e4, where the posterior of the hypersphere set is still far from uniform)
+    assert spread[0] < 1e-3 and spread[-1] > 0.5 * math.log(len(data)) and ((spread > 0.05) & (spread < 0.9 * math.log(len(data)))).sum() >= 2
+    ds = EmpiricalDataset(data, backend=backend)
+    from pdm_b200 import PosteriorEngine as PE
+    PE.noise_hook = staticmethod(lambda i, shape, dev: eps[i].reshape(shape).to(dev))
+    try:
+        for screen in (False, True):
+            eng = PosteriorEngine(ds, EngineConfig(screen=screen))
+            assert eng.precision() == "f16x3"
+            ns = eng.noised_stats(x0, temps)
+            st = {k: v.reshape(-1).cpu() for k, v in ns.items()}
+            _check_rows(st, ref, f"{name} noised_stats screen={screen}", xq=xt, data=data)
+    finally:
+        PE.noise_hook = None
+    del ds, eng
     torch.cuda.empty_cache()
 
 
