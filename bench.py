@@ -81,8 +81,8 @@ def measured_peaks():
 
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel at the bench's block shape, from
-    the committed `ncu --set full` summary (profiles/, captured with PDM_BENCH_NT=56 = one block of the C2 step)."""
-    path = os.path.join(ROOT, "profiles", "r1_fused_gemm_ncu_full_bench_block.csv")
+    the committed `ncu --set full` summary (profiles/, captured with PDM_BENCH_NT=168 = one 6 GiB block of the C2 step)."""
+    path = os.path.join(ROOT, "profiles", "r2_fused_gemm_f16x3_ncu_full_bench_block.csv")
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     total, seen = 0.0, 0
     try:
@@ -555,8 +555,10 @@ def run_ours(args):
                 torch.manual_seed(31 + rank)
                 x_init = (ab.sqrt() * data_full[torch.randint(0, n, (mq_local,), device=dev)]
                           + (1 - ab).sqrt() * torch.randn(mq_local, d, device=dev)).view(mq_local, *w["shape"])
-                sampler.batch_sample(mq_local, x_init=x_init.clone())              # warm-up pass over the slice
+                for _ in range(2):       # two warm-up passes over the slice: the second finds every CUDA graph of the first captured
+                    sampler.batch_sample(mq_local, x_init=x_init.clone())
                 barrier()
+                replays0 = sampler.graph_replays
                 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s0.record()
                 out = sampler.batch_sample(mq_local, x_init=x_init.clone())["x"]
@@ -568,7 +570,11 @@ def run_ours(args):
                 n_steps = i1 - i0
                 pps = n_steps * mq * n / (sms * 1e-3)
                 c5_line[tag] = {"steps": n_steps, "ms_per_step": sms / n_steps, "steps_per_s": n_steps / (sms * 1e-3),
-                                "value": pps, "unit": UNIT, "screening": engine is eng_rep_s}
+                                "value": pps, "unit": UNIT, "screening": engine is eng_rep_s,
+                                "cuda_graph_replays_in_timed_pass": sampler.graph_replays - replays0}
+                if os.environ.get("PDM_BENCH_DEBUG"):
+                    print(f"c5 {tag}: marks screen_t={engine._pm_screen_t:.4g} f8_t={engine._pm_f8_t:.4g} keys={sampler._graph_seen} "
+                          f"report={ {k: v for k, v in engine.screen_report.items() if k.startswith('pm_')} }", file=sys.stderr)
                 if tag.startswith("transition"):        # every pair is contracted there; the low-noise steps are gathers
                     c5_line[tag]["algorithmic_tflops"] = pps * 4 * d / 1e12
                     c5_line[tag]["roofline_frac"] = pps * 4 * d / 1e12 / (peaks["tflops"] * world)

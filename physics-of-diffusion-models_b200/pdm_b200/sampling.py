@@ -65,6 +65,7 @@ class IdealSampler:
         self.use_graphs = bool(use_graphs)
         self._graphs: dict = {}
         self._graph_seen: dict = {}
+        self._graph_pool = None
         self.graph_replays = 0
         self.engine = engine if engine is not None else PosteriorEngine(
             EmpiricalDataset(train_data, backend=default_backend()), config)
@@ -126,6 +127,8 @@ class IdealSampler:
         dev, d, rows = self.backend.device, self.engine.ds.d, hi - lo
         t = (1.0 - ab) / ab
         has_noise = self.step_type == "ddpm" and not last
+        if last and self.step_type == "ddpm":
+            return False                                  # the one step without a noise draw (ddpm_sampling.py:107): eager, once
         mode = self._graph_mode(t)
         key = (flat.data_ptr(), rows, batch_size, lo, mode, has_noise)
         seen = self._graph_seen.get(key, 0)
@@ -149,9 +152,11 @@ class IdealSampler:
                 self.backend.sampler_step(x0_hat, flat, noise, 0.0, 0.0, 0.0, out=flat, coef=scal[2:5])
 
             graph = torch.cuda.CUDAGraph()
+            if self._graph_pool is None:                 # one memory pool for all graphs of this sampler: they replay one
+                self._graph_pool = torch.cuda.graph_pool_handle()      # after the other, their scratch can overlap
             try:
                 torch.cuda.synchronize(dev)
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, pool=self._graph_pool):
                     body()
             except Exception as exc:                     # noqa: BLE001  (capture is an optimisation: fall back, say so once)
                 import warnings

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    env = dict(os.environ, PDM_BENCH_N="3000", PDM_BENCH_CPU_B="32", PDM_BENCH_CPU_NT="2", OMP_NUM_THREADS="4")
+    env = dict(os.environ, PDM_BENCH_N="3000", PDM_BENCH_CPU_B="32", PDM_BENCH_CPU_NT="2", OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -23,6 +23,10 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
     assert line["vs_baseline"] is None and line["gpu_launches"] == 0
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the arm must still use every host core, and report the stock
+    # dataloader_batch_size = 100 variant beside the chunk-5000 one
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["stock_dataloader_batch_size_100"]["value"] > 0
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():

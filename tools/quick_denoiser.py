@@ -12,7 +12,7 @@ torch.manual_seed(0)
 y = torch.rand(n, d, device=be.device) * 2 - 1
 ds = EmpiricalDataset(y, backend=be)
 eng = PosteriorEngine(ds, EngineConfig())
-ab = torch.tensor(0.3, device=be.device)
+ab = torch.tensor(float(os.environ.get("AB", 0.002)), device=be.device)        # T ~ 500: every point carries weight
 x = ab.sqrt() * y[torch.randint(0, n, (b,), device=be.device)] + (1 - ab).sqrt() * torch.randn(b, d, device=be.device)
 t = ((1 - ab) / ab).expand(b)
 post = ab.rsqrt().expand(b)
