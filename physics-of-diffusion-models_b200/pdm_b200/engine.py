@@ -192,7 +192,8 @@ class EngineConfig:
     n_splits: int = 0
     max_query_bytes: int = 6 << 30     # scratch budget for one block of query rows (noise + split): fewer, larger
                                        # launches (and fewer cross-GPU merges) per schedule; 180 GB of HBM3e to spare
-    max_energy_bytes: int = 3 << 30    # scratch budget for the energy tile of the posterior-mean path
+    max_energy_bytes: int = 8 << 30    # scratch budget for the energy tile + weights of the posterior-mean path: 10^4 queries against
+                                       # N = 50 000 in ONE block (two blocks of 8053 + 1947 rows cost a whole extra round of tiles)
     sync_noise: bool = True            # sharded runs: make every rank draw rank 0's noise stream (set False when
                                        # every rank seeds its generator identically)
     delta_shortcut: bool = True        # posterior mean: rows whose posterior is a delta to fp32 resolution take their
