@@ -380,13 +380,16 @@ def run_ours(args):
         if not eng_s.screening_usable():
             return None
         try:
-            ms_s, k_ms_s, k_pairs_s, launches_s, _, _ = measure(eng_s, queries, temps, extra_steps, 1)
+            ms_s, k_ms_s, k_pairs_s, launches_s, ph_s, _ = measure(eng_s, queries, temps, extra_steps, 1)
         except Exception as exc:                    # a secondary entry must never cost the headline line
             backend.kernel_events = None
             backend.phase_events = None
             return {"error": f"{type(exc).__name__}: {exc}"[:300]}
         rep = eng_s.screen_report
         runs = 1 + extra_steps
+        if os.environ.get("PDM_BENCH_PHASES") and rank == 0:
+            print(f"screened run: {ms_s / extra_steps:.2f} ms/step wall on the device; phases ms/step:",
+                  {k: round(v / extra_steps, 2) for k, v in (ph_s or {}).items()}, file=sys.stderr)
         val = pairs_per_step * extra_steps / (ms_s * 1e-3)
         return {"value": val, "unit": UNIT, "ms_per_step": ms_s / extra_steps, "steps": extra_steps,
                 "precision": eng_s.precision() + (" + screening cascade (e4m3 pass, then fp16 one-product pass)"

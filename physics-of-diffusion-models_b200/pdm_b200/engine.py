@@ -600,24 +600,31 @@ class PosteriorEngine:
         r0, r1 = screen_rows
         flags = torch.zeros(rows, dtype=torch.uint8, device=dev)          # unscreened rows count as unproven: listed
         arg1 = torch.zeros(rows, dtype=torch.int64, device=dev)
+        ph = getattr(be, "phase", None)
+        if ph is None:
+            import contextlib
+            ph = lambda _n: contextlib.nullcontext()      # noqa: E731
         sub = {k: (v[r0:r1] if isinstance(v, Tensor) else v) for k, v in prep.items()}
-        f, a, _, _, _, nl8 = self._screen_cascade_async(sub, r1 - r0, inv_temp[r0:r1], self._screen_f8_live)
-        flags[r0:r1] = f
-        arg1[r0:r1] = a
-        tile_list, n_listed = be.screen_tile_list(flags, rpt)
-        parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=tiles,
-                                     n_row_tiles_dev=n_listed, plan_row_tiles=plan_tiles)
-        out, argmin = self._merge(parts, inv_temp)
-        y_hi, y_lo = ds.split()
-        be.screen_finalize(flags, arg1, ds.d, (prep["hi"], prep["lo"], prep["inv_scale"]), prep["norms"],
-                           (y_hi, None if precision == "f16x2" else y_lo), 1.0 / ds.scale, ds.y_norm, aux,
-                           ds.index_offset, ds.n, ds.n_total, out, argmin)
-        if self.world > 1:
-            import torch.distributed as dist
-            both = torch.stack([out[_cabi.OUT_E_MIN], -out[_cabi.OUT_AUX_MEAN]])
-            dist.all_reduce(both, op=dist.ReduceOp.MIN, group=self.group)
-            out[_cabi.OUT_E_MIN].copy_(both[0])
-            out[_cabi.OUT_AUX_MEAN].copy_(-both[1])
+        with ph("screen: cascade"):
+            f, a, _, _, _, nl8 = self._screen_cascade_async(sub, r1 - r0, inv_temp[r0:r1], self._screen_f8_live)
+            flags[r0:r1] = f
+            arg1[r0:r1] = a
+            tile_list, n_listed = be.screen_tile_list(flags, rpt)
+        with ph("screen: full pass over listed tiles"):
+            parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=tiles,
+                                         n_row_tiles_dev=n_listed, plan_row_tiles=plan_tiles)
+            out, argmin = self._merge(parts, inv_temp)
+        with ph("screen: closed form"):
+            y_hi, y_lo = ds.split()
+            be.screen_finalize(flags, arg1, ds.d, (prep["hi"], prep["lo"], prep["inv_scale"]), prep["norms"],
+                               (y_hi, None if precision == "f16x2" else y_lo), 1.0 / ds.scale, ds.y_norm, aux,
+                               ds.index_offset, ds.n, ds.n_total, out, argmin)
+            if self.world > 1:
+                import torch.distributed as dist
+                both = torch.stack([out[_cabi.OUT_E_MIN], -out[_cabi.OUT_AUX_MEAN]])
+                dist.all_reduce(both, op=dist.ReduceOp.MIN, group=self.group)
+                out[_cabi.OUT_E_MIN].copy_(both[0])
+                out[_cabi.OUT_AUX_MEAN].copy_(-both[1])
         open_rows = f == 0
         frac, t_run = self._open_runs(open_rows, temp_rows[r0:r1], per_temp)
         t_open = torch.where(frac > 0.5, t_run, torch.full_like(t_run, math.inf)).min()
@@ -780,7 +787,7 @@ class PosteriorEngine:
                             for i in range(nb):
                                 draw_into(noise[i], qr + (k0 + i) * qw)
                             prep = self._prepare(x0f, nb * b, noise.view(nb * b, -1), t_rows.sqrt(), None, self.precision(), False)
-                    with ph("fused"):
+                    if True:
                         key = (n_t, b, k0)
                         o, i, fb = self._screened_block_prior(prep, nb * b, t_rows, (1.0 / t_rows).contiguous(), aux,
                                                               self.precision(), span, self._screen_hint.get(key, 0), per_temp=b)
