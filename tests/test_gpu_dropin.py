@@ -264,8 +264,9 @@ def test_denoiser_backward_lattice_and_sampler_chain(cuda_device):
     assert (lt.grad.double().cpu() - lt64.grad).abs().max().item() <= 2e-3 * lt64.grad.abs().max().item() + 1e-7
 
 
-def test_sharded_sliced_noise_two_gpus(cuda_device):
-    """Row-sharded dataset + rank-sliced noise draw against the unsharded engine (needs >= 2 GPUs; tools/check_sharded_gpu.py)."""
+def test_sharded_grid_two_gpus(cuda_device):
+    """Every dataset-shards x temperature-groups layout of the visible GPUs against the unsharded engine, plus both multi-GPU
+    samplers against the one-GPU sampler (needs >= 2 GPUs; tools/check_sharded_gpu.py under torchrun)."""
     import os
     import subprocess
     import sys
