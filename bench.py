@@ -585,8 +585,43 @@ def run_ours(args):
                     c5_line[tag]["note"] = ("certified delta posteriors: a one-product screening pass proves every row, the mean is a "
                                             "gather of nearest training points -- no flop rate is claimed for these steps")
                 del sampler
+            # ---- C5 whole: the named configuration itself -- 10 000 samples x all 1000 DDPM steps from pure noise -------
+            # (DDPMSampler(n_steps=1000, n_samples=10_000, batch_size=10_000, step_type="ddpm")).
+            # Size-independent check of the result: the reverse process of the EMPIRICAL denoiser ends on training points
+            # (its last steps are delta posteriors), so every sample must sit on its nearest training image.
+            if os.environ.get("PDM_BENCH_C5_FULL", "1") == "1" and n_t >= 1000:
+                engine = eng_rep_s if eng_rep_s.screening_usable() else eng_rep
+                sampler = IdealSampler(data_full.view(n, *w["shape"]), log_t, step_type="ddpm", engine=engine,
+                                       query_group=(dist.group.WORLD if world > 1 else None))
+                torch.manual_seed(41)
+                sampler.batch_sample(mq)                 # untimed pass: captures the CUDA graph of every step configuration
+                barrier()
+                replays0 = sampler.graph_replays
+                torch.manual_seed(42)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                samples = sampler.batch_sample(mq)["x"]
+                f1.record()
+                barrier()
+                fms = max_over_ranks(f0.elapsed_time(f1))
+                near_v, _ = engine.nearest(samples[q_lo:q_hi].reshape(mq_local, d), 1)
+                worst = near_v.max().reshape(1) if mq_local > 0 else torch.zeros(1, device=dev)
+                if world > 1:
+                    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+                n_steps = len(log_t)
+                c5_line["full_trajectory"] = {
+                    "workload": f"C5 whole: {mq} samples x {n_steps} DDPM steps from pure noise (T = {float(temps[-1]):.4g} -> "
+                                f"{float(temps[0]):.4g}); samples / {world}, dataset replicated, one all-gather at the end",
+                    "seconds": fms * 1e-3, "ms_per_step": fms / n_steps, "steps_per_s": n_steps / (fms * 1e-3),
+                    "value": n_steps * mq * n / (fms * 1e-3), "unit": UNIT, "pairs": n_steps * mq * n,
+                    "cuda_graph_replays_in_timed_pass": sampler.graph_replays - replays0,
+                    "max_sq_distance_of_a_sample_to_its_nearest_training_point": float(worst.item()),
+                    "samples_finite": bool(torch.isfinite(samples).all())}
+                if not c5_line["full_trajectory"]["samples_finite"]:
+                    raise RuntimeError("C5 trajectory produced non-finite samples")
+                del sampler, samples
         except Exception as exc:                # secondary entry
-            c5_line = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            c5_line = dict(c5_line or {}, error=f"{type(exc).__name__}: {exc}"[:300])
         del eng_rep, eng_rep_s, ds_rep
         torch.cuda.empty_cache()
 
