@@ -787,10 +787,9 @@ class PosteriorEngine:
                             for i in range(nb):
                                 draw_into(noise[i], qr + (k0 + i) * qw)
                             prep = self._prepare(x0f, nb * b, noise.view(nb * b, -1), t_rows.sqrt(), None, self.precision(), False)
-                    if True:
-                        key = (n_t, b, k0)
-                        o, i, fb = self._screened_block_prior(prep, nb * b, t_rows, (1.0 / t_rows).contiguous(), aux,
-                                                              self.precision(), span, self._screen_hint.get(key, 0), per_temp=b)
+                    key = (n_t, b, k0)
+                    o, i, fb = self._screened_block_prior(prep, nb * b, t_rows, (1.0 / t_rows).contiguous(), aux,
+                                                          self.precision(), span, self._screen_hint.get(key, 0), per_temp=b)
                     pending.append((fb, span[1] - span[0], (span[1] - span[0] + rpt - 1) // rpt, key, nb * b))
                     outs.append(o)
                     idxs.append(i)

@@ -335,3 +335,57 @@ def test_ideal_sampler_on_gpu(cuda_device, step_type):
     # the trajectories end on training images (the posterior is a delta at the lowest noise level)
     d2 = torch.cdist(got.reshape(64, -1), data.reshape(800, -1)).min(1).values
     assert d2.max().item() < 0.5
+
+
+@pytest.mark.parametrize("step_type,kind", [("ddpm", "continuous"), ("ddim", "pixels")])
+def test_ideal_sampler_every_step_against_the_fp64_oracle(cuda_device, step_type, kind):
+    """Every state of a fused-sampler trajectory against the ORACLE's fp64 one-step update of the state before it
+    (teacher-forced, so the comparison does not depend on how round-off grows along a chaotic trajectory): the ideal
+    denoiser of diffusion/scheduler/scheduler.py:58-69 in fp64 on the CPU, the DDPMPredictions algebra and the DDPM / DDIM
+    update of diffusion/ddpm_sampling.py:94-110 written out, the noise re-drawn from the same CUDA stream."""
+    from diffusion.scheduler import LinearBetaScheduler
+    from pdm_b200 import IdealSampler
+    gen = torch.Generator().manual_seed(5)
+    if kind == "pixels":
+        px = torch.randint(0, 256, (900, 3, 8, 8), generator=gen, dtype=torch.uint8)
+        data = (px.float() / 255 - 0.5) / 0.5
+    else:
+        centres = torch.randn(12, 3, 8, 8, generator=gen)
+        data = (centres[torch.randint(0, 12, (900,), generator=gen)] + 0.15 * torch.randn(900, 3, 8, 8, generator=gen)).clamp(-1, 1)
+    obj, bsz, n_steps = tuple(data.shape[1:]), 48, 40
+    sch = LinearBetaScheduler(1e-4, 2.478e4)
+    log_temp = sch.log_temp_from_tau(torch.linspace(0, 1, n_steps + 1, dtype=torch.float64)[1:])
+    sampler = IdealSampler(data.to(cuda_device), log_temp, step_type=step_type)
+    for _ in range(2):                       # second pass: every step configuration replays its CUDA graph
+        torch.manual_seed(77)
+        states = sampler.batch_sample(bsz, track_states=True)["states"].cpu().double()       # states[idx] = state after step idx
+    assert sampler.graph_replays > 0 and states.shape == (n_steps, bsz, *obj)
+    torch.manual_seed(77)                    # the draws of that pass, in order: initial state, then one per DDPM step but the last
+    x_init = torch.randn(bsz, *obj, device=cuda_device).cpu().double()
+    ab_all = torch.sigmoid(-log_temp)
+    worst = 0.0
+    for idx in range(n_steps - 1, -1, -1):
+        xt = x_init if idx == n_steps - 1 else states[idx + 1]
+        ab, abp = ab_all[idx], (ab_all[idx - 1] if idx > 0 else torch.tensor(1.0, dtype=torch.float64))
+        x0_hat = orc.posterior_mean_x0(xt, ab.reshape(1), data, dtype=torch.float64)
+        if step_type == "ddpm":
+            alpha = ab / abp
+            beta = 1 - alpha
+            noise = torch.randn(bsz, *obj, device=cuda_device).cpu().double() if idx > 0 else 0.0
+            want = x0_hat * (abp.sqrt() * beta) / (1 - ab) + xt * (alpha.sqrt() * (1 - abp)) / (1 - ab) \
+                + noise * ((1 - abp) / (1 - ab) * beta).sqrt()
+        else:
+            eps = (xt - ab.sqrt() * x0_hat) / (1 - ab).sqrt()
+            want = abp.sqrt() * x0_hat + (1 - abp).sqrt() * eps
+        # fp32 state: 2^-24 relative round-off of each of the three terms, plus 1e-4 of the denoiser's output scale, or twice
+        # what the reference's own fp32 denoiser deviates from fp64 on this state (the arbitration rule of the other tests)
+        x0_ref32 = orc.posterior_mean_x0(xt.float(), ab.float().reshape(1), data).double()
+        c_x0 = float(abp.sqrt() * (1 - ab / abp) / (1 - ab)) if step_type == "ddpm" else 1.0
+        tol = max(1e-4 * max(1.0, float(want.abs().max())), 2 * c_x0 * float((x0_ref32 - x0_hat).abs().max())) \
+            + 4 * 2.0 ** -24 * float(xt.abs().max())
+        err = float((states[idx] - want).abs().max())
+        worst = max(worst, err / tol)
+        assert err <= tol, (idx, err, tol)
+    print(f"[parity sampler {step_type}/{kind}] worst one-step error / tolerance over {n_steps} steps: {worst:.3f}")
+    near = torch.cdist(states[0].reshape(bsz, -1), data.reshape(len(data), -1).double()).min(1).values
+    assert near.max().item() < 1e-3                    # the trajectory ends ON training points
