@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(256) column_moments_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // energy -> normalised weights p = exp(-(E - m)/T) / l   (scheduler.py:66-68)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ energy, int64_t lde, int64_t M, int64_t N,
+template <bool kP32>
+__global__ void __launch_bounds__(256, 3) weights_kernel(const float* __restrict__ energy, int64_t lde, int64_t M, int64_t N,
                                                       const float* __restrict__ e_min, const float* __restrict__ l,
                                                       const float* __restrict__ inv_temp,
                                                       float* __restrict__ p32, int64_t ldp32,
@@ -333,40 +334,66 @@ __global__ void __launch_bounds__(256) weights_kernel(const float* __restrict__ 
     const float m = e_min[row], it = inv_temp[row], inv_l = 1.f / l[row];
     const int64_t width = ph ? ldph : N;
     if (vec) {
-        // 8 columns per thread: two 128-bit energy loads, one 128-bit store per fp16 plane
-        const int64_t groups = width >> 3;
-        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t j0 = g << 3;
-            float e[8];
-            if (j0 + 8 <= N) {
-                const float4 a = ldg_f4(energy + row * lde + j0), b = ldg_f4(energy + row * lde + j0 + 4);
-                e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
-            } else {
+        // 8 columns per group: two 128-bit energy loads, one 128-bit store per fp16 plane.  A thread takes kU groups per
+        // trip with all of their loads issued before the first exponential (128 bytes in flight per thread: the kernel
+        // is HBM-bound, 8 bytes per pair, and a block walks a whole row -- or a few blocks share it when rows are few).
+        constexpr int kU = 4;
+        const int groups = (int)(width >> 3), n32 = (int)N;             // N < 2^31 (checked by the launcher)
+        const int stride = (int)(gridDim.x * blockDim.x);
+        const float* er = energy + row * lde;
+        __half* phr = ph ? ph + row * ldph : nullptr;
+        __half* plr = ph ? pl + row * ldph : nullptr;
+        float* p32r = (kP32 && p32) ? p32 + row * ldp32 : nullptr;
+        for (int g0 = (int)(blockIdx.x * blockDim.x + threadIdx.x); g0 < groups; g0 += kU * stride) {
+            float4 ea[kU], eb[kU];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) e[k] = (j0 + k < N) ? __ldg(energy + row * lde + j0 + k) : INFINITY;
+            for (int u = 0; u < kU; ++u) {
+                const int g = g0 + u * stride, j0 = g << 3;
+                if (g < groups && j0 + 8 <= n32) { ea[u] = ldg_f4(er + j0); eb[u] = ldg_f4(er + j0 + 4); }
             }
-            __half h[8], lo[8];
-            float pv[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float ee = fminf((e[k] - m) * it, kMaxE);
-                pv[k] = (j0 + k < N) ? fast_exp2(-ee * kLog2e) * inv_l : 0.f;
-                split_f16(pv[k] * 16384.f, h[k], lo[k]);
-            }
-            if (ph) {
-                *reinterpret_cast<uint4*>(ph + row * ldph + j0) = *reinterpret_cast<uint4*>(h);
-                *reinterpret_cast<uint4*>(pl + row * ldph + j0) = *reinterpret_cast<uint4*>(lo);
-            }
-            if (p32 && j0 + 8 <= N) {
-                *reinterpret_cast<float4*>(p32 + row * ldp32 + j0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                *reinterpret_cast<float4*>(p32 + row * ldp32 + j0 + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
-            } else if (p32) {
-                for (int k = 0; k < 8; ++k) if (j0 + k < N) p32[row * ldp32 + j0 + k] = pv[k];
+            for (int u = 0; u < kU; ++u) {
+                const int g = g0 + u * stride, j0 = g << 3;
+                if (g < groups && j0 + 8 <= n32) {
+                    const float ev[8] = {ea[u].x, ea[u].y, ea[u].z, ea[u].w, eb[u].x, eb[u].y, eb[u].z, eb[u].w};
+                    float pv[8];
+                    uint32_t hw[4], lw[4];             // the fp16 planes, two columns per word
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2) {
+                        __half h0, l0, h1, l1;
+                        pv[k] = fast_exp2(-fminf((ev[k] - m) * it, kMaxE) * kLog2e) * inv_l;
+                        pv[k + 1] = fast_exp2(-fminf((ev[k + 1] - m) * it, kMaxE) * kLog2e) * inv_l;
+                        split_f16(pv[k] * 16384.f, h0, l0);
+                        split_f16(pv[k + 1] * 16384.f, h1, l1);
+                        hw[k / 2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        lw[k / 2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    }
+                    if (phr) {
+                        *reinterpret_cast<uint4*>(phr + j0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(plr + j0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    if (kP32 && p32r) {
+                        *reinterpret_cast<float4*>(p32r + j0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                        *reinterpret_cast<float4*>(p32r + j0 + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+                    }
+                } else if (g < groups) {               // the ragged last group of a row (and the padding up to ldph)
+                    for (int k = 0; k < 8; ++k) {
+                        float pk = 0.f;
+                        if (j0 + k < n32) pk = fast_exp2(-fminf((__ldg(er + j0 + k) - m) * it, kMaxE) * kLog2e) * inv_l;
+                        if (phr) {
+                            __half h, lo;
+                            split_f16(pk * 16384.f, h, lo);
+                            phr[j0 + k] = h;
+                            plr[j0 + k] = lo;
+                        }
+                        if (p32r && j0 + k < n32) p32r[j0 + k] = pk;
+                    }
+                }
             }
         }
         // tail columns of an fp32-only output whose width is not a multiple of 8
         if (!ph && blockIdx.x == 0) {
-            for (int64_t j = (groups << 3) + threadIdx.x; j < N; j += blockDim.x) {
+            for (int64_t j = ((int64_t)groups << 3) + threadIdx.x; j < N; j += blockDim.x) {
                 const float ee = fminf((__ldg(energy + row * lde + j) - m) * it, kMaxE);
                 p32[row * ldp32 + j] = fast_exp2(-ee * kLog2e) * inv_l;
             }
@@ -659,13 +686,19 @@ extern "C" int pdm_weights_from_energy_tiles(const float* energy, int64_t lde, i
     const int64_t slots = row_tiles ? n_row_tiles * rows_per_tile : M;      // rows to visit (upper bound with a device count)
     if (M == 0 || slots == 0) return PDM_OK;
     PDM_REQUIRE(slots <= 65535 * 1024LL, "pdm_weights_from_energy: M too large for one launch");
+    PDM_REQUIRE(N < (1ll << 31) - 16 && (!p_hi || ldph < (1ll << 31) - 16), "pdm_weights_from_energy: N must fit in int32");
     const int64_t width = p_hi ? ldph : N;
     const bool vec = lde % 4 == 0 && aligned16(energy) && (!p_hi || (aligned16(p_hi) && aligned16(p_lo))) &&
                      (!p_f32 || (ldp32 % 4 == 0 && aligned16(p_f32)));
     for (int64_t r0 = 0; r0 < slots; r0 += 65535) {
         const int64_t rows = std::min<int64_t>(65535, slots - r0);
-        dim3 grid((unsigned)std::min<int64_t>(ceil_div(width, vec ? 2048 : 256), 64), (unsigned)rows);
-        weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+        // vectorised path: a block takes 1024 groups of 8 columns per trip and walks its share of the row; rows are split
+        // over several blocks only while there are too few rows to fill the device
+        const int64_t per_row = vec ? std::max<int64_t>(1, std::min<int64_t>(ceil_div(width, 8 * 1024), ceil_div(148 * 16, rows)))
+                                    : std::min<int64_t>(ceil_div(width, 256), 64);
+        dim3 grid((unsigned)per_row, (unsigned)rows);
+        auto kern = p_f32 ? weights_kernel<true> : weights_kernel<false>;
+        kern<<<grid, 256, 0, as_stream(stream)>>>(
             energy, lde, M, N, e_min, l, inv_temp, p_f32, ldp32, reinterpret_cast<__half*>(p_hi), reinterpret_cast<__half*>(p_lo),
             ldph, vec ? 1 : 0, row_tiles, rows_per_tile, n_row_tiles_dev, r0);
         PDM_CUDA_CHECK(cudaGetLastError());
