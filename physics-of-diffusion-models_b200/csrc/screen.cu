@@ -95,7 +95,20 @@ __global__ void __launch_bounds__(1024) tile_list_kernel(const uint8_t* __restri
         bool listed = false;
         if (t < tiles) {
             const int64_t r0 = t * rows_per_tile, r1 = min(M, r0 + rows_per_tile);
-            for (int64_t r = r0; r < r1 && !listed; ++r) listed = flags[r] == 0;
+            if (r1 - r0 == rows_per_tile && rows_per_tile % 16 == 0 && ((reinterpret_cast<uintptr_t>(flags) + r0) & 15) == 0) {
+                // a whole tile: independent 128-bit loads, any zero byte lists it (a serial byte scan of a fully certified
+                // tile -- the common case of a low-noise sampling step -- took 17 us per launch)
+                const uint4* f4 = reinterpret_cast<const uint4*>(flags + r0);
+                uint32_t zero = 0;
+                for (int i = 0; i < rows_per_tile / 16; ++i) {
+                    const uint4 v = __ldg(f4 + i);
+                    zero |= ((v.x - 0x01010101u) & ~v.x) | ((v.y - 0x01010101u) & ~v.y) |
+                            ((v.z - 0x01010101u) & ~v.z) | ((v.w - 0x01010101u) & ~v.w);
+                }
+                listed = (zero & 0x80808080u) != 0;
+            } else {
+                for (int64_t r = r0; r < r1 && !listed; ++r) listed = flags[r] == 0;
+            }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, listed);
         if (lane == 0) warp_count[warp] = __popc(bal);
