@@ -628,10 +628,12 @@ class PosteriorEngine:
         open_rows = f == 0
         frac, t_run = self._open_runs(open_rows, temp_rows[r0:r1], per_temp)
         t_open = torch.where(frac > 0.5, t_run, torch.full_like(t_run, math.inf)).min()
-        top = t_run.argmax()                                   # the highest screened temperature and how it fared
+        # the highest screened temperature and how it fared.  (Indexing with the 0-dim result of argmax() would read it
+        # back -- torch turns a 0-dim integer tensor index into .item() -- and stall the host once per block: gather.)
+        top = t_run.argmax().reshape(1)
         feedback = torch.stack([n_listed[0].to(torch.float64), t_open.to(torch.float64), open_rows.sum().to(torch.float64),
                                 (nl8[0] if nl8 is not None else n_listed.new_full((1,), -1)[0]).to(torch.float64),
-                                t_run[top].to(torch.float64), frac[top].to(torch.float64)])
+                                t_run.gather(0, top)[0].to(torch.float64), frac.gather(0, top)[0].to(torch.float64)])
         return out, argmin, feedback
 
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
