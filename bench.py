@@ -640,8 +640,11 @@ def run_ours(args):
     del data_full, eng, ds
     torch.cuda.empty_cache()
     with contextlib.redirect_stdout(io.StringIO()):
-        torch.manual_seed(1)
-        ustats.compute_stats_batch(loader, x0_host, temps_host)         # uploads + caches the dataset
+        # W untimed calls: the first uploads + caches the dataset and finds the certifiable range by probing, the second is
+        # the first on the remembered-boundary path (new scratch sizes: ~0.1 s of cudaMalloc, once per process)
+        for i in range(max(2, args.warmup)):
+            torch.manual_seed(1 + i)
+            ustats.compute_stats_batch(loader, x0_host, temps_host)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):

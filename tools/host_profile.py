@@ -22,9 +22,13 @@ y = torch.rand(n, d, device=dev) * 2 - 1
 eng = PosteriorEngine(EmpiricalDataset(y, backend=be), EngineConfig())
 temps = ddpm_temperatures(1000, 1e-4, 2.478e4).to(dev)[0::int(os.environ.get("STRIDE", 4))].contiguous()
 x0 = y[:b].clone()
-for _ in range(3):
+for i in range(6):                      # the first calls one by one: probing call, first remembered-boundary call, steady state
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     eng.noised_stats(x0, temps)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    print(f"call {i}: {(time.perf_counter() - t0) * 1e3:.2f} ms, reserved {torch.cuda.memory_reserved() / 2**30:.2f} GiB, "
+          f"boundary {eng._screen_prior}")
 t0 = time.perf_counter()
 for _ in range(5):
     eng.noised_stats(x0, temps)
