@@ -255,6 +255,7 @@ class PosteriorEngine:
         self._screen_t_retry = math.inf    # after a screened block that certified nothing: next attempt at T <= this
         self._pm_pending: list = []        # posterior_mean: screening counts in flight to the host (lagged feedback)
         self._screen_prior = None          # noised_stats: lowest temperature at which a row stayed unproven (across calls)
+        self._screen_prior_f8 = None       # noised_stats: the same mark for the E4M3 first stage alone (rows between the two marks skip it)
         self._screen_hint: dict = {}       # noised_stats: listed tiles of a block in the previous call (schedule hint)
         self._y_norm_max = None
         if group is not None:
@@ -427,6 +428,7 @@ class PosteriorEngine:
         if not (use_f8 and self._f8_stage_usable()):
             return self._screen_certificate(prep, rows, inv_temp) + (None,)
         f8, a8, tl8, nl8, rpt = self._screen_certificate(prep, rows, inv_temp, stage="f8x1")
+        self._last_open8 = f8 == 0           # what the E4M3 stage alone left unproven (feeds its own mark in noised_stats)
         tiles = (rows + rpt - 1) // rpt
         f1, a1, _, _, _ = self._screen_certificate(prep, rows, inv_temp, row_tiles=tl8, n_row_tiles=tiles, n_row_tiles_dev=nl8)
         be.screen_merge_stage(tl8, nl8, tiles, rpt, f1, a1, f8, a8)
@@ -587,7 +589,8 @@ class PosteriorEngine:
         return out, argmin
 
     def _screened_block_prior(self, prep: dict, rows: int, temp_rows: Tensor, inv_temp: Tensor, aux: Optional[Tensor],
-                              precision: str, screen_rows: tuple, plan_tiles: int = 0, per_temp: int = 1):
+                              precision: str, screen_rows: tuple, plan_tiles: int = 0, per_temp: int = 1,
+                              f8_rows: Optional[tuple] = None):
         """The same pipeline once the certifiable temperature range is known from an earlier call on this dataset: rows
         ``screen_rows`` = [r0, r1) (tile-aligned, the block's low-temperature end) go through the cascade in one go, the rest
         is left to the full pass, and NOTHING is read back -- the list of row tiles with an unproven row and its length stay
@@ -604,12 +607,29 @@ class PosteriorEngine:
         if ph is None:
             import contextlib
             ph = lambda _n: contextlib.nullcontext()      # noqa: E731
-        sub = {k: (v[r0:r1] if isinstance(v, Tensor) else v) for k, v in prep.items()}
+        # ``f8_rows`` = [a, b) inside the span: the rows below the E4M3 stage's own mark.  They go through the whole cascade;
+        # the rest of the span -- temperatures the E4M3 stage is known to leave unproven -- starts at the fp16 stage.
+        a8, b8 = f8_rows if (f8_rows is not None and self._screen_f8_live) else ((r0, r1) if self._screen_f8_live else (r0, r0))
+        nl8 = None
+        f8_fb = None                               # (lowest temperature the E4M3 stage mostly failed, its top temperature, how that fared)
         with ph("screen: cascade"):
-            f, a, _, _, _, nl8 = self._screen_cascade_async(sub, r1 - r0, inv_temp[r0:r1], self._screen_f8_live)
-            flags[r0:r1] = f
-            arg1[r0:r1] = a
+            for (ca, cb), use8 in (((a8, b8), True), ((r0, a8), False), ((b8, r1), False)):
+                if cb <= ca:
+                    continue
+                sub = {k: (v[ca:cb] if isinstance(v, Tensor) else v) for k, v in prep.items()}
+                self._last_open8 = None
+                f, a, _, _, _, n8 = self._screen_cascade_async(sub, cb - ca, inv_temp[ca:cb], use8)
+                flags[ca:cb] = f
+                arg1[ca:cb] = a
+                if use8 and n8 is not None:
+                    nl8 = n8
+                    if self._last_open8 is not None:
+                        fr8, tr8 = self._open_runs(self._last_open8, temp_rows[ca:cb], per_temp)
+                        top8 = tr8.argmax().reshape(1)
+                        f8_fb = (torch.where(fr8 > 0.5, tr8, torch.full_like(tr8, math.inf)).min(),
+                                 tr8.gather(0, top8)[0], fr8.gather(0, top8)[0])
             tile_list, n_listed = be.screen_tile_list(flags, rpt)
+        f = flags[r0:r1]
         with ph("screen: full pass over listed tiles"):
             parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=tiles,
                                          n_row_tiles_dev=n_listed, plan_row_tiles=plan_tiles)
@@ -631,9 +651,11 @@ class PosteriorEngine:
         # the highest screened temperature and how it fared.  (Indexing with the 0-dim result of argmax() would read it
         # back -- torch turns a 0-dim integer tensor index into .item() -- and stall the host once per block: gather.)
         top = t_run.argmax().reshape(1)
+        nan = torch.full((), math.nan, dtype=torch.float64, device=dev)
         feedback = torch.stack([n_listed[0].to(torch.float64), t_open.to(torch.float64), open_rows.sum().to(torch.float64),
                                 (nl8[0] if nl8 is not None else n_listed.new_full((1,), -1)[0]).to(torch.float64),
-                                t_run.gather(0, top)[0].to(torch.float64), frac.gather(0, top)[0].to(torch.float64)])
+                                t_run.gather(0, top)[0].to(torch.float64), frac.gather(0, top)[0].to(torch.float64)]
+                               + ([v.to(torch.float64) for v in f8_fb] if f8_fb is not None else [nan, nan, nan]))
         return out, argmin, feedback
 
     def stats_block(self, src: Tensor, rows: int, temp_rows: Tensor, *, noise: Optional[Tensor] = None,
@@ -790,9 +812,23 @@ class PosteriorEngine:
                                 draw_into(noise[i], qr + (k0 + i) * qw)
                             prep = self._prepare(x0f, nb * b, noise.view(nb * b, -1), t_rows.sqrt(), None, self.precision(), False)
                     key = (n_t, b, k0)
+                    # the E4M3 first stage has a mark of its own (lower: 4 significant bits): rows of the span above it start
+                    # at the fp16 stage instead of paying for an E4M3 pass that is known to leave them unproven
+                    f8_span = None
+                    if self._screen_prior_f8 is not None:
+                        below8 = int((th < self._screen_prior_f8).sum())
+                        if below8 == 0:
+                            f8_span = (span[0], span[0])
+                        elif bool(th[0] <= th[-1]):
+                            f8_span = (span[0], min(span[1], -(-below8 * b // rpt) * rpt))
+                        else:
+                            f8_span = (max(span[0], (nb - below8) * b // rpt * rpt), span[1])
                     o, i, fb = self._screened_block_prior(prep, nb * b, t_rows, (1.0 / t_rows).contiguous(), aux,
-                                                          self.precision(), span, self._screen_hint.get(key, 0), per_temp=b)
-                    pending.append((fb, span[1] - span[0], (span[1] - span[0] + rpt - 1) // rpt, key, nb * b))
+                                                          self.precision(), span, self._screen_hint.get(key, 0), per_temp=b,
+                                                          f8_rows=f8_span)
+                    s8 = f8_span if f8_span is not None else span
+                    pending.append((fb, span[1] - span[0], (span[1] - span[0] + rpt - 1) // rpt, key, nb * b,
+                                    (s8[1] - s8[0] + rpt - 1) // rpt))
                     outs.append(o)
                     idxs.append(i)
                     continue
@@ -841,8 +877,13 @@ class PosteriorEngine:
         if pending:
             vals = torch.stack([p[0] for p in pending]).cpu()
             t_fail, t_top, top_open = math.inf, 0.0, 1.0
-            for (_, rows_s, tiles_s, key, rows_blk), v in zip(pending, vals.tolist()):
+            t_fail8, t_top8, top_open8 = math.inf, 0.0, 1.0
+            for (_, rows_s, tiles_s, key, rows_blk, tiles8), v in zip(pending, vals.tolist()):
                 n_l, t_open, n_open, n8 = int(v[0]), float(v[1]), int(v[2]), int(v[3])
+                if not math.isnan(v[6]):                      # this block ran the E4M3 stage: how its own verdicts fell
+                    t_fail8 = min(t_fail8, float(v[6]))
+                    if v[7] > t_top8:
+                        t_top8, top_open8 = float(v[7]), float(v[8])
                 unscreened_tiles = (rows_blk - rows_s + rpt - 1) // rpt
                 rep["rows_screened"] += rows_s
                 rep["rows_certified"] += rows_s - n_open
@@ -850,7 +891,7 @@ class PosteriorEngine:
                 rep["tiles_screened"] += tiles_s
                 rep["tiles_full_pass"] += max(0, n_l - unscreened_tiles)
                 if n8 >= 0:
-                    rep["f8_tiles_screened"] = rep.get("f8_tiles_screened", 0) + tiles_s
+                    rep["f8_tiles_screened"] = rep.get("f8_tiles_screened", 0) + tiles8
                     rep["f8_tiles_left"] = rep.get("f8_tiles_left", 0) + n8
                 self._screen_hint[key] = n_l + 2              # schedule hint for the same block of the next call
                 t_fail = min(t_fail, t_open)
@@ -862,6 +903,11 @@ class PosteriorEngine:
                 self._screen_prior = t_fail
             elif top_open < 0.2:
                 self._screen_prior = max(self._screen_prior, min(1.25 * t_top, 2.0 * t_max))
+            # the E4M3 stage's mark moves by the same rule on the stage's own verdicts
+            if math.isfinite(t_fail8):
+                self._screen_prior_f8 = t_fail8
+            elif t_top8 > 0.0 and top_open8 < 0.2:
+                self._screen_prior_f8 = max(self._screen_prior_f8 or 0.0, min(1.25 * t_top8, 2.0 * t_max))
         elif self._screen_prior is None and math.isfinite(self._screen_t_fail):
             self._screen_prior = self._screen_t_fail          # first call: the probing found the boundary
         elif self._screen_prior is None and self.screen_report["rows_screened"] > 0 and not math.isfinite(self._screen_t_fail):

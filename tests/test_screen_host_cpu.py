@@ -421,3 +421,41 @@ def test_posterior_mean_mixed_block_contracts_only_the_listed_tiles():
     assert (got.double() - want).abs().max() < 1e-5
     assert torch.equal(got[:8], data[idx[:8]])                     # first tile: every row proven
     assert "tiles:f16x3:1" in be.calls and "weights:1" in be.calls and "gemm2:1" in be.calls
+
+
+def test_e4m3_stage_has_a_remembered_mark_of_its_own():
+    """Remembered-boundary path with the cascade on: the first such call runs the E4M3 stage on the whole certifiable range and
+    learns where the stage alone stops proving rows; later calls start the rows between the two marks at the fp16 stage.  Same
+    results, fewer rows through the E4M3 pass, and the stage's tile accounting follows its own span."""
+    g = syn.gen(312)
+    n, d, b = 400, 256, 32
+    data = _dataset(2, n, d, g)
+    x0 = data[torch.randint(0, n, (b,), generator=g)].clone()
+    temp = torch.logspace(-5, 3, 24)
+    be = SplitFakeBackend()
+    cfg = EngineConfig(precision="f16x3", screen=True, screen_f8=True)
+    cfg.max_query_bytes = 8 * b * d * 12                                   # blocks of eight temperatures
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=be), cfg)
+    noise = torch.randn(len(temp), b, d, generator=syn.gen(311))
+    runs = []
+    for _ in range(4):
+        n0 = len(be.calls)
+        rep0 = dict(eng.screen_report)
+        res = eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+        runs.append((res, be.calls[n0:], eng._screen_prior, eng._screen_prior_f8,
+                     eng.screen_report.get("f8_tiles_screened", 0) - rep0.get("f8_tiles_screened", 0)))
+    (r1, _, p1, f1, _), (r2, c2, p2, f2, t2), (r3, c3, p3, f3, t3), (r4, c4, p4, f4, t4) = runs
+    assert p1 is not None and f1 is None                                   # the probing call knows nothing about the stage
+    assert f2 is not None and 0 < f2 <= p2, (f2, p2)                       # learnt by the first remembered-boundary call
+    assert t3 < t2 and t4 <= t3, (t2, t3, t4)                              # fewer row tiles through the E4M3 pass afterwards
+    assert any(c.startswith("stats:f8x1") for c in c3)
+    plain = PosteriorEngine(EmpiricalDataset(data, backend=SplitFakeBackend()), EngineConfig(precision="f16x3", screen=False))
+    ref = plain.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+    for res in (r2, r3, r4):
+        for k in ("log_l", "mean_e", "var_e", "entropy"):
+            assert torch.isfinite(res[k]).all(), k
+            assert torch.allclose(res[k], ref[k], rtol=1e-4, atol=2e-6), k
+        assert torch.equal(res["argmin"], ref["argmin"])
+    # a descending schedule takes the same path (the E4M3 rows sit at the END of a block)
+    r5 = eng.noised_stats(x0, temp.flip(0), noise_fn=lambda i: noise[len(temp) - 1 - i])
+    assert torch.allclose(r5["entropy"].flip(0), ref["entropy"], rtol=1e-4, atol=2e-6)
