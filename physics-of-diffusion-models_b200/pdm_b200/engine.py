@@ -209,6 +209,9 @@ class EngineConfig:
     screen_f8: bool = True             # screening cascade: an E4M3 pass (twice the MMA rate) first, the fp16 one-product pass
                                        # only on the row tiles it leaves unproven (PDM_SCREEN_F8=0 turns the first stage off)
     screen_g: float = 0.0              # weight cut-off exponent; 0 = 17 + log N (everything dropped sums to < 2^-24)
+    screen_compact: bool = True        # remembered-boundary blocks: the unproven rows of the screened range are gathered into
+                                       # dense row tiles before the full-precision pass (near the boundary a 256-row tile
+                                       # holds proven and unproven rows side by side).  PDM_SCREEN_COMPACT=0 turns it off.
 
     @staticmethod
     def from_env() -> "EngineConfig":
@@ -219,6 +222,8 @@ class EngineConfig:
             cfg.screen = os.environ["PDM_SCREEN"] == "1"
         if os.environ.get("PDM_SCREEN_F8", "") in ("0", "1"):
             cfg.screen_f8 = os.environ["PDM_SCREEN_F8"] == "1"
+        if os.environ.get("PDM_SCREEN_COMPACT", "") in ("0", "1"):
+            cfg.screen_compact = os.environ["PDM_SCREEN_COMPACT"] == "1"
         return cfg
 
 
@@ -628,12 +633,48 @@ class PosteriorEngine:
                         top8 = tr8.argmax().reshape(1)
                         f8_fb = (torch.where(fr8 > 0.5, tr8, torch.full_like(tr8, math.inf)).min(),
                                  tr8.gather(0, top8)[0], fr8.gather(0, top8)[0])
-            tile_list, n_listed = be.screen_tile_list(flags, rpt)
         f = flags[r0:r1]
+        compact = self.cfg.screen_compact and r1 > r0
+        if compact:
+            # Near the boundary a row tile holds proven and unproven rows side by side (C2: 18 k unproven rows spread over
+            # 237 tiles = 61 k rows).  The unproven rows of the span are gathered into dense tiles -- index list, count and
+            # tile count all stay on the device -- and go through the full-precision pass on their own; ``cap`` (from the
+            # count this block had in the previous call) only sizes the buffers: rows beyond it stay on the tile-list path.
+            span = r1 - r0
+            hint_rows = plan_tiles[1] if isinstance(plan_tiles, tuple) else -1
+            cap = min(span, max(2 * rpt, (2 * hint_rows + rpt) if hint_rows >= 0 else span // 4))
+            cap = (cap + rpt - 1) // rpt * rpt
+            open_span = f == 0
+            pos = torch.cumsum(open_span, 0, dtype=torch.int64) - 1           # dense position of every unproven row
+            take = open_span & (pos < cap)
+            idx_c = torch.zeros(cap + 1, dtype=torch.int64, device=dev)       # slot ``cap`` collects everything not taken
+            idx_c.scatter_(0, torch.where(take, pos, torch.full_like(pos, cap)), torch.arange(span, device=dev))
+            idx_c = idx_c[:cap]
+            n_c = (pos[-1] + 1).clamp(max=cap)
+            n_tiles_c = ((n_c + rpt - 1) // rpt).to(torch.int32).reshape(1)
+            # what the tile-list launch still has to cover: the unscreened rows and any unproven row beyond ``cap``
+            flags_u = flags.clone()
+            flags_u[r0:r1] = (~(open_span & ~take)).to(torch.uint8)
+            tile_list, n_listed = be.screen_tile_list(flags_u, rpt)
+        else:
+            tile_list, n_listed = be.screen_tile_list(flags, rpt)
         with ph("screen: full pass over listed tiles"):
+            plan_u = plan_tiles[0] if isinstance(plan_tiles, tuple) else plan_tiles
             parts = self._local_partials(prep, rows, inv_temp, aux, precision, row_tiles=tile_list, n_row_tiles=tiles,
-                                         n_row_tiles_dev=n_listed, plan_row_tiles=plan_tiles)
+                                         n_row_tiles_dev=n_listed, plan_row_tiles=plan_u)
             out, argmin = self._merge(parts, inv_temp)
+            if compact:
+                prep_c = {k: (v[r0:r1].index_select(0, idx_c) if isinstance(v, Tensor) else v) for k, v in prep.items()}
+                inv_temp_c = inv_temp[r0:r1].index_select(0, idx_c)
+                cap_tiles = cap // rpt
+                iota = torch.arange(cap_tiles, dtype=torch.int32, device=dev)
+                parts_c = self._local_partials(prep_c, cap, inv_temp_c, aux, precision, row_tiles=iota, n_row_tiles=cap_tiles,
+                                               n_row_tiles_dev=n_tiles_c,
+                                               plan_row_tiles=max(1, (hint_rows + rpt - 1) // rpt) if hint_rows >= 0 else 0)
+                out_c, arg_c = self._merge(parts_c, inv_temp_c)
+                back = pos.clamp(min=0, max=cap - 1)
+                out[:, r0:r1] = torch.where(take, out_c.index_select(1, back), out[:, r0:r1])
+                argmin[r0:r1] = torch.where(take, arg_c.index_select(0, back), argmin[r0:r1])
         with ph("screen: closed form"):
             y_hi, y_lo = ds.split()
             be.screen_finalize(flags, arg1, ds.d, (prep["hi"], prep["lo"], prep["inv_scale"]), prep["norms"],
@@ -889,11 +930,11 @@ class PosteriorEngine:
                 rep["rows_certified"] += rows_s - n_open
                 rep["rows_unscreened"] += rows_blk - rows_s
                 rep["tiles_screened"] += tiles_s
-                rep["tiles_full_pass"] += max(0, n_l - unscreened_tiles)
+                rep["tiles_full_pass"] += max(0, n_l - unscreened_tiles) + ((n_open + rpt - 1) // rpt if self.cfg.screen_compact else 0)
                 if n8 >= 0:
                     rep["f8_tiles_screened"] = rep.get("f8_tiles_screened", 0) + tiles8
                     rep["f8_tiles_left"] = rep.get("f8_tiles_left", 0) + n8
-                self._screen_hint[key] = n_l + 2              # schedule hint for the same block of the next call
+                self._screen_hint[key] = (n_l + 2, n_open)    # schedule / buffer hints for the same block of the next call
                 t_fail = min(t_fail, t_open)
                 if v[4] > t_top:
                     t_top, top_open = float(v[4]), float(v[5])

@@ -459,3 +459,47 @@ def test_e4m3_stage_has_a_remembered_mark_of_its_own():
     # a descending schedule takes the same path (the E4M3 rows sit at the END of a block)
     r5 = eng.noised_stats(x0, temp.flip(0), noise_fn=lambda i: noise[len(temp) - 1 - i])
     assert torch.allclose(r5["entropy"].flip(0), ref["entropy"], rtol=1e-4, atol=2e-6)
+
+
+def test_unproven_rows_are_compacted_and_an_overflowing_buffer_is_harmless():
+    """Remembered-boundary blocks gather the unproven rows of the screened range into dense row tiles for the full-precision
+    pass (index list, count and tile count on the device).  The buffer is sized from the previous call's count; rows beyond it
+    stay on the tile-list path -- forced here by a hint of zero rows -- and the results do not change."""
+    data, x0 = _setup(n=400, d=96, b=16)
+    for j in (41, 42, 43):                                   # four duplicated training points: the rows of queries 5..8 never certify
+        data[j] = data[j - 35]
+    b, d = x0.shape
+    temp = torch.logspace(-4, 3, 36)
+    noise = torch.randn(len(temp), b, d, generator=syn.gen(321))
+    plain = PosteriorEngine(EmpiricalDataset(data, backend=SplitFakeBackend()), EngineConfig(precision="f16x3", screen=False))
+    ref = plain.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+    results = {}
+    for compact in (True, False):
+        be = SplitFakeBackend()
+        cfg = EngineConfig(precision="f16x3", screen=True, screen_f8=False, screen_compact=compact)
+        eng = PosteriorEngine(EmpiricalDataset(data, backend=be), cfg)
+        eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])                  # probing call
+        eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])                  # first remembered-boundary call
+        rep0 = dict(eng.screen_report)
+        results[compact] = eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+        full = eng.screen_report["tiles_full_pass"] - rep0["tiles_full_pass"]
+        open_rows = (eng.screen_report["rows_screened"] - rep0["rows_screened"]) - (eng.screen_report["rows_certified"] - rep0["rows_certified"])
+        assert open_rows > 0
+        if compact:
+            assert full == -(-open_rows // be.row_tile), (full, open_rows)          # dense tiles
+            assert all(isinstance(v, tuple) and v[1] == open_rows for v in eng._screen_hint.values())
+            eng._screen_hint = {k: (v[0], 0) for k, v in eng._screen_hint.items()}  # next call: a buffer of two row tiles
+            assert open_rows > 2 * be.row_tile
+            results["overflow"] = eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+        else:
+            assert full >= -(-open_rows // be.row_tile)
+    xn = ((noise * temp.sqrt()[:, None, None] + x0[None]) ** 2).sum(-1)
+    for name, res in results.items():
+        for k in ("log_l", "mean_e", "var_e", "entropy"):
+            assert torch.isfinite(res[k]).all(), (name, k)
+            assert torch.allclose(res[k], ref[k], rtol=1e-4, atol=2e-6), (name, k)
+        assert ((res["e_min"] - ref["e_min"]).abs() <= 8 * 2.0 ** -24 * (xn + d)).all(), name     # proven rows: E_min recomputed in fp64
+        assert torch.equal(res["argmin"], ref["argmin"]), name
+    for k in ("log_l", "mean_e", "var_e", "entropy", "e_min"):                     # same arithmetic row by row: identical
+        assert torch.equal(results[True][k], results[False][k]), k
+        assert torch.equal(results["overflow"][k], results[False][k]), k
