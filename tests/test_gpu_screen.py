@@ -279,3 +279,38 @@ def test_one_product_error_bounds_hold_for_every_pair(backend, kind):
     rec = (prep["hi"].double() + prep["lo"].double())[:, :d].cpu()
     from_bytes = q8.view(torch.float8_e4m3fn).double()[:, :d].cpu() * 16
     assert torch.allclose((rec - from_bytes).norm(dim=1), q_err.cpu().double(), rtol=1e-4, atol=1e-12)
+
+
+@pytest.mark.parametrize("compact", [True, False])
+def test_remembered_boundary_calls_match_the_oracle(backend, compact):
+    """Calls two to four on one engine: the certifiable range is remembered, every block runs its cascade and its
+    full-precision pass without a host read-back, the E4M3 stage gets its own mark, and (``compact``) the unproven rows of the
+    screened range are gathered into dense row tiles.  Each call against the oracle on every row, like the first."""
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    n, d, b = 3000, 512, 300                                  # b = 300: row tiles of 256 straddle temperatures
+    g = syn.gen(41)
+    centres = torch.rand(40, d, generator=g) * 2 - 1          # clustered: rows near the boundary are a mix of proven / unproven
+    data = (centres[torch.randint(0, 40, (n,), generator=g)] + 0.25 * torch.randn(n, d, generator=g)).clamp(-1, 1)
+    data[7] = data[3]                                         # a duplicate: query 3 never certifies, at any temperature
+    x0 = data[:b].clone()
+    temp = torch.logspace(-4, 4, 24)
+    noise = torch.randn(len(temp), b, d, generator=syn.gen(42))
+    fn = lambda i: noise[i].to(backend.device)                # noqa: E731
+    cfg = EngineConfig(screen=True, screen_compact=compact)
+    cfg.max_query_bytes = 8 * b * d * 12                      # blocks of eight temperatures
+    eng = PosteriorEngine(EmpiricalDataset(data, backend=backend), cfg)
+    xq = (noise * temp.sqrt()[:, None, None] + x0[None]).reshape(len(temp) * b, d)
+    ref = oracle_rows(xq, data, temp.repeat_interleave(b))
+    outs = []
+    for call in range(4):
+        rep0 = dict(eng.screen_report)
+        o, a = stacked(eng.noised_stats(x0, temp, noise_fn=fn))
+        check_stats(o, a, ref, what=f"call {call} compact={compact}")
+        outs.append((o, a, {k: eng.screen_report.get(k, 0) - rep0.get(k, 0) for k in eng.screen_report}))
+    assert eng._screen_prior is not None and eng._screen_prior_f8 is not None
+    open_rows = outs[3][2]["rows_screened"] - outs[3][2]["rows_certified"]
+    assert open_rows >= len(temp) // 4                        # the duplicate's query at every screened temperature, at least
+    if compact:
+        assert outs[3][2]["tiles_full_pass"] <= -(-open_rows // 256) + 3, outs[3][2]     # dense tiles, rounded up per block
+    assert outs[3][2].get("f8_tiles_screened", 0) <= outs[1][2].get("f8_tiles_screened", 0)
+    assert torch.equal(outs[3][1], outs[0][1])                # arg-min: the same points on every path
