@@ -57,6 +57,13 @@ def main():
             eng = PosteriorEngine(shard, cfg, group=grid.data_group, query_group=grid.query_group)
             st, off = run(eng, seed)
             tag = f"rank {rank} grid {grid.data_shards}x{grid.query_groups} sync={sync} screen={screen}"
+            later = []
+            if screen:                 # calls two and three: the remembered-boundary path (no probing, dense tiles, E4M3 mark)
+                for call in (2, 3):
+                    later.append((call,) + run(eng, seed))
+                if eng._screen_prior is None:
+                    ok = False
+                    print(f"{tag}: no remembered boundary after three calls")
             if screen:
                 rep = eng.screen_report
                 if rank == 0:
@@ -87,6 +94,23 @@ def main():
             if not (sync and rank != 0) and off != off_ref:
                 ok = False
                 print(f"{tag}: generator offset {off} != {off_ref}")
+            for call, st_l, off_l in later:
+                for k in ("log_l", "mean_e", "entropy"):
+                    err = (st_l[k].double() - ref[k].double()).abs()
+                    tol = torch.maximum(2e-5 * ref[k].double().abs() + 2e-6, 0.25 * floor)
+                    if (err > tol).any():
+                        ok = False
+                        print(f"{tag} call {call}: {k} mismatch, worst {err.max().item():.3e}")
+                if not torch.equal(st_l["argmin"], ref["argmin"]):
+                    ok = False
+                    print(f"{tag} call {call}: argmin mismatch")
+                err = (st_l["e_min"].double() - ref["e_min"].double()).abs()
+                if (err > floor * temps.double()[:, None]).any():
+                    ok = False
+                    print(f"{tag} call {call}: e_min off by {err.max().item():.3e}")
+                if not (sync and rank != 0) and off_l != off_ref:
+                    ok = False
+                    print(f"{tag} call {call}: generator offset {off_l} != {off_ref}")
             # per-point aux vector over the WHOLE dataset (the k-NN regulariser): every shard must use its own rows
             if not screen:
                 aux = torch.rand(n, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) + 0.1
