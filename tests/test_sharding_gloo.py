@@ -134,3 +134,79 @@ def test_grid_equals_unsharded(tmp_path, world, data_shards, capsys):
     xt = orc.draw_noised_queries(x0, temp)
     ref = orc.metric_batch(xt, data, temp, regularize=True, sigma_reg_sq_per_point=orc.knn_sigma_reg_sq(data, 5, 1.0))
     torch.testing.assert_close(r0["metric_knn"], ref, rtol=2e-3, atol=1e-5)
+
+
+def _screen_inputs():
+    g = torch.Generator().manual_seed(7)
+    n, d, b = 240, 64, 16
+    data = torch.rand(n, d, generator=g) * 2 - 1
+    data[37] = data[5]                                      # a duplicate: the rows of query 5 never certify
+    x0 = data[:b].clone()
+    temp = torch.logspace(-4, 3, 15)
+    noise = torch.randn(len(temp), b, d, generator=g)
+    return data, x0, temp, noise
+
+
+def _screen_worker(rank, world, data_shards, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "physics-of-diffusion-models_b200"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from test_screen_host_cpu import SplitFakeBackend
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    from pdm_b200.sharding import make_grid
+    data, x0, temp, noise = _screen_inputs()
+    grid = make_grid(data_shards)
+    lo, hi = grid.rows(len(data))
+    be = SplitFakeBackend()
+    ds = EmpiricalDataset(data[lo:hi], backend=be, index_offset=lo, n_total=len(data), global_absmax=float(data.abs().max()))
+    cfg = EngineConfig(precision="f16x3", screen=True, screen_f8=True)
+    cfg.sync_noise = False
+    cfg.max_query_bytes = 4 * x0.shape[0] * data.shape[1] * 12            # blocks of four temperatures
+    eng = PosteriorEngine(ds, cfg, group=grid.data_group, query_group=grid.query_group)
+    res = {}
+    for call in range(4):                 # probing call, then three on the remembered-boundary path (E4M3 mark, dense tiles)
+        st = eng.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+        res[f"call{call}"] = {k: st[k] for k in ("entropy", "log_l", "mean_e", "var_e", "e_min", "argmin", "l")}
+    res["prior"] = torch.tensor([eng._screen_prior if eng._screen_prior is not None else -1.0,
+                                 eng._screen_prior_f8 if eng._screen_prior_f8 is not None else -1.0])
+    res["report"] = dict(eng.screen_report)
+    res["calls"] = list(be.calls)
+    torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,data_shards", [(2, 2), (2, 1), (4, 2)])
+def test_screened_grid_repeated_calls_equal_unsharded(tmp_path, world, data_shards):
+    """Certified delta posteriors over the grid, calls one to four on one engine: every rank of a dataset group holds the same
+    certificate (merged screening records), so the remembered boundary, the E4M3 stage's mark, the dense tiles of unproven rows
+    and their buffer hints agree without any extra exchange; the results equal the unsharded, unscreened engine's."""
+    mp.spawn(_screen_worker, args=(world, data_shards, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ranks = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    sys.path.insert(0, HERE)
+    from test_screen_host_cpu import SplitFakeBackend
+    from pdm_b200 import EmpiricalDataset, PosteriorEngine, EngineConfig
+    data, x0, temp, noise = _screen_inputs()
+    plain = PosteriorEngine(EmpiricalDataset(data, backend=SplitFakeBackend()), EngineConfig(precision="f16x3", screen=False))
+    ref = plain.noised_stats(x0, temp, noise_fn=lambda i: noise[i])
+    xn = ((noise * temp.sqrt()[:, None, None] + x0[None]) ** 2).sum(-1)
+    for r in ranks:
+        assert r["prior"][0] > 0, r["prior"]                              # a boundary was found and remembered
+        assert r["report"]["rows_certified"] > 0
+        assert any(c.startswith("tiles:f16x3:") for c in r["calls"])      # device-side list lengths: the sync-free path ran
+        for call in range(4):
+            st = r[f"call{call}"]
+            for k in ("entropy", "log_l", "mean_e", "var_e"):
+                assert torch.isfinite(st[k]).all(), (call, k)
+                assert torch.allclose(st[k], ref[k], rtol=1e-4, atol=2e-6), (call, k, (st[k] - ref[k]).abs().max())
+            assert torch.equal(st["argmin"], ref["argmin"]), call
+            assert ((st["e_min"] - ref["e_min"]).abs() <= 8 * 2.0 ** -24 * (xn + data.shape[1])).all(), call
+            assert (st["l"][:4, 5] >= 1.9).all()                           # the duplicate's query is never a certified delta
+    for r in ranks[1:]:                                                   # every rank ends with the same numbers
+        for call in range(4):
+            for k in ("entropy", "argmin", "e_min"):
+                assert torch.equal(ranks[0][f"call{call}"][k], r[f"call{call}"][k]), (call, k)
