@@ -1,6 +1,8 @@
 """Host logic of the engine and of the reference-facing drop-in modules, on the CPU with the test double of the
 backend (tests/fake_backend.py): schedule blocking, RNG order, dataset caching, record merge, posterior mean."""
 
+import os
+
 import pytest
 import torch
 from torch.utils.data import DataLoader, TensorDataset
@@ -331,3 +333,34 @@ def test_thermo_stats_legacy_schema(fake):
     torch.testing.assert_close(th["var_H"] / g["temp"] ** 2, th["heat_capacity"], rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(th["free_energy"], -g["temp"] * th["log_Z"] + (th["full_U"] - th["U"]), rtol=1e-4, atol=1e-4)
     assert (th["var_H"] >= 0).all() and (th["full_U"] >= th["U"] - 1e-6).all()
+
+
+@pytest.mark.parametrize("parametrization", ["x0", "eps", "score"])
+def test_predictions_algebra(parametrization):
+    """DDPMPredictions: the three views of one prediction are mutually consistent (xt = sqrt(ab) x0 + sqrt(1-ab) eps,
+    score = -eps/sqrt(1-ab)), evaluated on demand, differentiable -- and, where the reference checkout is present, equal to the
+    reference's class bit for bit (diffusion/ddpm/ddpm.py:12-30; loaded from its file, no package import needed)."""
+    from diffusion import DDPMPredictions
+    g = torch.Generator().manual_seed(3)
+    xt = torch.randn(5, 3, 4, 4, generator=g)
+    pred = torch.randn(5, 3, 4, 4, generator=g, requires_grad=True)
+    ab = torch.rand(5, 1, 1, 1, generator=g) * 0.98 + 0.01
+    p = DDPMPredictions(pred, xt, ab, parametrization)
+    assert p.pred is pred and getattr(p, parametrization) is pred and p.parametrization == parametrization
+    assert len(p._cache) == 1                                              # nothing computed until asked for
+    torch.testing.assert_close(ab.sqrt() * p.x0 + (1 - ab).sqrt() * p.eps, xt, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(p.score, -p.eps / (1 - ab).sqrt(), rtol=1e-6, atol=1e-6)
+    assert p.x0 is p.x0                                                    # cached
+    (p.x0.sum() + p.score.sum()).backward()
+    assert pred.grad is not None and torch.isfinite(pred.grad).all()
+    with pytest.raises(ValueError):
+        DDPMPredictions(pred, xt, ab, "v")
+    ref_file = "/root/reference/diffusion/ddpm/ddpm.py"
+    if os.path.exists(ref_file):
+        src = open(ref_file).read()
+        body = src[src.index("class DDPMPredictions"):src.index("class DDPM(")]
+        ns = {"Tensor": torch.Tensor}
+        exec(body, ns)                                                     # the reference's class, verbatim, stand-alone
+        r = ns["DDPMPredictions"](pred.detach(), xt, ab, parametrization)
+        for k in ("x0", "eps", "score"):
+            assert torch.equal(getattr(p, k).detach(), getattr(r, k)), k
