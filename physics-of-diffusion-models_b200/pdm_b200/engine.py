@@ -597,10 +597,13 @@ class PosteriorEngine:
                               precision: str, screen_rows: tuple, plan_tiles: int = 0, per_temp: int = 1,
                               f8_rows: Optional[tuple] = None):
         """The same pipeline once the certifiable temperature range is known from an earlier call on this dataset: rows
-        ``screen_rows`` = [r0, r1) (tile-aligned, the block's low-temperature end) go through the cascade in one go, the rest
-        is left to the full pass, and NOTHING is read back -- the list of row tiles with an unproven row and its length stay
-        on the device (pdm_stats_args.n_row_tiles_dev).  Returns (out, argmin, feedback) with feedback = device scalars
-        (listed tiles, lowest unproven temperature, unproven rows) that the caller reads once at the end of the call."""
+        ``screen_rows`` = [r0, r1) (tile-aligned, the block's low-temperature end) go through the cascade in one go -- those
+        of ``f8_rows`` from the E4M3 stage on, the others from the fp16 stage -- the rest is left to the full pass, and NOTHING
+        is read back: tile lists, the index list of the unproven rows and all their lengths stay on the device
+        (pdm_stats_args.n_row_tiles_dev).  ``plan_tiles`` = (listed tiles, unproven rows) of the same block in the previous
+        call: schedule and buffer-size hints only.  Returns (out, argmin, feedback) with feedback = device scalars (listed
+        tiles, lowest mostly-unproven temperature, unproven rows, tiles the E4M3 stage left, the top screened temperature and
+        how it fared, the same three numbers for the E4M3 stage alone) that the caller reads once at the end of the call."""
         be, ds = self.backend, self.ds
         dev = be.device
         rpt = getattr(be, "row_tile", None) or 128 * (self.cfg.cta_group or 2)
